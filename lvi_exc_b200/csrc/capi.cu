@@ -1,0 +1,96 @@
+// capi.cu — context management and misc entry points of the C-ABI (include/lvi_exc_b200.h).
+#include <nccl.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace lvi {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace lvi
+
+using namespace lvi;
+
+extern "C" {
+
+const char* lvi_last_error(void) { return g_error.c_str(); }
+int lvi_abi_version(void) { return LVI_ABI_VERSION; }
+int lvi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static void ctx_init(lvi_ctx* c, int device) {
+  LVI_REQUIRE(lvi_device_count() > 0, LVI_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  LVI_REQUIRE(device >= 0 && device < lvi_device_count(), LVI_ERR_INVALID, "bad device ordinal");
+  LVI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LVI_CUDA(cudaGetDeviceProperties(&prop, device));
+  LVI_REQUIRE(prop.major >= 10, LVI_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + ", library is built for sm_100a only");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  LVI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+}
+
+int lvi_ctx_create(int device, void* nccl_comm, int rank, int world, lvi_ctx** out) {
+  return guarded([&] {
+    LVI_REQUIRE(out, LVI_ERR_INVALID, "lvi_ctx_create: null out");
+    LVI_REQUIRE(world >= 1 && rank >= 0 && rank < world, LVI_ERR_INVALID, "lvi_ctx_create: bad rank/world");
+    LVI_REQUIRE(world == 1 || nccl_comm, LVI_ERR_INVALID, "lvi_ctx_create: world > 1 needs an NCCL communicator");
+    auto c = new lvi_ctx();
+    try { ctx_init(c, device); } catch (...) { delete c; throw; }
+    c->nccl = nccl_comm; c->rank = rank; c->world = world;
+    *out = c;
+  });
+}
+
+int lvi_nccl_unique_id(void* id128) {
+  return guarded([&] {
+    LVI_REQUIRE(id128, LVI_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    LVI_REQUIRE(ncclGetUniqueId(&id) == ncclSuccess, LVI_ERR_NCCL, "ncclGetUniqueId failed");
+    std::memcpy(id128, &id, 128);
+  });
+}
+
+int lvi_ctx_create_nccl(int device, const void* id128, int rank, int world, lvi_ctx** out) {
+  return guarded([&] {
+    LVI_REQUIRE(out && id128, LVI_ERR_INVALID, "lvi_ctx_create_nccl: null argument");
+    LVI_REQUIRE(world >= 1 && rank >= 0 && rank < world, LVI_ERR_INVALID, "lvi_ctx_create_nccl: bad rank/world");
+    auto c = new lvi_ctx();
+    try {
+      ctx_init(c, device);
+      ncclUniqueId id;
+      std::memcpy(&id, id128, 128);
+      ncclComm_t comm;
+      ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
+      LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+      c->nccl = comm; c->owns_nccl = true; c->rank = rank; c->world = world;
+    } catch (...) { delete c; throw; }
+    *out = c;
+  });
+}
+
+int lvi_ctx_destroy(lvi_ctx* ctx) {
+  if (!ctx) return LVI_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->owns_nccl && ctx->nccl) ncclCommDestroy(static_cast<ncclComm_t>(ctx->nccl));
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LVI_OK;
+}
+
+int lvi_ctx_synchronize(lvi_ctx* ctx) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx, LVI_ERR_INVALID, "null ctx");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+void* lvi_ctx_stream(lvi_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+int64_t lvi_ctx_launch_count(lvi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// common.cuh — shared plumbing of the CUDA library (context, error handling, device buffers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lvi_exc_b200.h"
+
+namespace lvi {
+
+void set_error(const std::string& msg);
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define LVI_CUDA(call)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      throw ::lvi::Error(LVI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define LVI_REQUIRE(cond, code, msg)                 \
+  do {                                               \
+    if (!(cond)) throw ::lvi::Error((code), (msg));  \
+  } while (0)
+
+// catch-all wrapper for extern "C" entry points
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return LVI_OK;
+  } catch (const Error& e) {
+    set_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return LVI_ERR_INVALID;
+  }
+}
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+}  // namespace lvi
+
+struct lvi_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  void* nccl = nullptr;  // ncclComm_t
+  bool owns_nccl = false;
+  int rank = 0, world = 1;
+  int64_t launches = 0;
+  int sm_count = lvi::kNumSMs;
+};
+
+namespace lvi {
+
+// RAII device buffer on a context's stream-ordered pool
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  explicit DBuf(size_t count) { alloc(count); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) LVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void zero(cudaStream_t s) { if (n) LVI_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t count, cudaStream_t s) { if (count) LVI_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
+  void download(T* h, size_t count, cudaStream_t s) const { if (count) LVI_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+};
+
+inline int grid_for(int64_t work_items, int block, int sm_count, int blocks_per_sm = 8) {
+  int64_t g = (work_items + block - 1) / block;
+  const int64_t cap = static_cast<int64_t>(sm_count) * blocks_per_sm;  // grid sized in multiples of the SM count
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+#define LVI_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+  do {                                                                       \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+    ++(ctx)->launches;                                                       \
+    LVI_CUDA(cudaGetLastError());                                            \
+  } while (0)
+
+}  // namespace lvi
