@@ -1,0 +1,308 @@
+// lowering.hpp — host-side lowering of an `lvi_problem_desc` (what the Kontiki-shaped facade records) into the
+// flat tables the kernels consume.  Replaces the per-residual pointer bookkeeping of
+//   TrajectoryEstimator::AddTrajectoryForTimes / CheckTimeSpans   K/trajectory_estimator.h:76-130
+//   SplineEntity::AddToProblem                                    K/trajectories/spline_base.h:380-426
+//   SensorEntity / ImuEntity / ConstantBiasImuEntity::AddToProblem K/sensors/{sensors.h:137-167, imu.h:129-142,
+//                                                                  constant_bias_imu.h:100-119}
+// by index tables: per evaluation the first knot i0 and the interpolation amount u (times are constants because
+// the time offsets are locked, cfg optimize_time_offset=false), and per parameter block its position in the linear
+// system.  Ordering: trajectory knots in time order [r3_i, so3_i] with each landmark's inverse depth placed right
+// after the last knot of its reference window (band part), then the "arrow" border: knots touched by the map-time
+// evaluation of every surfel residual + the sensor blocks (SURVEY §5 "long-context").  Pure host C++ (no CUDA).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lvi_exc_b200.h"
+#include "residuals.cuh"
+
+namespace lvi {
+
+struct RangeError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct LoweredTable {
+  int n = 0, active = 1;
+  std::vector<int> i0a, i0b, ia, ib;
+  std::vector<double> ua, ub, v, weight, huber;
+};
+
+struct Lowered {
+  int n_knots = 0, n_landmarks = 0, n_planes = 0, has_r3 = 1;
+  double t0 = 0, dt = 1;
+  LoweredTable tab[RT_COUNT];
+  std::vector<int> pos_r3, pos_so3, pos_rho;
+  int pos_sens[TB_COUNT];
+  int nb = 0, nbo = 0, bw = 0;   // band dims, border dims, half bandwidth
+  int n_res = 0, n_res_blocks = 0;
+  int res_offset[RT_COUNT + 1];  // row offsets of each table in the residual vector
+  bool constrained = false;      // a free block has bounds (rho >= 0) -> projected steps + Armijo check
+  int nt() const { return nb + nbo; }
+};
+
+
+inline void time_to_index(const lvi_problem_desc& d, double t, int& i0, double& u) {
+  const double s = (t - d.t0) / d.dt;   // SplineSegmentView::CalculateIndexAndInterpolationAmount, spline_base.h:153-157
+  i0 = static_cast<int>(std::floor(s));
+  u = s - i0;
+}
+// Segment bookkeeping of SplineEntity::AddToProblem (spline_base.h:380-426) and the lookup of SplineView::Evaluate
+// (spline_base.h:194-222) INCLUDING its retry at t - 1e-5 when t sits on a segment boundary (Q6): with timestamps
+// commensurate with the knot grid the reference really evaluates 10 us early, and so do we.
+struct SegList {
+  double t0[2]; int n[2]; int first[2]; int count = 0;
+};
+inline SegList build_segments(const lvi_problem_desc& d, const double (*spans)[2], int nspans) {
+  SegList S;
+  int cur_start = 0, cur_end = -1;
+  for (int k = 0; k < nspans; ++k) {
+    int i1 = static_cast<int>(std::floor((spans[k][0] - d.t0) / d.dt));
+    const int i2 = static_cast<int>(std::floor((spans[k][1] - d.t0) / d.dt));
+    if (i1 > cur_end) { S.t0[S.count] = d.t0 + d.dt * i1; S.n[S.count] = 0; S.first[S.count] = i1; ++S.count; cur_start = i1; }
+    else i1 = cur_end + 1;
+    for (int i = i1; i < i2 + 4; ++i) S.n[S.count - 1] += 1;
+    cur_end = cur_start + S.n[S.count - 1] - 1;
+  }
+  return S;
+}
+inline void locate(const lvi_problem_desc& d, const SegList& S, double t, int& i0, double& u) {
+  for (int k = 0; k < S.count; ++k) {
+    const double mn = S.t0[k], mx = S.t0[k] + (S.n[k] - 3) * d.dt;
+    double te = t;
+    bool ok = (t >= mn) && (t < mx);
+    if (!ok) { te = t - 0.00001; ok = (te >= mn) && (te < mx); }
+    if (!ok) continue;
+    const double s = (te - S.t0[k]) / d.dt;
+    const int il = static_cast<int>(std::floor(s));
+    if (S.n[k] < 4 || il < 0 || il > S.n[k] - 4) throw RangeError("t is out of range for spline segment");
+    i0 = S.first[k] + il;
+    u = s - il;
+    if (i0 < 0 || i0 > d.n_knots - 4) throw RangeError("t is out of range for spline");
+    return;
+  }
+  throw RangeError("No segment found for time t");
+}
+inline void locate1(const lvi_problem_desc& d, double t_span, double t_eval, int& i0, double& u) {
+  const double sp[1][2] = {{t_span, t_span}};
+  locate(d, build_segments(d, sp, 1), t_eval, i0, u);
+}
+inline void locate2(const lvi_problem_desc& d, double ta, double tb, double ea, double eb, int& i0a, double& ua, int& i0b, double& ub) {
+  const double sp[2][2] = {{ta, ta}, {tb, tb}};
+  const SegList S = build_segments(d, sp, 2);
+  locate(d, S, ea, i0a, ua);
+  locate(d, S, eb, i0b, ub);
+}
+
+inline void check_span(const lvi_problem_desc& d, double t1, double t2) {  // CheckTimeSpans
+  const double mn = d.t0, mx = d.t0 + (d.n_knots - 3) * d.dt;
+  if (t1 < mn || t2 >= mx) throw RangeError("Time span out of range for trajectory");
+  if (t1 > t2) throw RangeError("At least one time span begins before it ends");
+}
+
+inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
+  if (d.n_knots < 4) throw RangeError("Spline had too few control points");
+  if (!d.so3_knots) throw std::invalid_argument("so3_knots is null");
+  L.n_knots = d.n_knots; L.n_landmarks = d.n_landmarks; L.n_planes = d.n_planes; L.t0 = d.t0; L.dt = d.dt;
+  L.has_r3 = d.r3_knots != nullptr;
+  const int n = d.n_knots;
+  const bool r3_free = L.has_r3 && !d.lock_r3, so3_free = !d.lock_so3;
+  const bool traj_free = r3_free || so3_free;
+  std::vector<char> knot_used(n, 0);
+  std::vector<char> rho_used(std::max(d.n_landmarks, 1), 0);
+  bool sens_used[TB_COUNT] = {false, false, false, false, false, false, false};
+  auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) knot_used[k] = 1; };
+  auto use_span = [&](double ta, double tb) { int ia, ib; double u; time_to_index(d, ta, ia, u); time_to_index(d, tb, ib, u); for (int k = ia; k < ib + 4 && k < n; ++k) if (k >= 0) knot_used[k] = 1; };
+  auto need = [&](const void* p, int cnt, const char* what) { if (cnt > 0 && !p) throw std::invalid_argument(std::string("null table pointer: ") + what); };
+  // ---- gyro / accel / orient: single evaluation
+  {
+    LoweredTable& T = L.tab[RT_GYRO];
+    need(d.gyro_t, d.n_gyro, "gyro_t"); need(d.gyro_w, d.n_gyro, "gyro_w"); need(d.gyro_weight, d.n_gyro, "gyro_weight");
+    T.n = d.n_gyro; T.active = 1;  // gravity blocks are never constant (imu.h:129-142, Q5)
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.v.assign(d.gyro_w, d.gyro_w + 3 * static_cast<size_t>(T.n)); T.weight.assign(d.gyro_weight, d.gyro_weight + T.n);
+    for (int i = 0; i < T.n; ++i) {
+      const double t = d.gyro_t[i] + d.imu_toff;
+      check_span(d, d.gyro_t[i], d.gyro_t[i]);
+      locate1(d, d.gyro_t[i], t, T.i0a[i], T.ua[i]);
+      use_window(T.i0a[i]);
+    }
+    if (T.n) { sens_used[TB_G] = sens_used[TB_BA] = sens_used[TB_BG] = true; }
+  }
+  {
+    LoweredTable& T = L.tab[RT_ACCEL];
+    need(d.accel_t, d.n_accel, "accel_t"); need(d.accel_a, d.n_accel, "accel_a"); need(d.accel_weight, d.n_accel, "accel_weight");
+    T.n = d.n_accel; T.active = 1;
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.v.assign(d.accel_a, d.accel_a + 3 * static_cast<size_t>(T.n)); T.weight.assign(d.accel_weight, d.accel_weight + T.n);
+    for (int i = 0; i < T.n; ++i) {
+      check_span(d, d.accel_t[i], d.accel_t[i]);
+      locate1(d, d.accel_t[i], d.accel_t[i] + d.imu_toff, T.i0a[i], T.ua[i]);
+      use_window(T.i0a[i]);
+    }
+    if (T.n) { sens_used[TB_G] = sens_used[TB_BA] = sens_used[TB_BG] = true; }
+  }
+  {
+    LoweredTable& T = L.tab[RT_ORIENT];
+    need(d.orient_t, d.n_orient, "orient_t"); need(d.orient_q, d.n_orient, "orient_q");
+    T.n = d.n_orient; T.active = so3_free;
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.v.assign(d.orient_q, d.orient_q + 4 * static_cast<size_t>(T.n)); T.weight.assign(d.orient_weight, d.orient_weight + T.n);
+    for (int i = 0; i < T.n; ++i) {
+      check_span(d, d.orient_t[i], d.orient_t[i]);
+      locate1(d, d.orient_t[i], d.orient_t[i], T.i0a[i], T.ua[i]);
+      if (T.active) use_window(T.i0a[i]);
+    }
+  }
+  // ---- surfel (map time first: spans must be ordered, Q12)
+  std::set<int> border_knots;
+  {
+    LoweredTable& T = L.tab[RT_SURFEL];
+    need(d.surfel_t, d.n_surfel, "surfel_t"); need(d.surfel_point, d.n_surfel, "surfel_point"); need(d.surfel_plane, d.n_surfel, "surfel_plane");
+    if (d.n_surfel && !L.has_r3) throw std::invalid_argument("surfel residuals need the R3 spline");
+    T.n = d.n_surfel; T.active = traj_free || !d.lock_lidar_q || !d.lock_lidar_p;
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n);
+    T.v.assign(d.surfel_point, d.surfel_point + 3 * static_cast<size_t>(T.n)); T.ia.assign(d.surfel_plane, d.surfel_plane + T.n);
+    T.weight.assign(d.surfel_weight, d.surfel_weight + T.n); T.huber.assign(d.surfel_huber, d.surfel_huber + T.n);
+    for (int i = 0; i < T.n; ++i) {
+      check_span(d, d.surfel_tmap[i], d.surfel_tmap[i]); check_span(d, d.surfel_t[i], d.surfel_t[i]);
+      if (d.surfel_t[i] < d.surfel_tmap[i]) throw RangeError("Time spans are not ordered");
+      if (T.ia[i] < 0 || T.ia[i] >= d.n_planes) throw std::invalid_argument("surfel plane id out of range");
+      locate2(d, d.surfel_tmap[i], d.surfel_t[i], d.surfel_tmap[i] + d.lidar_toff, d.surfel_t[i] + d.lidar_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
+      if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) border_knots.insert(T.i0a[i] + k); }
+    }
+    if (T.n && T.active) sens_used[TB_LQ] = sens_used[TB_LP] = true;
+  }
+  // ---- camera
+  std::vector<int> rho_anchor(std::max(d.n_landmarks, 1), -1);
+  {
+    LoweredTable& T = L.tab[RT_CAM];
+    need(d.cam_t0_ref, d.n_cam, "cam_t0_ref"); need(d.cam_uv_ref, d.n_cam, "cam_uv_ref"); need(d.cam_landmark, d.n_cam, "cam_landmark");
+    if (d.n_cam && !L.has_r3) throw std::invalid_argument("camera residuals need the R3 spline");
+    T.n = d.n_cam;
+    T.active = traj_free || !d.lock_cam_q || !d.lock_cam_p || d.rho_locked == nullptr;
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n); T.v.resize(4 * static_cast<size_t>(T.n));
+    T.ia.assign(d.cam_landmark, d.cam_landmark + T.n);
+    T.weight.assign(d.cam_weight, d.cam_weight + T.n); T.huber.assign(d.cam_huber, d.cam_huber + T.n);
+    const double row_delta = d.readout / static_cast<double>(d.cam_rows);
+    const double margin = 1e-3;
+    for (int i = 0; i < T.n; ++i) {
+      double t1 = d.cam_t0_ref[i], t2 = d.cam_t0_obs[i];
+      if (!(t1 <= t2)) std::swap(t1, t2);
+      check_span(d, t1 - margin, t1 + d.readout + margin); check_span(d, t2 - margin, t2 + d.readout + margin);
+      if (T.ia[i] < 0 || T.ia[i] >= d.n_landmarks) throw std::invalid_argument("camera landmark id out of range");
+      T.v[4 * i] = d.cam_uv_ref[2 * i]; T.v[4 * i + 1] = d.cam_uv_ref[2 * i + 1]; T.v[4 * i + 2] = d.cam_uv_obs[2 * i]; T.v[4 * i + 3] = d.cam_uv_obs[2 * i + 1];
+      {
+        const double sp[2][2] = {{t1 - margin, t1 + d.readout + margin}, {t2 - margin, t2 + d.readout + margin}};
+        const SegList S = build_segments(d, sp, 2);
+        locate(d, S, d.cam_t0_ref[i] + d.cam_toff + d.cam_uv_ref[2 * i + 1] * row_delta, T.i0a[i], T.ua[i]);
+        locate(d, S, d.cam_t0_obs[i] + d.cam_toff + d.cam_uv_obs[2 * i + 1] * row_delta, T.i0b[i], T.ub[i]);
+      }
+      if (T.active) {
+        use_span(t1 - margin, t1 + d.readout + margin); use_span(t2 - margin, t2 + d.readout + margin);
+        rho_used[T.ia[i]] = 1;
+        rho_anchor[T.ia[i]] = std::max(rho_anchor[T.ia[i]], T.i0a[i] + 3);
+      }
+    }
+    if (T.n && T.active) sens_used[TB_CQ] = sens_used[TB_CP] = true;
+  }
+  {
+    LoweredTable& T = L.tab[RT_CAMSURF];
+    need(d.cs_t, d.n_camsurf, "cs_t"); need(d.cs_uv, d.n_camsurf, "cs_uv"); need(d.cs_landmark, d.n_camsurf, "cs_landmark"); need(d.cs_plane, d.n_camsurf, "cs_plane");
+    if (d.n_camsurf && !L.has_r3) throw std::invalid_argument("camera-surfel residuals need the R3 spline");
+    T.n = d.n_camsurf;
+    T.active = 1;  // the rho block is added (and read as a constant, Q4); with the camera unlocked in every caller the block set is never all-constant
+    T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n);
+    T.v.assign(d.cs_uv, d.cs_uv + 2 * static_cast<size_t>(T.n)); T.ia.assign(d.cs_plane, d.cs_plane + T.n); T.ib.assign(d.cs_landmark, d.cs_landmark + T.n);
+    T.weight.assign(d.cs_weight, d.cs_weight + T.n); T.huber.assign(d.cs_huber, d.cs_huber + T.n);
+    for (int i = 0; i < T.n; ++i) {
+      check_span(d, d.cs_tmap[i], d.cs_tmap[i]); check_span(d, d.cs_t[i], d.cs_t[i]);
+      if (d.cs_t[i] < d.cs_tmap[i]) throw RangeError("Time spans are not ordered");
+      if (T.ia[i] < 0 || T.ia[i] >= d.n_planes || T.ib[i] < 0 || T.ib[i] >= d.n_landmarks) throw std::invalid_argument("camera-surfel id out of range");
+      locate2(d, d.cs_tmap[i], d.cs_t[i], d.cs_tmap[i] + d.cam_toff, d.cs_t[i] + d.cam_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
+      use_window(T.i0a[i]); use_window(T.i0b[i]);
+      for (int k = 0; k < 4; ++k) border_knots.insert(T.i0a[i] + k);
+      rho_used[T.ib[i]] = 1;
+      rho_anchor[T.ib[i]] = std::max(rho_anchor[T.ib[i]], T.i0b[i] + 3);
+    }
+    if (T.n) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
+  }
+  if (border_knots.size() > 16) border_knots.clear();  // not an arrow structure: leave those knots in the band
+  // ---- positions
+  L.pos_r3.assign(n, -1); L.pos_so3.assign(n, -1); L.pos_rho.assign(std::max(d.n_landmarks, 1), -1);
+  std::vector<std::vector<int>> rho_at(n);
+  for (int l = 0; l < d.n_landmarks; ++l) {
+    const bool locked = d.rho_locked && d.rho_locked[l];
+    if (rho_used[l] && !locked) { rho_at[std::min(std::max(rho_anchor[l], 0), n - 1)].push_back(l); L.constrained = true; }
+  }
+  int pb = 0;
+  for (int i = 0; i < n; ++i) {
+    if (knot_used[i] && !border_knots.count(i)) {
+      if (r3_free) { L.pos_r3[i] = pb; pb += 3; }
+      if (so3_free) { L.pos_so3[i] = pb; pb += 3; }
+    }
+    for (int l : rho_at[i]) L.pos_rho[l] = pb++;
+  }
+  L.nb = pb;
+  for (int i : border_knots) {
+    if (!knot_used[i]) continue;
+    if (r3_free) { L.pos_r3[i] = pb; pb += 3; }
+    if (so3_free) { L.pos_so3[i] = pb; pb += 3; }
+  }
+  const bool sens_free[TB_COUNT] = {!d.lock_lidar_q, !d.lock_lidar_p, !d.lock_cam_q, !d.lock_cam_p, true, !d.lock_acc_bias, !d.lock_gyr_bias};
+  const int sens_dim[TB_COUNT] = {3, 3, 3, 3, 2, 3, 3};
+  for (int b = 0; b < TB_COUNT; ++b) {
+    L.pos_sens[b] = -1;
+    if (sens_used[b] && sens_free[b]) { L.pos_sens[b] = pb; pb += sens_dim[b]; }
+  }
+  L.nbo = pb - L.nb;
+  // ---- residual vector layout + bandwidth
+  int ro = 0, nblk = 0;
+  for (int t = 0; t < RT_COUNT; ++t) { L.res_offset[t] = ro; ro += L.tab[t].n * rt_rows(t); nblk += L.tab[t].n; }
+  L.res_offset[RT_COUNT] = ro; L.n_res = ro; L.n_res_blocks = nblk;
+  L.bw = 0;  // filled by compute_bandwidth()
+}
+
+
+// host ProblemView over the lowered tables (parameters are read straight from the desc)
+inline ProblemView host_view(const lvi_problem_desc& d, const Lowered& L, const double* sens /*SENS_N*/) {
+  ProblemView P{};
+  P.dt_inv = 1.0 / d.dt; P.n_knots = d.n_knots; P.r3 = d.r3_knots; P.so3 = d.so3_knots; P.sens = sens; P.rho = d.rho; P.planes = d.planes;
+  P.fx = d.fx; P.fy = d.fy; P.cx = d.cx; P.cy = d.cy; P.has_r3 = L.has_r3;
+  for (int t = 0; t < RT_COUNT; ++t) {
+    const LoweredTable& T = L.tab[t];
+    ResTable& R = P.tab[t];
+    R.n = T.n; R.active = T.active; R.i0a = T.i0a.data(); R.ua = T.ua.data(); R.i0b = T.i0b.data(); R.ub = T.ub.data(); R.v = T.v.data();
+    R.ia = T.ia.data(); R.ib = T.ib.data(); R.weight = T.weight.data(); R.huber = T.huber.empty() ? nullptr : T.huber.data();
+  }
+  P.pos_r3 = L.pos_r3.data(); P.pos_so3 = L.pos_so3.data(); P.pos_rho = L.pos_rho.data();
+  for (int b = 0; b < TB_COUNT; ++b) P.pos_sens[b] = L.pos_sens[b];
+  return P;
+}
+
+inline void pack_sens(const lvi_problem_desc& d, double* s) {
+  static const double ident[4] = {0, 0, 0, 1}, zero[3] = {0, 0, 0};
+  const double* lq = d.lidar_q ? d.lidar_q : ident; const double* lp = d.lidar_p ? d.lidar_p : zero;
+  const double* cq = d.cam_q ? d.cam_q : ident; const double* cp = d.cam_p ? d.cam_p : zero;
+  for (int k = 0; k < 4; ++k) { s[SENS_LQ + k] = lq[k]; s[SENS_CQ + k] = cq[k]; }
+  for (int k = 0; k < 3; ++k) { s[SENS_LP + k] = lp[k]; s[SENS_CP + k] = cp[k]; s[SENS_BA + k] = d.acc_bias ? d.acc_bias[k] : 0; s[SENS_BG + k] = d.gyr_bias ? d.gyr_bias[k] : 0; }
+  s[SENS_G] = d.gravity ? d.gravity[0] : 0; s[SENS_G + 1] = d.gravity ? d.gravity[1] : 0;
+}
+
+template <int TYPE> inline void bw_of_type(const ProblemView& P, int nb, int& bw) {
+  const ResTable& T = P.tab[TYPE];
+  if (!T.active) return;
+  for (int i = 0; i < T.n; ++i) {
+    int lo = 1 << 30, hi = -1;
+    for (int c = 0; c < rt_cols(TYPE); ++c) { const int p = col_pos<TYPE>(P, i, c); if (p >= 0 && p < nb) { lo = std::min(lo, p); hi = std::max(hi, p); } }
+    if (hi >= 0) bw = std::max(bw, hi - lo);
+  }
+}
+inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
+  int bw = 0;
+  bw_of_type<RT_GYRO>(P, L.nb, bw); bw_of_type<RT_ACCEL>(P, L.nb, bw); bw_of_type<RT_SURFEL>(P, L.nb, bw);
+  bw_of_type<RT_CAM>(P, L.nb, bw); bw_of_type<RT_CAMSURF>(P, L.nb, bw); bw_of_type<RT_ORIENT>(P, L.nb, bw);
+  L.bw = bw;
+}
+
+}  // namespace lvi
