@@ -224,7 +224,8 @@ int lvi_problem_create(lvi_ctx* ctx, const lvi_problem_desc* desc, lvi_problem**
 int lvi_problem_destroy(lvi_problem* p);
 /* ceres::Solve with TRUST_REGION / LEVENBERG_MARQUARDT / exact Schur-equivalent linear solve
  * (K/trajectory_estimator.h:38-68); writes the optimum back into the desc's in/out arrays. Under world>1
- * every rank passes its own shard of the residual tables and identical parameters. */
+ * every rank passes the SAME full problem; the library evaluates a contiguous time chunk of every residual table
+ * per rank and all-reduces the normal equations (NCCL), so every rank returns identical parameters. */
 int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary);
 /* One evaluation at the current parameters (ceres::Problem::Evaluate analogue, used for parity tests):
  *   cost (with loss, excluding fixed cost) ; residuals[num_residuals] after loss correction, in table order
@@ -244,14 +245,46 @@ int lvi_problem_jacobian_dense(lvi_problem* p, double* J);
  * Jacobians + normal equations + damped solve + trial-step cost. Parameters are restored afterwards. */
 int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase /* [4] jac, assemble, solve, trial */);
 
+/* ---- (a-3') visual landmark -> surfel association ------------------------------------------------------- */
+/* Inner test of SurfelAssociation::associateVisualPointsWithPlanes (L/src/core/surfel_association.cpp:196-210) for
+ * landmark positions already expressed in the map (L0) frame: strict bbox test + point2PlaneDistance <= 2*radius;
+ * the LAST matching plane wins (:206).  pts[n*3] double; plane_out[n] = plane id or -1. */
+int lvi_associate_landmarks(lvi_ctx* ctx, const lvi_surfel_set* s, const double* pts, int64_t n, double radius,
+                            int32_t* plane_out);
+
 /* ---- (f-1) scan undistortion / map assembly -------------------------------------------------------------- */
-/* Replaces ScanUndistortion::undistort (L/include/core/scan_undistortion.h:132-180) for a batch of raw points:
- * out = q_G_to_target * (q_Lk_to_G * p + [correct_position] (p_Lk_in_G - p_target_in_G)), with the LiDAR pose
- * evaluated from the spline at each point's own timestamp (TrajectoryManagerLVI::evaluateLidarPose,
- * L/src/core/trajectory_manager_lvi.cpp:398-408). Output points are pcl::PointXYZI-shaped (32 B). */
-int lvi_undistort(lvi_ctx* ctx, const lvi_problem_desc* traj /* t0,dt,n_knots,knots,lidar_q,lidar_p used */,
-                  const lvi_point_xyzit* scans_raw, int64_t n_points, double target_time, int correct_position,
-                  void* out_xyzi /* n_points*32 B */);
+/* Replaces ScanUndistortion::undistort (L/include/core/scan_undistortion.h:132-180) for a batch of n_scans raw scans of
+ * pts_per_scan points: out = q_G_to_target * (q_Lk_to_G * p + [correct_position] (p_Lk_in_G - p_target_in_G)), with
+ * the LiDAR pose evaluated from the spline at each point's own timestamp (TrajectoryManagerLVI::evaluateLidarPose,
+ * L/src/core/trajectory_manager_lvi.cpp:398-408).  target_time[s] is the time scan s is expressed at: its own stamp
+ * for undistortScan() (:40-57), the map time for undistortScanInMap() (:59-74).  Output points are
+ * pcl::PointXYZI-shaped (32 B: x,y,z,1,intensity,0,0,0); NaN in -> NaN out; a point whose time is outside the
+ * trajectory stays a default-constructed (zero) point as in the reference.  *n_bad_targets (may be NULL) counts scans
+ * whose target time is outside the trajectory (all their points are NaN).
+ * `traj` uses t0, dt, n_knots, r3_knots, so3_knots, lidar_q, lidar_p, lidar_toff (host pointers). */
+int lvi_undistort(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw, int32_t n_scans,
+                  int64_t pts_per_scan, const double* target_time, int correct_position, void* out_xyzi,
+                  int32_t* n_bad_targets);
+int lvi_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw_d, int32_t n_scans,
+                    int64_t pts_per_scan, const double* target_time, int correct_position, void* out_xyzi_d,
+                    int32_t* n_bad_targets);
+/* IMU pose of the trajectory (SplitTrajectory::Evaluate, K/trajectories/split_trajectory.h:41-58; Position|Orientation)
+ * at n times: pos[n*3], quat[n*4] (x,y,z,w), valid[n] = 0 where t is outside [MinTime, MaxTime). */
+int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* traj, const double* t, int64_t n, double* pos,
+                            double* quat, uint8_t* valid);
+/* pcl::transformPointCloud(scan, out, pose) with the pose cast to a float 4x4 (L/include/core/scan_undistortion.h:111,
+ * L/src/core/lidar_odometry.cpp:98), one pose per scan: poses[n_scans*16] row-major double. In/out PointXYZI (32 B). */
+int lvi_transform_scans(lvi_ctx* ctx, const void* scans_xyzi, int32_t n_scans, int64_t pts_per_scan,
+                        const double* poses, void* out_xyzi);
+int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scans, int64_t pts_per_scan,
+                          const double* poses, void* out_xyzi_d);
+
+/* ---- diagnostics ---------------------------------------------------------------------------------------------- */
+/* Solves A x = rhs through the band+arrow tile Cholesky used by lvi_problem_solve (tests only). A_dense is
+ * [n x n] row-major symmetric positive definite, n = nb + nbo; within the first nb rows/cols entries with
+ * |i-j| > bw must be zero. Returns LVI_ERR_NUMERIC on Cholesky breakdown. */
+int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_dense, const double* rhs,
+                         double* x_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,275 @@
+"""CUDA backend of the calibration pipeline: every heavy step goes through the C-ABI of liblvi_exc_b200.so
+(include/lvi_exc_b200.h).  There is no CPU fallback: constructing the backend without the library or without a CUDA
+device raises.
+
+Mirrors, on the host side, the objects the reference driver holds (L/test/lvi_initialize_surfel_orb.cpp:227-241):
+  CudaSurfelMap  = LiDAROdometry's pclomp::NormalDistributionsTransform target cells + SurfelAssociation::surfel_planes_
+  CudaBackend    = the calls LIinitializer::DataAssociation / Mapping / trajInitFrom* make (T:1169-1300)
+
+Point clouds stay resident in HBM between steps (torch tensors are used only as device-memory holders; all compute
+is in the library's own kernels on the library's own stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import SURFEL_POINT_DTYPE, SolveOptions, SolveSummary, check, ptr
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class CudaSurfelMap:
+    def __init__(self, backend: "CudaBackend", cloud, leaf: float, lam: float, min_points=6, eig_mult=0.01, min_leaf_points=10,
+                 ransac_thr=0.05, min_inliers=20):
+        self.b = backend
+        lib = backend.lib
+        self.vmap = C.c_void_p()
+        self.surfels = C.c_void_p()
+        dev, n, stride, keep = backend._as_device_cloud(cloud)
+        self._keep = keep
+        check(lib.lvi_voxel_build_d(backend.ctx, dev, stride, n, leaf, min_points, eig_mult, C.byref(self.vmap)))
+        check(lib.lvi_surfel_extract(backend.ctx, self.vmap, lam, min_leaf_points, ransac_thr, min_inliers, C.byref(self.surfels)))
+        self._keep = None  # the map keeps its own sorted copy of the points
+        self.num_leaves = lib.lvi_voxel_num_leaves(self.vmap)
+        self.num_planes = lib.lvi_surfel_count(self.surfels)
+        self.planes = self.export_planes()
+        self.planes_Pi = self.planes["Pi"]
+
+    def export_planes(self) -> dict:
+        P = self.num_planes
+        out = dict(p4=np.zeros((P, 4)), Pi=np.zeros((P, 3)), box_min=np.zeros((P, 3)), box_max=np.zeros((P, 3)),
+                   leaf_key=np.zeros(P, np.int64), n_inliers=np.zeros(P, np.int32))
+        check(self.b.lib.lvi_surfel_export(self.b.ctx, self.surfels, ptr(out["p4"]), ptr(out["Pi"]), ptr(out["box_min"]),
+                                           ptr(out["box_max"]), ptr(out["leaf_key"]), ptr(out["n_inliers"])))
+        return out
+
+    def export_leaves(self) -> dict:
+        L = self.num_leaves
+        npts = self.b.lib.lvi_voxel_num_points(self.vmap)
+        out = dict(keys=np.zeros(L, np.int64), nr_points=np.zeros(L, np.int32), mean=np.zeros((L, 3)), cov=np.zeros((L, 9)),
+                   evals=np.zeros((L, 3)), evecs=np.zeros((L, 9)), icov=np.zeros((L, 9)), leaf_start=np.zeros(L + 1, np.int64),
+                   point_index=np.zeros(npts, np.int32))
+        check(self.b.lib.lvi_voxel_export(self.b.ctx, self.vmap, ptr(out["keys"]), ptr(out["nr_points"]), ptr(out["mean"]), ptr(out["cov"]),
+                                          ptr(out["evals"]), ptr(out["evecs"]), ptr(out["icov"]), ptr(out["leaf_start"]), ptr(out["point_index"])))
+        return out
+
+    def grid(self):
+        mn, dv = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        check(self.b.lib.lvi_voxel_grid(self.vmap, ptr(mn), ptr(dv)))
+        return mn, dv
+
+    def close(self):
+        if self.surfels:
+            self.b.lib.lvi_surfel_destroy(self.surfels); self.surfels = C.c_void_p()
+        if self.vmap:
+            self.b.lib.lvi_voxel_destroy(self.vmap); self.vmap = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaProblem:
+    """kontiki::TrajectoryEstimator + ceres::Problem on the device (lvi_problem)."""
+
+    def __init__(self, backend: "CudaBackend", pd):
+        self.b, self.pd = backend, pd
+        self.desc = pd.desc()
+        self.h = C.c_void_p()
+        check(backend.lib.lvi_problem_create(backend.ctx, C.byref(self.desc), C.byref(self.h)))
+
+    @property
+    def num_residuals(self):
+        return self.b.lib.lvi_problem_num_residuals(self.h)
+
+    @property
+    def num_tangent(self):
+        return self.b.lib.lvi_problem_num_tangent(self.h)
+
+    def evaluate(self, jacobian=False, gradient=True, residuals=True):
+        cost = np.zeros(1)
+        res = np.zeros(self.num_residuals) if residuals else None
+        g = np.zeros(self.num_tangent) if gradient else None
+        check(self.b.lib.lvi_problem_evaluate(self.h, ptr(cost), ptr(res), ptr(g)))
+        J = None
+        if jacobian:
+            J = np.zeros((self.num_residuals, self.num_tangent))
+            check(self.b.lib.lvi_problem_jacobian_dense(self.h, ptr(J)))
+        return dict(cost=float(cost[0]), residuals=res, gradient=g, J=J)
+
+    def solve(self, max_iterations=30, verbose=False, **kw) -> SolveSummary:
+        opt = SolveOptions.default(max_iterations, verbose)
+        for k, v in kw.items():
+            setattr(opt, k, v)
+        s = SolveSummary()
+        check(self.b.lib.lvi_problem_solve(self.h, C.byref(opt), C.byref(s)))
+        return s
+
+    def bench_iterations(self, iters: int) -> np.ndarray:
+        ms = (C.c_float * 4)()
+        check(self.b.lib.lvi_problem_bench_iterations(self.h, iters, ms))
+        return np.array(list(ms), dtype=np.float64)
+
+    def close(self):
+        if self.h:
+            self.b.lib.lvi_problem_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, device: int = 0, verbose: bool = False, nccl_id: bytes | None = None, rank: int = 0, world: int = 1):
+        self.lib = _capi.load()          # raises LibraryMissing when the CUDA library has not been built
+        self.verbose = verbose
+        self.device = device
+        self.ctx = C.c_void_p()
+        if world > 1:
+            assert nccl_id is not None and len(nccl_id) == 128
+            buf = C.create_string_buffer(nccl_id, 128)
+            check(self.lib.lvi_ctx_create_nccl(device, buf, rank, world, C.byref(self.ctx)))
+        else:
+            check(self.lib.lvi_ctx_create(device, None, 0, 1, C.byref(self.ctx)))  # LVI_ERR_NO_DEVICE without a GPU
+        self.rank, self.world = rank, world
+        self._dev_cache = {}
+
+    def close(self):
+        if self.ctx:
+            self.lib.lvi_ctx_destroy(self.ctx); self.ctx = C.c_void_p()
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lvi_ctx_launch_count(self.ctx))
+
+    def synchronize(self):
+        check(self.lib.lvi_ctx_synchronize(self.ctx))
+
+    # ---- device-memory helpers (torch = allocator only) ------------------------------------------------------
+    def to_device(self, a, cache: bool = False):
+        """numpy -> device tensor; `cache=True` keeps the copy resident across calls (the raw scans are uploaded once)"""
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            return a
+        if cache:
+            hit = self._dev_cache.get(id(a))
+            if hit is not None and hit[0] is a:
+                return hit[1]
+            t = self.to_device(a)
+            self._dev_cache = {id(a): (a, t)}   # one resident batch at a time
+            return t
+        a = np.ascontiguousarray(a)
+        if a.dtype.fields is not None:   # PointXYZIT records -> [..., 8] float32 view (same bytes)
+            a = a.view(np.float32).reshape(a.shape + (8,))
+        t = torch.from_numpy(a).to(f"cuda:{self.device}")
+        torch.cuda.synchronize(self.device)
+        return t
+
+    def _as_device_cloud(self, cloud):
+        """-> (device pointer, n_points, stride_bytes, keep-alive)"""
+        t = self.to_device(cloud)
+        assert t.dtype == _torch().float32 and t.shape[-1] >= 3
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+        _torch().cuda.synchronize(self.device)
+        return C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1] * 4, t
+
+    # ---- backend protocol of pipeline.run_calibration -----------------------------------------------------------
+    def solve(self, pd, max_iterations, **kw):
+        prob = CudaProblem(self, pd)
+        try:
+            return prob.solve(max_iterations, verbose=self.verbose, **kw)
+        finally:
+            prob.close()
+
+    def build_surfel_map(self, cloud, leaf, lam):
+        return CudaSurfelMap(self, cloud, leaf, lam)
+
+    def associate(self, smap: CudaSurfelMap, scans_in_map, scans_raw, radius, k, step):
+        torch = _torch()
+        m = self.to_device(scans_in_map)
+        r = self.to_device(scans_raw, cache=True)
+        S, H, W = r.shape[0], r.shape[1], r.shape[2]
+        assert m.shape[:3] == (S, H, W)
+        m = m.contiguous(); r = r.contiguous()
+        torch.cuda.synchronize(self.device)
+        n_out, n_all = C.c_int64(0), C.c_int64(0)
+        args = (self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H, radius, k, step)
+        check(self.lib.lvi_associate_d(*args, None, 0, C.byref(n_out), C.byref(n_all)))
+        n = n_out.value
+        self.last_n_all = n_all.value
+        out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
+        if n == 0:
+            return out
+        od = torch.empty(n * 64, dtype=torch.uint8, device=m.device)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.lvi_associate_d(*args, C.c_void_p(od.data_ptr()), n, C.byref(n_out), C.byref(n_all)))
+        out[:] = od.cpu().numpy().view(SURFEL_POINT_DTYPE)
+        return out
+
+    def transform(self, scans_xyzi, poses):
+        torch = _torch()
+        t = self.to_device(scans_xyzi).contiguous()
+        S = t.shape[0]
+        pts = int(np.prod(t.shape[1:-1]))
+        assert t.shape[-1] == 8
+        out = torch.empty_like(t)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(S, 16)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.lvi_transform_scans_d(self.ctx, C.c_void_p(t.data_ptr()), S, pts, ptr(poses), C.c_void_p(out.data_ptr())))
+        return out
+
+    def undistort(self, pd, scans_raw, target_time, correct_position):
+        torch = _torch()
+        r = self.to_device(scans_raw, cache=True).contiguous()
+        S, H, W = r.shape[0], r.shape[1], r.shape[2]
+        if target_time is None:   # undistortScan(): each scan expressed at its own stamp (first point's firing time)
+            tt = r[:, 0, 0, 6:8].contiguous().cpu().numpy().view(np.float64).reshape(S).copy()
+        else:
+            tt = np.full(S, float(target_time))
+        out = torch.empty((S, H, W, 8), dtype=torch.float32, device=r.device)
+        d = pd.desc()
+        bad = C.c_int32(0)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.lvi_undistort_d(self.ctx, C.byref(d), C.c_void_p(r.data_ptr()), S, H * W, ptr(tt), int(correct_position),
+                                       C.c_void_p(out.data_ptr()), C.byref(bad)))
+        if bad.value:
+            raise IndexError(f"{bad.value} scan target time(s) outside the trajectory")
+        return out
+
+    def traj_eval_many(self, pd, times):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        n = len(times)
+        pos, quat, valid = np.zeros((n, 3)), np.zeros((n, 4)), np.zeros(n, np.uint8)
+        d = pd.desc()
+        check(self.lib.lvi_trajectory_evaluate(self.ctx, C.byref(d), ptr(times), n, ptr(pos), ptr(quat), ptr(valid)))
+        return pos, quat, valid.astype(bool)
+
+    def traj_eval(self, pd, t):
+        pos, quat, valid = self.traj_eval_many(pd, [t])
+        if not valid[0]:
+            raise IndexError("time out of range for trajectory")
+        return dict(p=pos[0], q=quat[0])
+
+    def associate_landmarks(self, smap: CudaSurfelMap, pts, radius):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(pts), np.int32)
+        check(self.lib.lvi_associate_landmarks(self.ctx, smap.surfels, ptr(pts), len(pts), radius, ptr(out)))
+        return out
+
+    def band_solve_dense(self, A, rhs, nb, nbo, bw):
+        A = np.ascontiguousarray(A, dtype=np.float64); rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros(nb + nbo)
+        check(self.lib.lvi_band_solve_dense(self.ctx, nb, nbo, bw, ptr(A), ptr(rhs), ptr(x)))
+        return x

@@ -165,6 +165,24 @@ __global__ void __launch_bounds__(256) assoc_emit_kernel(const int32_t* __restri
   }
 }
 
+// a-3'  associateVisualPointsWithPlanes inner test (L/src/core/surfel_association.cpp:196-210): thread per landmark sweeps the
+// plane list (<= 1e4 landmarks x <= 1e4 planes, all planes L2-resident); the LAST matching plane wins (:206).
+__global__ void __launch_bounds__(128) assoc_landmark_kernel(const double* __restrict__ pts, int64_t n, int n_planes, const double* __restrict__ p4,
+                                                             const double* __restrict__ bmin, const double* __restrict__ bmax, double radius2,
+                                                             int32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  int best = -1;
+  for (int k = 0; k < n_planes; ++k) {
+    const double* mn = bmin + 3 * k; const double* mx = bmax + 3 * k;
+    if (x > mn[0] && x < mx[0] && y > mn[1] && y < mx[1] && z > mn[2] && z < mx[2]) {
+      if (p2plane(x, y, z, p4 + 4 * k) <= radius2) best = k;
+    }
+  }
+  out[i] = best;
+}
+
 static void associate_device(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s, const void* map_d, size_t stride,
                              const lvi_point_xyzit* raw_d, int n_scans, int W, int H, double radius, int k, int time_step,
                              lvi_surfel_point* out_d, int64_t cap, int64_t* n_out, int64_t* n_all) {
@@ -236,6 +254,21 @@ int lvi_associate(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s,
     }
     if (n_out) *n_out = no;
     if (n_all) *n_all = na;
+  });
+}
+
+int lvi_associate_landmarks(lvi_ctx* ctx, const lvi_surfel_set* s, const double* pts, int64_t n, double radius, int32_t* plane_out) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && s && plane_out && (pts || n == 0), LVI_ERR_INVALID, "lvi_associate_landmarks: null argument");
+    if (n == 0) return;
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    DBuf<double> pd(3 * static_cast<size_t>(n));
+    DBuf<int32_t> od(n);
+    pd.upload(pts, 3 * static_cast<size_t>(n), ctx->stream);
+    LVI_LAUNCH(ctx, assoc_landmark_kernel, static_cast<int>((n + 127) / 128), 128, 0, pd.p, n, static_cast<int>(s->n_planes), s->p4.p, s->bmin.p, s->bmax.p,
+               radius * 2, od.p);
+    od.download(plane_out, n, ctx->stream);
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
 

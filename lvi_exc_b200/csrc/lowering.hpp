@@ -272,7 +272,7 @@ inline ProblemView host_view(const lvi_problem_desc& d, const Lowered& L, const 
   for (int t = 0; t < RT_COUNT; ++t) {
     const LoweredTable& T = L.tab[t];
     ResTable& R = P.tab[t];
-    R.n = T.n; R.active = T.active; R.i0a = T.i0a.data(); R.ua = T.ua.data(); R.i0b = T.i0b.data(); R.ub = T.ub.data(); R.v = T.v.data();
+    R.n = T.n; R.lo = 0; R.hi = T.n; R.active = T.active; R.i0a = T.i0a.data(); R.ua = T.ua.data(); R.i0b = T.i0b.data(); R.ub = T.ub.data(); R.v = T.v.data();
     R.ia = T.ia.data(); R.ib = T.ib.data(); R.weight = T.weight.data(); R.huber = T.huber.empty() ? nullptr : T.huber.data();
   }
   P.pos_r3 = L.pos_r3.data(); P.pos_so3 = L.pos_so3.data(); P.pos_rho = L.pos_rho.data();

@@ -1,0 +1,455 @@
+// problem.cu — residual / Jacobian evaluation and normal-equation assembly on sm_100a (SURVEY §8 a-4 … a-11, a-13).
+//
+// Replaces, for one kontiki::TrajectoryEstimator problem (K/trajectory_estimator.h:19-135):
+//   * ceres::DynamicAutoDiffCostFunction evaluation of the Kontiki Residual functors (4..26 Jet passes per residual per
+//     iteration, each re-evaluating both spline segments with heap allocations) -> analytic Jacobians (residuals.cuh)
+//   * Ceres' block-sparse Jacobian + SchurEliminator/normal-equation build -> fused J^T J / J^T r accumulation straight into
+//     the band+arrow tile storage (problem.cuh); J is never materialised.
+// linearize_kernel<TYPE>: one lane per residual evaluates r and J (fp64) into shared memory; the warp then reduces every run of
+// consecutive residuals that share a knot span (same column -> position map; residual tables are chronological) into ONE
+// J_run^T J_run contribution, so HBM sees one fp64 atomic per (run, column pair) instead of one per (residual, pair).
+// The Huber corrector (ceres Corrector, rho'' <= 0 branch) and the EigenQuaternionParameterization tangent are folded in.
+#include <cstring>
+
+#include "problem.cuh"
+
+namespace lvi {
+
+template <int TYPE> struct RTr {
+  static constexpr int rows = (TYPE == RT_GYRO || TYPE == RT_ACCEL) ? 3 : (TYPE == RT_CAM ? 2 : 1);
+  static constexpr int cols = TYPE == RT_GYRO ? 15 : TYPE == RT_ACCEL ? 29 : TYPE == RT_SURFEL ? 54 : TYPE == RT_CAM ? 55 : TYPE == RT_CAMSURF ? 60 : 12;
+  static constexpr int shared_cols = TYPE == RT_CAM ? 54 : cols;  // the inverse-depth column differs per residual
+  static constexpr bool two_eval = TYPE == RT_SURFEL || TYPE == RT_CAM || TYPE == RT_CAMSURF;
+  static constexpr int warp_doubles = 32 * rows * cols + 32 * rows + 32;  // J, r, positions (ints, padded)
+};
+
+constexpr int kLinWarps = 2;
+
+template <int TYPE>
+__global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P, BandSys H, double* __restrict__ g, double* __restrict__ cost) {
+  constexpr int ROWS = RTr<TYPE>::rows, COLS = RTr<TYPE>::cols, RC = ROWS * COLS, SC = RTr<TYPE>::shared_cols;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Jw = smem + warp * RTr<TYPE>::warp_doubles;
+  double* rw = Jw + 32 * RC;
+  int* posw = reinterpret_cast<int*>(rw + 32 * ROWS);
+  const ResTable& T = P.tab[TYPE];
+  double cost_acc = 0.0;
+  const int stride = gridDim.x * kLinWarps * 32;
+  for (int base = T.lo + (blockIdx.x * kLinWarps + warp) * 32; base < T.hi; base += stride) {
+    const int i = base + lane;
+    const bool valid = i < T.hi;
+    long long key = -1;
+    if (valid) {
+      ResOut o;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k)
+        for (int c = 0; c < COLS; ++c) o.J[k][c] = 0.0;
+      eval_residual<TYPE>(P, i, true, o);
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) s += o.r[k] * o.r[k];
+      double sc;
+      const double rho = huber(s, T.huber ? T.huber[i] : -1.0, sc);
+      cost_acc += 0.5 * rho;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        rw[lane * ROWS + k] = o.r[k] * sc;
+        for (int c = 0; c < COLS; ++c) Jw[lane * RC + k * COLS + c] = o.J[k][c] * sc;
+      }
+      key = T.i0a[i];
+      if (RTr<TYPE>::two_eval) key |= static_cast<long long>(T.i0b[i]) << 32;
+    }
+    __syncwarp();
+    const long long prev = __shfl_up_sync(FULL, key, 1);
+    const bool head = valid && (lane == 0 || key != prev);
+    unsigned heads = __ballot_sync(FULL, head);
+    const int nvalid = __popc(__ballot_sync(FULL, valid));
+    while (heads) {
+      const int s = __ffs(heads) - 1;
+      heads &= heads - 1;
+      const int e = heads ? (__ffs(heads) - 1) : nvalid;
+      for (int c = lane; c < COLS; c += 32) posw[c] = col_pos<TYPE>(P, base + s, c);
+      __syncwarp();
+      constexpr int NP = SC * (SC + 1) / 2;
+      for (int p = lane; p < NP; p += 32) {
+        int c1 = static_cast<int>((sqrtf(8.f * p + 1.f) - 1.f) * 0.5f);
+        while (c1 * (c1 + 1) / 2 > p) --c1;
+        while ((c1 + 1) * (c1 + 2) / 2 <= p) ++c1;
+        const int c2 = p - c1 * (c1 + 1) / 2;
+        const int p1 = posw[c1], p2 = posw[c2];
+        if (p1 < 0 || p2 < 0) continue;
+        double acc = 0.0;
+        for (int r = s; r < e; ++r) {
+          const double* Jr = Jw + r * RC;
+#pragma unroll
+          for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + c1] * Jr[k * COLS + c2];
+        }
+        if (c1 != c2 && p1 == p2) acc += acc;  // two columns of one residual on the same parameter (overlapping knot windows)
+        if (acc != 0.0) atomicAdd(band_addr(H, max(p1, p2), min(p1, p2)), acc);
+      }
+      for (int c = lane; c < SC; c += 32) {
+        const int pc = posw[c];
+        if (pc < 0) continue;
+        double acc = 0.0;
+        for (int r = s; r < e; ++r)
+#pragma unroll
+          for (int k = 0; k < ROWS; ++k) acc += Jw[r * RC + k * COLS + c] * rw[r * ROWS + k];
+        if (acc != 0.0) atomicAdd(g + pc, acc);
+      }
+      if (TYPE == RT_CAM) {  // inverse-depth column: one parameter per landmark
+        for (int r = s; r < e; ++r) {
+          const int pr = P.pos_rho[T.ia[base + r]];
+          if (pr < 0) continue;
+          const double* Jr = Jw + r * RC;
+          for (int c = lane; c <= SC; c += 32) {
+            const int pc = (c == SC) ? pr : posw[c];
+            if (pc < 0) continue;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + SC] * Jr[k * COLS + c];
+            if (acc != 0.0) atomicAdd(band_addr(H, max(pr, pc), min(pr, pc)), acc);
+          }
+          if (lane == 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + SC] * rw[r * ROWS + k];
+            atomicAdd(g + pr, acc);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(FULL, cost_acc, o);
+  if (lane == 0 && cost_acc != 0.0) atomicAdd(cost, cost_acc);
+}
+
+// cost only (trial steps, fixed cost): one thread per residual
+template <int TYPE>
+__global__ void __launch_bounds__(128) cost_kernel(ProblemView P, double* __restrict__ cost) {
+  constexpr int ROWS = RTr<TYPE>::rows;
+  const ResTable& T = P.tab[TYPE];
+  double acc = 0.0;
+  for (int i = T.lo + blockIdx.x * blockDim.x + threadIdx.x; i < T.hi; i += gridDim.x * blockDim.x) {
+    ResOut o;
+    eval_residual<TYPE>(P, i, false, o);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) s += o.r[k] * o.r[k];
+    double sc;
+    acc += 0.5 * huber(s, T.huber ? T.huber[i] : -1.0, sc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[4];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double s = part[0] + part[1] + part[2] + part[3];
+    if (s != 0.0) atomicAdd(cost, s);
+  }
+}
+
+// corrected residuals (and optionally the dense tangent Jacobian) for parity tests
+template <int TYPE>
+__global__ void __launch_bounds__(64) residual_kernel(ProblemView P, int res_offset, int nt, double* __restrict__ res, double* __restrict__ Jd) {
+  constexpr int ROWS = RTr<TYPE>::rows, COLS = RTr<TYPE>::cols;
+  const ResTable& T = P.tab[TYPE];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T.n; i += gridDim.x * blockDim.x) {
+    ResOut o;
+    for (int k = 0; k < ROWS; ++k)
+      for (int c = 0; c < COLS; ++c) o.J[k][c] = 0.0;
+    eval_residual<TYPE>(P, i, Jd != nullptr, o);
+    double s = 0.0;
+    for (int k = 0; k < ROWS; ++k) s += o.r[k] * o.r[k];
+    double sc;
+    huber(s, T.huber ? T.huber[i] : -1.0, sc);
+    for (int k = 0; k < ROWS; ++k) {
+      const size_t row = static_cast<size_t>(res_offset) + static_cast<size_t>(i) * ROWS + k;
+      if (res) res[row] = o.r[k] * sc;
+      if (Jd && T.active)
+        for (int c = 0; c < COLS; ++c) {
+          const int p = col_pos<TYPE>(P, i, c);
+          if (p >= 0) Jd[row * nt + p] += o.J[k][c] * sc;
+        }
+    }
+  }
+}
+
+template <int TYPE>
+static void launch_linearize(lvi_problem* p) {
+  const ResTable& T = p->view.tab[TYPE];
+  if (T.n == 0 || !T.active) return;
+  static bool attr_set = false;
+  const size_t smem = static_cast<size_t>(kLinWarps) * RTr<TYPE>::warp_doubles * sizeof(double);
+  if (!attr_set) {
+    LVI_CUDA(cudaFuncSetAttribute(linearize_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const int per_cta = kLinWarps * 32;
+  int grid = std::max(1, (T.hi - T.lo + per_cta - 1) / per_cta);
+  const int cap = p->ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  LVI_LAUNCH(p->ctx, linearize_kernel<TYPE>, grid, per_cta, smem, p->view, p->H, p->g.p, p->scal.p);
+}
+
+template <int TYPE>
+static void launch_cost(lvi_problem* p, double* cost_d, bool want_active, bool want_inactive) {
+  const ResTable& T = p->view.tab[TYPE];
+  if (T.n == 0) return;
+  if (T.active ? !want_active : !want_inactive) return;
+  int grid = std::max(1, (T.hi - T.lo + 127) / 128);
+  const int cap = p->ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  LVI_LAUNCH(p->ctx, cost_kernel<TYPE>, grid, 128, 0, p->view, cost_d);
+}
+
+template <int TYPE>
+static void launch_residual(lvi_problem* p, double* res_d, double* J_d) {
+  const ResTable& T = p->view.tab[TYPE];
+  if (T.n == 0) return;
+  int grid = (T.n + 63) / 64;
+  const int cap = p->ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  LVI_LAUNCH(p->ctx, residual_kernel<TYPE>, grid, 64, 0, p->view, p->L.res_offset[TYPE], p->nt, res_d, J_d);
+}
+
+void problem_set_param_source(lvi_problem* p, const double* x) {
+  p->view.r3 = x + p->off_r3; p->view.so3 = x + p->off_so3; p->view.sens = x + p->off_sens; p->view.rho = x + p->off_rho;
+}
+
+void problem_linearize(lvi_problem* p, double* cost_d) {
+  cudaStream_t st = p->ctx->stream;
+  problem_ensure_solver_buffers(p);
+  p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st);
+  LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
+  problem_set_param_source(p, p->X.p);
+  launch_linearize<RT_GYRO>(p); launch_linearize<RT_ACCEL>(p); launch_linearize<RT_SURFEL>(p);
+  launch_linearize<RT_CAM>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
+  if (cost_d && cost_d != p->scal.p) LVI_CUDA(cudaMemcpyAsync(cost_d, p->scal.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+}
+
+void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active, bool inactive) {
+  LVI_CUDA(cudaMemsetAsync(cost_d, 0, sizeof(double), p->ctx->stream));
+  problem_set_param_source(p, x_d);
+  launch_cost<RT_GYRO>(p, cost_d, active, inactive); launch_cost<RT_ACCEL>(p, cost_d, active, inactive);
+  launch_cost<RT_SURFEL>(p, cost_d, active, inactive); launch_cost<RT_CAM>(p, cost_d, active, inactive);
+  launch_cost<RT_CAMSURF>(p, cost_d, active, inactive); launch_cost<RT_ORIENT>(p, cost_d, active, inactive);
+  problem_set_param_source(p, p->X.p);
+}
+
+static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBuf<double>& C, double* Linv, double* x, int* fail) {
+  S.nb = L.nb; S.nbo = L.nbo;
+  S.NT = (L.nb + kTile - 1) / kTile;
+  S.T = S.NT > 0 ? std::min(S.NT - 1, (L.bw + kTile - 1) / kTile) : 0;
+  S.RB = (L.nbo + 1 + kTile - 1) / kTile;  // + the rhs row
+  S.TPC = S.T + 1 + S.RB;
+  S.ldc = S.RB * kTile;
+  tiles.alloc(std::max<size_t>(static_cast<size_t>(S.NT) * S.TPC * kTileElems, 1));
+  C.alloc(static_cast<size_t>(S.ldc) * S.ldc);
+  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail;
+}
+
+void problem_ensure_solver_buffers(lvi_problem* p) {
+  if (p->has_solver_buffers) return;
+  const Lowered& L = p->L;
+  p->fail.alloc(4);
+  const int NT = (L.nb + kTile - 1) / kTile;
+  const int RB = (L.nbo + 1 + kTile - 1) / kTile;
+  p->A_Linv.alloc(std::max<size_t>(static_cast<size_t>(NT) * kTileElems, 1));
+  p->A_x.alloc(static_cast<size_t>(NT) * kTile + static_cast<size_t>(RB) * kTile);
+  alloc_bandsys(p->H, L, p->H_tiles, p->H_C, nullptr, nullptr, nullptr);
+  alloc_bandsys(p->A, L, p->A_tiles, p->A_C, p->A_Linv.p, p->A_x.p, p->fail.p);
+  const size_t nt = std::max(p->nt, 1);
+  p->g.alloc(nt); p->scale.alloc(nt); p->diag.alloc(nt); p->y.alloc(nt); p->delta.alloc(nt);
+  p->has_solver_buffers = true;
+}
+
+void problem_download_params(lvi_problem* p) {
+  cudaStream_t st = p->ctx->stream;
+  std::vector<double> h(p->nx);
+  p->X.download(h.data(), p->nx, st);
+  LVI_CUDA(cudaStreamSynchronize(st));
+  const lvi_problem_desc& d = p->desc;
+  const int n = d.n_knots;
+  if (d.r3_knots) std::memcpy(d.r3_knots, h.data() + p->off_r3, sizeof(double) * 3 * n);
+  std::memcpy(d.so3_knots, h.data() + p->off_so3, sizeof(double) * 4 * n);
+  const double* s = h.data() + p->off_sens;
+  if (d.lidar_q) std::memcpy(d.lidar_q, s + SENS_LQ, 32);
+  if (d.lidar_p) std::memcpy(d.lidar_p, s + SENS_LP, 24);
+  if (d.cam_q) std::memcpy(d.cam_q, s + SENS_CQ, 32);
+  if (d.cam_p) std::memcpy(d.cam_p, s + SENS_CP, 24);
+  if (d.gravity) std::memcpy(d.gravity, s + SENS_G, 16);
+  if (d.acc_bias) std::memcpy(d.acc_bias, s + SENS_BA, 24);
+  if (d.gyr_bias) std::memcpy(d.gyr_bias, s + SENS_BG, 24);
+  if (d.rho && d.n_landmarks) std::memcpy(d.rho, h.data() + p->off_rho, sizeof(double) * d.n_landmarks);
+}
+
+static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
+  auto p = std::unique_ptr<lvi_problem>(new lvi_problem());
+  p->ctx = ctx; p->desc = *d;
+  Lowered& L = p->L;
+  try {
+    lower_problem(*d, L);
+  } catch (const RangeError& e) {
+    throw Error(LVI_ERR_RANGE, e.what());
+  } catch (const std::invalid_argument& e) {
+    throw Error(LVI_ERR_INVALID, e.what());
+  }
+  // unit-quaternion check of the control points (UniformSO3SplineEntity validator, K/trajectories/uniform_so3_spline_trajectory.h:23-27)
+  for (int i = 0; i < d->n_knots; ++i) {
+    const double* q = d->so3_knots + 4 * i;
+    const double nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (std::fabs(nrm - 1.0) > 1e-5) throw Error(LVI_ERR_DOMAIN, "SO3 control point is not a unit quaternion");
+  }
+  double sens[SENS_N];
+  pack_sens(*d, sens);
+  {
+    ProblemView hv = host_view(*d, L, sens);
+    compute_bandwidth(hv, L);
+  }
+  cudaStream_t st = ctx->stream;
+  const int n = d->n_knots, nl = d->n_landmarks;
+  p->off_r3 = 0; p->off_so3 = 3 * n; p->off_sens = 7 * n; p->off_rho = 7 * n + SENS_N; p->nx = 7 * n + SENS_N + std::max(nl, 1);
+  std::vector<double> hx(p->nx, 0.0);
+  if (d->r3_knots) std::memcpy(hx.data(), d->r3_knots, sizeof(double) * 3 * n);
+  std::memcpy(hx.data() + p->off_so3, d->so3_knots, sizeof(double) * 4 * n);
+  std::memcpy(hx.data() + p->off_sens, sens, sizeof(sens));
+  if (nl && d->rho) std::memcpy(hx.data() + p->off_rho, d->rho, sizeof(double) * nl);
+  p->X.alloc(p->nx); p->XC.alloc(p->nx); p->XS.alloc(p->nx);
+  p->X.upload(hx.data(), p->nx, st);
+  LVI_CUDA(cudaMemcpyAsync(p->XC.p, p->X.p, sizeof(double) * p->nx, cudaMemcpyDeviceToDevice, st));
+  // tables
+  ProblemView& V = p->view;
+  V = ProblemView{};
+  V.dt_inv = 1.0 / d->dt; V.n_knots = n; V.fx = d->fx; V.fy = d->fy; V.cx = d->cx; V.cy = d->cy; V.has_r3 = L.has_r3;
+  auto up_i = [&](DBuf<int>& b, const std::vector<int>& h) -> const int* { if (h.empty()) return nullptr; b.alloc(h.size()); b.upload(h.data(), h.size(), st); return b.p; };
+  auto up_d = [&](DBuf<double>& b, const std::vector<double>& h) -> const double* { if (h.empty()) return nullptr; b.alloc(h.size()); b.upload(h.data(), h.size(), st); return b.p; };
+  for (int t = 0; t < RT_COUNT; ++t) {
+    const LoweredTable& T = L.tab[t];
+    ResTable& R = V.tab[t];
+    R.n = T.n; R.active = T.active;
+    R.lo = static_cast<int>(static_cast<long long>(T.n) * ctx->rank / ctx->world);
+    R.hi = static_cast<int>(static_cast<long long>(T.n) * (ctx->rank + 1) / ctx->world);
+    R.i0a = up_i(p->tab_i[t][0], T.i0a); R.i0b = up_i(p->tab_i[t][1], T.i0b); R.ia = up_i(p->tab_i[t][2], T.ia); R.ib = up_i(p->tab_i[t][3], T.ib);
+    R.ua = up_d(p->tab_d[t][0], T.ua); R.ub = up_d(p->tab_d[t][1], T.ub); R.v = up_d(p->tab_d[t][2], T.v);
+    R.weight = up_d(p->tab_d[t][3], T.weight); R.huber = up_d(p->tab_d[t][4], T.huber);
+  }
+  V.pos_r3 = up_i(p->pos_r3, L.pos_r3); V.pos_so3 = up_i(p->pos_so3, L.pos_so3); V.pos_rho = up_i(p->pos_rho, L.pos_rho);
+  for (int b = 0; b < TB_COUNT; ++b) V.pos_sens[b] = L.pos_sens[b];
+  if (d->n_planes > 0) {
+    LVI_REQUIRE(d->planes, LVI_ERR_INVALID, "planes is null");
+    p->planes.alloc(3 * static_cast<size_t>(d->n_planes));
+    p->planes.upload(d->planes, 3 * static_cast<size_t>(d->n_planes), st);
+  }
+  V.planes = p->planes.p;
+  problem_set_param_source(p.get(), p->X.p);
+  // free parameter blocks
+  std::vector<FreeBlock> fb;
+  for (int i = 0; i < n; ++i) {
+    if (L.pos_r3[i] >= 0) fb.push_back({p->off_r3 + 3 * i, L.pos_r3[i], 3, 0});
+    if (L.pos_so3[i] >= 0) fb.push_back({p->off_so3 + 4 * i, L.pos_so3[i], 4, 1});
+  }
+  const int s_off[TB_COUNT] = {SENS_LQ, SENS_LP, SENS_CQ, SENS_CP, SENS_G, SENS_BA, SENS_BG};
+  const int s_size[TB_COUNT] = {4, 3, 4, 3, 2, 3, 3};
+  const int s_kind[TB_COUNT] = {1, 0, 1, 0, 0, 0, 0};
+  for (int b = 0; b < TB_COUNT; ++b)
+    if (L.pos_sens[b] >= 0) fb.push_back({p->off_sens + s_off[b], L.pos_sens[b], s_size[b], s_kind[b]});
+  for (int l = 0; l < nl; ++l)
+    if (L.pos_rho[l] >= 0) fb.push_back({p->off_rho + l, L.pos_rho[l], 1, 2});
+  p->n_blocks = static_cast<int>(fb.size());
+  p->blocks.alloc(std::max<size_t>(fb.size(), 1));
+  p->blocks.upload(fb.data(), fb.size(), st);
+  p->nt = L.nt();
+  p->scal.alloc(64);
+  LVI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_scal), 64 * sizeof(double)));
+  LVI_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  return p.release();
+}
+
+}  // namespace lvi
+
+using namespace lvi;
+
+extern "C" {
+
+void lvi_solve_options_default(lvi_solve_options* o) {
+  if (!o) return;
+  o->max_num_iterations = 30; o->verbose = 0;  // K/trajectory_estimator.h:38 Solve(max_iterations = 30)
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1;
+}
+
+int lvi_problem_create(lvi_ctx* ctx, const lvi_problem_desc* desc, lvi_problem** out) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && desc && out, LVI_ERR_INVALID, "lvi_problem_create: null argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    *out = create_problem(ctx, desc);
+  });
+}
+
+int lvi_problem_destroy(lvi_problem* p) {
+  if (p) { cudaSetDevice(p->ctx->device); delete p; }
+  return LVI_OK;
+}
+
+int lvi_problem_num_residuals(const lvi_problem* p) { return p ? p->L.n_res : 0; }
+int lvi_problem_num_tangent(const lvi_problem* p) { return p ? p->nt : 0; }
+int lvi_problem_tangent_offset_knot(const lvi_problem* p, int knot) {
+  if (!p || knot < 0 || knot >= p->L.n_knots) return -1;
+  return p->L.pos_r3[knot] >= 0 ? p->L.pos_r3[knot] : p->L.pos_so3[knot];
+}
+int lvi_problem_tangent_offset_block(const lvi_problem* p, int which) {
+  if (!p || which < 0) return -1;
+  if (which < TB_COUNT) return p->L.pos_sens[which];
+  const int l = which - TB_COUNT;
+  return l < p->L.n_landmarks ? p->L.pos_rho[l] : -1;
+}
+
+int lvi_problem_evaluate(lvi_problem* p, double* cost, double* residuals, double* gradient) {
+  return guarded([&] {
+    LVI_REQUIRE(p, LVI_ERR_INVALID, "lvi_problem_evaluate: null problem");
+    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t st = p->ctx->stream;
+    if (gradient) {
+      problem_linearize(p, nullptr);
+      p->g.download(gradient, p->nt, st);
+      if (cost) LVI_CUDA(cudaMemcpyAsync(cost, p->scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else if (cost) {
+      problem_cost(p, p->X.p, p->scal.p, true, false);
+      LVI_CUDA(cudaMemcpyAsync(cost, p->scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (residuals) {
+      DBuf<double> r(std::max(p->L.n_res, 1));
+      launch_residual<RT_GYRO>(p, r.p, nullptr); launch_residual<RT_ACCEL>(p, r.p, nullptr); launch_residual<RT_SURFEL>(p, r.p, nullptr);
+      launch_residual<RT_CAM>(p, r.p, nullptr); launch_residual<RT_CAMSURF>(p, r.p, nullptr); launch_residual<RT_ORIENT>(p, r.p, nullptr);
+      r.download(residuals, p->L.n_res, st);
+      LVI_CUDA(cudaStreamSynchronize(st));
+    }
+    LVI_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int lvi_problem_jacobian_dense(lvi_problem* p, double* J) {
+  return guarded([&] {
+    LVI_REQUIRE(p && J, LVI_ERR_INVALID, "lvi_problem_jacobian_dense: null argument");
+    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    const size_t n = static_cast<size_t>(p->L.n_res) * p->nt;
+    LVI_REQUIRE(n < (1ull << 28), LVI_ERR_INVALID, "lvi_problem_jacobian_dense: problem too large for a dense Jacobian");
+    cudaStream_t st = p->ctx->stream;
+    DBuf<double> Jd(std::max<size_t>(n, 1)), r(std::max(p->L.n_res, 1));
+    Jd.zero(st);
+    launch_residual<RT_GYRO>(p, r.p, Jd.p); launch_residual<RT_ACCEL>(p, r.p, Jd.p); launch_residual<RT_SURFEL>(p, r.p, Jd.p);
+    launch_residual<RT_CAM>(p, r.p, Jd.p); launch_residual<RT_CAMSURF>(p, r.p, Jd.p); launch_residual<RT_ORIENT>(p, r.p, Jd.p);
+    Jd.download(J, n, st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

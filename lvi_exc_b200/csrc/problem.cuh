@@ -1,0 +1,85 @@
+// problem.cuh — device-resident least-squares problem shared by problem.cu (linearisation) and solver.cu (LM + band solver).
+//
+// HBM layout:
+//   X        one flat fp64 parameter vector [r3 3n | so3 4n | sens 22 | rho nl]; a second copy XC holds the LM candidate
+//   tables   per residual type SoA (ResTable, residuals.cuh), in the caller's (chronological) order
+//   H / A    normal equations in 32x32 TILE storage: block column J holds tiles d = 0..T (band, rows 32(J+d)..) followed by
+//            RB border tiles (arrow rows: map-time knots + sensor blocks + one extra row carrying the right-hand side);
+//            the border x border corner is a small dense matrix C.  Never dense n^2 (SURVEY §5 "long-context").
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+#include "lowering.hpp"
+
+namespace lvi {
+
+constexpr int kTile = 32;
+constexpr int kTileElems = kTile * kTile;
+
+struct BandSys {
+  int nb, nbo;       // band dims, border dims (without the rhs row)
+  int NT, T, RB;     // block columns, sub-diagonal tile rows, border tile rows
+  int TPC;           // tiles per block column = T + 1 + RB
+  int ldc;           // RB * 32
+  double* tiles;     // [NT * TPC * 1024]
+  double* C;         // [ldc * ldc] column-major, lower
+  double* Linv;      // [NT * 1024] inverse of each diagonal Cholesky block (filled by the factorisation)
+  double* x;         // [NT*32 + ldc] solution (band part then border part)
+  int* fail;         // != 0: Cholesky breakdown
+};
+
+// address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row
+__device__ __forceinline__ double* band_addr(const BandSys& S, int i, int j) {
+  if (j >= S.nb) {
+    return S.C + (i - S.nb) + static_cast<size_t>(S.ldc) * (j - S.nb);
+  }
+  const int J = j >> 5;
+  size_t tile;
+  int a;
+  if (i >= S.nb) { const int b = i - S.nb; tile = static_cast<size_t>(J) * S.TPC + S.T + 1 + (b >> 5); a = b & 31; }
+  else { tile = static_cast<size_t>(J) * S.TPC + ((i >> 5) - J); a = i & 31; }
+  return S.tiles + (tile << 10) + ((j & 31) << 5) + a;
+}
+
+// free parameter block (for Plus / norms): kind 0 Euclidean, 1 quaternion (x,y,z,w), 2 Euclidean with lower bound 0
+struct FreeBlock { int off; int pos; int size; int kind; };
+
+}  // namespace lvi
+
+struct lvi_problem {
+  lvi_ctx* ctx = nullptr;
+  lvi_problem_desc desc{};   // caller's arrays (in/out)
+  lvi::Lowered L;
+  // parameter vectors
+  int off_r3 = 0, off_so3 = 0, off_sens = 0, off_rho = 0, nx = 0;
+  lvi::DBuf<double> X, XC, XS;        // current, candidate, saved
+  lvi::DBuf<lvi::FreeBlock> blocks;   // free blocks
+  int n_blocks = 0;
+  // tables
+  lvi::DBuf<int> tab_i[lvi::RT_COUNT][4];      // i0a, i0b, ia, ib
+  lvi::DBuf<double> tab_d[lvi::RT_COUNT][5];   // ua, ub, v, weight, huber
+  lvi::DBuf<int> pos_r3, pos_so3, pos_rho;
+  lvi::DBuf<double> planes;
+  lvi::ProblemView view{};   // device pointers, parameters -> X
+  // normal equations
+  lvi::BandSys H{}, A{};
+  lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x;
+  lvi::DBuf<int> fail;
+  lvi::DBuf<double> g, scale, diag, y, delta, scal;  // scal: small scalar scratch (cost etc.)
+  double* h_scal = nullptr;                          // pinned host mirror of scal
+  int nt = 0;
+  bool has_solver_buffers = false;
+  ~lvi_problem() { if (h_scal) cudaFreeHost(h_scal); }
+};
+
+namespace lvi {
+// problem.cu
+void problem_set_param_source(lvi_problem* p, const double* x_d);                     // point the view at X or XC
+void problem_linearize(lvi_problem* p, double* cost_d);                               // zero H,g ; accumulate J^T J, J^T r, cost
+void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active_only, bool inactive_only);
+void problem_ensure_solver_buffers(lvi_problem* p);
+void problem_download_params(lvi_problem* p);
+// solver.cu
+void band_factor_solve(lvi_ctx* ctx, BandSys& A);
+}  // namespace lvi

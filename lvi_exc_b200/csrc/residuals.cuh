@@ -36,6 +36,7 @@ LVI_HD int rt_cols(int t) { return t == RT_GYRO ? 15 : t == RT_ACCEL ? 29 : t ==
 
 struct ResTable {   // one residual table, SoA, device (or host) pointers
   int n;
+  int lo, hi;       // index range this rank evaluates (data-parallel sharding by time chunk); [0, n) on one GPU
   int active;       // 0: every parameter block constant -> contributes only to the fixed cost
   const int* i0a; const double* ua;   // first evaluation (map time / ref time / the only one)
   const int* i0b; const double* ub;   // second evaluation (point time / obs time)

@@ -1,0 +1,705 @@
+// solver.cu — on-device Levenberg-Marquardt with an exact band+arrow Cholesky solve.
+//
+// Replaces ceres::Solve as configured by kontiki::TrajectoryEstimator::Solve (K/trajectory_estimator.h:38-68):
+// TRUST_REGION / LEVENBERG_MARQUARDT / SPARSE_SCHUR (an exact solve), Jacobi scaling, Ceres (<= 2.1) default
+// tolerances.  Ceres is not vendored; the loop below restates TrustRegionMinimizer +
+// LevenbergMarquardtStrategy step by step and is kept line-for-line comparable with the CPU oracle (oracle/orc_solve.cpp).
+//
+// Linear algebra: (S H S + D^2) y = -S g with H in 32x32 tile storage (problem.cuh).
+//   band_factor_kernel   cooperative persistent kernel, right-looking blocked Cholesky.  Per block column: every CTA factors the
+//                        32x32 diagonal tile in ONE WARP (rows in registers, shuffles, no barriers) and inverts it; the panel
+//                        (band tiles + arrow-border tiles + the rhs row, so the forward substitution comes for free) is solved
+//                        as a small GEMM against the inverse; grid.sync; trailing tiles are updated X_i X_j^T; grid.sync.
+//   corner_solve_kernel  dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
+//   band_backsolve_kernel  backward substitution, one CTA, 32 warps over the tiles of a block row.
+// All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
+#include <cooperative_groups.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "problem.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lvi {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kLP = 33;  // padded leading dimension of the 32x32 shared-memory tiles
+
+// ---- small elementwise kernels -------------------------------------------------------------------------------------
+__global__ void diag_kernel(BandSys H, int nt, double* __restrict__ d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) d[t] = *band_addr(H, t, t);
+}
+__global__ void scale_init_kernel(const double* __restrict__ dH, int nt, int jacobi, double* __restrict__ scale) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) scale[t] = jacobi ? 1.0 / (1.0 + sqrt(dH[t])) : 1.0;  // ceres: 1 / (1 + ||J_col||)
+}
+__global__ void lm_diag_kernel(const double* __restrict__ dH, const double* __restrict__ scale, int nt, double lo, double hi, double* __restrict__ diag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) diag[t] = fmin(fmax(dH[t] * scale[t] * scale[t], lo), hi);  // LevenbergMarquardtStrategy: clamp(diag(J^T J))
+}
+
+// A = S H S + diag(D2) in tile storage; the extra border row carries rhs = -S g.  One CTA per tile (+ corner CTAs).
+__global__ void __launch_bounds__(256) build_system_kernel(BandSys H, BandSys A, const double* __restrict__ scale, const double* __restrict__ diag,
+                                                           double inv_radius, const double* __restrict__ g) {
+  const int ntile = A.NT * A.TPC;
+  const int nb = A.nb, nbo = A.nbo;
+  if (static_cast<int>(blockIdx.x) < ntile) {
+    const int J = blockIdx.x / A.TPC, q = blockIdx.x % A.TPC;
+    if (q <= A.T && J + q >= A.NT) return;
+    const double* src = H.tiles + (static_cast<size_t>(blockIdx.x) << 10);
+    double* dst = A.tiles + (static_cast<size_t>(blockIdx.x) << 10);
+    for (int e = threadIdx.x; e < kTileElems; e += blockDim.x) {
+      const int a = e & 31, b = e >> 5;
+      const int j = J * 32 + b;
+      double v = 0.0;
+      if (q <= A.T) {
+        const int i = (J + q) * 32 + a;
+        if (i < nb && j < nb) {
+          if (i >= j) v = src[e] * scale[i] * scale[j];
+          if (i == j) v += diag[i] * inv_radius;
+        } else if (i == j) v = 1.0;  // padding rows keep the factorisation well defined
+      } else if (j < nb) {
+        const int bi = (q - A.T - 1) * 32 + a;
+        if (bi < nbo) v = src[e] * scale[nb + bi] * scale[j];
+        else if (bi == nbo) v = -g[j] * scale[j];
+      }
+      dst[e] = v;
+    }
+  } else {
+    const int ldc = A.ldc;
+    for (int e = (blockIdx.x - ntile) * blockDim.x + threadIdx.x; e < ldc * ldc; e += (gridDim.x - ntile) * blockDim.x) {
+      const int bi = e % ldc, bj = e / ldc;
+      double v = 0.0;
+      if (bi < nbo && bj < nbo) {
+        if (bi >= bj) v = H.C[e] * scale[nb + bi] * scale[nb + bj];
+        if (bi == bj) v += diag[nb + bi] * inv_radius;
+      } else if (bi == nbo && bj < nbo) v = -g[nb + bj] * scale[nb + bj];
+      else if (bi == bj) v = 1.0;
+      A.C[e] = v;
+    }
+  }
+}
+
+// ---- 32x32 Cholesky + inverse in one warp ----------------------------------------------------------------------------
+// lane a owns row a of the tile (column-major in global).  Writes L (lower, zero upper) to sL[r*33+c] and W = L^-1 to sW[r*33+m].
+__device__ __forceinline__ bool warp_potrf_inv(const double* tile, double* sL, double* sW) {
+  const int a = threadIdx.x & 31;
+  double A[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) A[c] = tile[a + 32 * c];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double d = __shfl_sync(FULL, A[j], j);
+    if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+    const double s = sqrt(d);
+    const double l = (a == j) ? s : A[j] / s;
+    A[j] = l;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) {
+      const double lc = __shfl_sync(FULL, l, c);
+      if (a >= c) A[c] -= l * lc;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) sL[a * kLP + c] = (c <= a) ? A[c] : 0.0;
+  __syncwarp();
+  // column a of W: forward substitution L w = e_a
+  double w[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    double acc = (r == a) ? 1.0 : 0.0;
+#pragma unroll
+    for (int t = 0; t < r; ++t) acc -= sL[r * kLP + t] * w[t];
+    w[r] = acc / sL[r * kLP + r];
+  }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) sW[r * kLP + a] = w[r];
+  __syncwarp();
+  return !bad;
+}
+
+__global__ void __launch_bounds__(256) band_factor_kernel(BandSys S) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sL[32 * kLP], sW[32 * kLP], sA[kTileElems], sB[kTileElems];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a = tid & 31, c0 = tid >> 5;
+  for (int k = 0; k < S.NT; ++k) {
+    const int Tk = min(S.T, S.NT - 1 - k);
+    double* col = S.tiles + static_cast<size_t>(k) * S.TPC * kTileElems;
+    // ---- phase A: diagonal block (redundantly in every CTA) + panel solve X = P L^-T = P W^T
+    if (warp == 0) {
+      const bool ok = warp_potrf_inv(col, sL, sW);
+      if (!ok && tid == 0 && blockIdx.x == 0) *S.fail = 1;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+      double* Wg = S.Linv + static_cast<size_t>(k) * kTileElems;
+      for (int e = tid; e < kTileElems; e += 256) {
+        const int r = e & 31, m = e >> 5;
+        col[e] = sL[r * kLP + m];
+        Wg[e] = sW[r * kLP + m];
+      }
+    }
+    const int npanel = Tk + S.RB;
+    for (int q = blockIdx.x; q < npanel; q += gridDim.x) {
+      double* tile = col + static_cast<size_t>(q < Tk ? q + 1 : S.T + 1 + (q - Tk)) * kTileElems;
+      for (int e = tid; e < kTileElems; e += 256) sA[e] = tile[e];
+      __syncthreads();
+      double out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + 8 * j;
+        double acc = 0.0;
+        for (int m = 0; m <= c; ++m) acc += sA[a + 32 * m] * sW[c * kLP + m];
+        out[j] = acc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tile[a + 32 * (c0 + 8 * j)] = out[j];
+    }
+    grid.sync();
+    // ---- phase B: trailing update
+    const int nband = Tk * (Tk + 1) / 2, nbord = S.RB * Tk, ncorn = S.RB * (S.RB + 1) / 2;
+    for (int o = blockIdx.x; o < nband + nbord + ncorn; o += gridDim.x) {
+      const double *Xi, *Xj;
+      double* dst;
+      int ld = 32;
+      if (o < nband) {
+        int i = static_cast<int>((sqrtf(8.f * o + 1.f) - 1.f) * 0.5f);
+        while (i * (i + 1) / 2 > o) --i;
+        while ((i + 1) * (i + 2) / 2 <= o) ++i;
+        const int j = o - i * (i + 1) / 2;  // 0 <= j <= i < Tk ; tile rows i+1, j+1
+        Xi = col + static_cast<size_t>(i + 1) * kTileElems;
+        Xj = col + static_cast<size_t>(j + 1) * kTileElems;
+        dst = S.tiles + (static_cast<size_t>(k + j + 1) * S.TPC + (i - j)) * kTileElems;
+      } else if (o < nband + nbord) {
+        const int oo = o - nband;
+        const int rb = oo / Tk, j = oo % Tk;
+        Xi = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems;
+        Xj = col + static_cast<size_t>(j + 1) * kTileElems;
+        dst = S.tiles + (static_cast<size_t>(k + j + 1) * S.TPC + S.T + 1 + rb) * kTileElems;
+      } else {
+        const int oo = o - nband - nbord;
+        int i = static_cast<int>((sqrtf(8.f * oo + 1.f) - 1.f) * 0.5f);
+        while (i * (i + 1) / 2 > oo) --i;
+        while ((i + 1) * (i + 2) / 2 <= oo) ++i;
+        const int j = oo - i * (i + 1) / 2;
+        Xi = col + static_cast<size_t>(S.T + 1 + i) * kTileElems;
+        Xj = col + static_cast<size_t>(S.T + 1 + j) * kTileElems;
+        dst = S.C + 32 * i + static_cast<size_t>(S.ldc) * 32 * j;
+        ld = S.ldc;
+      }
+      for (int e = tid; e < kTileElems; e += 256) { sA[e] = Xi[e]; sB[e] = Xj[e]; }
+      __syncthreads();
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int m = 0; m < 32; ++m) {
+        const double xa = sA[a + 32 * m];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += xa * sB[c0 + 8 * j + 32 * m];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[a + static_cast<size_t>(ld) * (c0 + 8 * j)] -= acc[j];
+      __syncthreads();
+    }
+    grid.sync();
+  }
+}
+
+// dense Cholesky of the border Schur complement S (nbo x nbo, lower, column-major ld = ldc) with the rhs carried as row nbo,
+// then x2 = L^-T z2.  One CTA.
+__global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
+  const int n = S.nbo, ld = S.ldc, tid = threadIdx.x;
+  double* C = S.C;
+  double* x2 = S.x + static_cast<size_t>(S.NT) * 32;
+  __shared__ double xs[1024];
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    double d = C[j + static_cast<size_t>(ld) * j];
+    if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) bad = 1; d = 1.0; }
+    const double s = sqrt(d);
+    __syncthreads();
+    if (tid == 0) C[j + static_cast<size_t>(ld) * j] = s;
+    for (int i = j + 1 + tid; i <= n; i += 256) C[i + static_cast<size_t>(ld) * j] /= s;
+    __syncthreads();
+    const int m = n - j;  // rows j+1..n (n = rhs row), columns j+1..n-1
+    for (int e = tid; e < m * m; e += 256) {
+      const int i = j + 1 + e % m, c = j + 1 + e / m;
+      if (c <= i && c < n) C[i + static_cast<size_t>(ld) * c] -= C[i + static_cast<size_t>(ld) * j] * C[c + static_cast<size_t>(ld) * j];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < ld; i += 256) xs[i] = 0.0;
+  __syncthreads();
+  if (tid < 32) {
+    for (int c = n - 1; c >= 0; --c) {
+      double part = 0.0;
+      for (int i = c + 1 + tid; i < n; i += 32) part += C[i + static_cast<size_t>(ld) * c] * xs[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+      if (tid == 0) xs[c] = (C[n + static_cast<size_t>(ld) * c] - part) / C[c + static_cast<size_t>(ld) * c];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ld; i += 256) x2[i] = xs[i];
+  if (tid == 0 && bad) *S.fail = 1;
+}
+
+// x1 = L11^-T (z1 - L21^T x2): backward block substitution.  One CTA of 32 warps.
+__global__ void __launch_bounds__(1024) band_backsolve_kernel(BandSys S) {
+  __shared__ double red[32 * 32], x2s[1024], sv[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* x = S.x;
+  for (int i = tid; i < S.ldc; i += 1024) x2s[i] = x[static_cast<size_t>(S.NT) * 32 + i];
+  __syncthreads();
+  const int zrb = S.nbo >> 5, zrow = S.nbo & 31;
+  for (int k = S.NT - 1; k >= 0; --k) {
+    const int Tk = min(S.T, S.NT - 1 - k);
+    const double* col = S.tiles + static_cast<size_t>(k) * S.TPC * kTileElems;
+    const int ntile = Tk + S.RB;
+    double acc = 0.0;
+    for (int q = warp; q < ntile; q += 32) {
+      const double* tile = col + static_cast<size_t>(q < Tk ? q + 1 : S.T + 1 + (q - Tk)) * kTileElems + 32 * lane;
+      const double* xv = q < Tk ? x + static_cast<size_t>(k + q + 1) * 32 : x2s + 32 * (q - Tk);
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) acc += tile[r] * xv[r];
+    }
+    red[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double v = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + 32 * lane];
+      const int nw = ntile < 32 ? ntile : 32;
+      for (int w = 0; w < nw; ++w) v -= red[w * 32 + lane];
+      sv[lane] = v;
+      __syncwarp();
+      const double* W = S.Linv + static_cast<size_t>(k) * kTileElems + 32 * lane;  // column `lane` of W
+      double xk = 0.0;
+      for (int m = lane; m < 32; ++m) xk += W[m] * sv[m];
+      x[static_cast<size_t>(k) * 32 + lane] = xk;
+    }
+    __syncthreads();
+  }
+}
+
+// y (tangent order) from the solver's x, delta = S y, and the scalars of the step: [2] y.g_s  [3] sum D2 y^2  [4] #non-finite
+__global__ void __launch_bounds__(256) finish_step_kernel(BandSys A, int nt, const double* __restrict__ scale, const double* __restrict__ diag,
+                                                          double inv_radius, const double* __restrict__ g, double* __restrict__ y,
+                                                          double* __restrict__ delta, double* __restrict__ scal) {
+  double yg = 0.0, dy = 0.0, nf = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const double v = t < A.nb ? A.x[t] : A.x[static_cast<size_t>(A.NT) * 32 + (t - A.nb)];
+    y[t] = v;
+    delta[t] = v * scale[t];
+    if (!isfinite(v)) nf += 1.0;
+    yg += v * g[t] * scale[t];
+    dy += diag[t] * inv_radius * v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { yg += __shfl_xor_sync(FULL, yg, o); dy += __shfl_xor_sync(FULL, dy, o); nf += __shfl_xor_sync(FULL, nf, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(scal + 2, yg); atomicAdd(scal + 3, dy); if (nf != 0.0) atomicAdd(scal + 4, nf); }
+}
+
+// ---- parameter update (Program::Plus): EigenQuaternionParameterization + bounds projection -------------------------------------
+__global__ void __launch_bounds__(256) plus_kernel(const FreeBlock* __restrict__ blocks, int n_blocks, const double* __restrict__ X,
+                                                   const double* __restrict__ delta, double step, double sign, double* __restrict__ XC) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const FreeBlock fb = blocks[b];
+  const double* x = X + fb.off;
+  double* o = XC + fb.off;
+  const double* d = delta + fb.pos;
+  const double f = step * sign;
+  if (fb.kind == 1) {  // q+ = [sin|d|/|d| d, cos|d|] * q
+    const double d0 = f * d[0], d1 = f * d[1], d2 = f * d[2];
+    const double n = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    if (n > 0.0) {
+      const double s = sin(n) / n;
+      const Q4 r = qmul(q4(s * d0, s * d1, s * d2, cos(n)), q4(x[0], x[1], x[2], x[3]));
+      o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+    } else { o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3]; }
+  } else {
+    for (int c = 0; c < fb.size; ++c) {
+      double v = x[c] + f * d[c];
+      if (fb.kind == 2) v = fmax(v, 0.0);  // inverse depth lower bound (K/measurements/static_rscamera_measurement.h:185)
+      o[c] = v;
+    }
+  }
+}
+
+// scal[5] += sum (x - xc)^2 ; scal[6] = max |x - xc| ; scal[7] += sum x^2   over the free blocks
+__global__ void __launch_bounds__(256) diff_kernel(const FreeBlock* __restrict__ blocks, int n_blocks, const double* __restrict__ X,
+                                                   const double* __restrict__ XC, double* __restrict__ scal) {
+  double ss = 0.0, mx = 0.0, xx = 0.0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += gridDim.x * blockDim.x) {
+    const FreeBlock fb = blocks[b];
+    for (int c = 0; c < fb.size; ++c) {
+      const double xv = X[fb.off + c], dv = xv - XC[fb.off + c];
+      ss += dv * dv; mx = fmax(mx, fabs(dv)); xx += xv * xv;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(FULL, ss, o); xx += __shfl_xor_sync(FULL, xx, o); mx = fmax(mx, __shfl_xor_sync(FULL, mx, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(scal + 5, ss); atomicAdd(scal + 7, xx);
+    atomicMax(reinterpret_cast<unsigned long long*>(scal + 6), static_cast<unsigned long long>(__double_as_longlong(mx)));
+  }
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) s += a[t] * b[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+static int coop_grid_limit(lvi_ctx* ctx) {
+  static int limit = 0;
+  if (!limit) {
+    int per_sm = 0;
+    LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band_factor_kernel, 256, 0));
+    limit = std::max(1, std::min(per_sm, 1) * ctx->sm_count);
+  }
+  return limit;
+}
+
+void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
+  cudaStream_t st = ctx->stream;
+  LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), st));
+  if (A.NT > 0) {
+    const int ops = A.T * (A.T + 1) / 2 + A.RB * A.T + A.RB * (A.RB + 1) / 2;
+    int grid = std::min(coop_grid_limit(ctx), std::max(1, ops));
+    void* args[] = {&A};
+    LVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band_factor_kernel), dim3(grid), dim3(256), args, 0, st));
+    ++ctx->launches;
+  }
+  LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
+  if (A.NT > 0) LVI_LAUNCH(ctx, band_backsolve_kernel, 1, 1024, 0, A);
+}
+
+struct Scalars {  // mirrors p->scal
+  double cost, cand_cost, yg, d2y2, nonfinite, diff_ss, diff_max, xnorm_ss, gd;
+};
+
+static void allreduce_sum(lvi_ctx* ctx, double* buf, size_t count) {
+  if (ctx->world <= 1 || count == 0) return;
+  ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl), ctx->stream);
+  LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+}
+
+static void read_scalars(lvi_problem* p, Scalars& s) {
+  cudaStream_t st = p->ctx->stream;
+  LVI_CUDA(cudaMemcpyAsync(p->h_scal, p->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LVI_CUDA(cudaStreamSynchronize(st));
+  const double* h = p->h_scal;
+  s.cost = h[0]; s.cand_cost = h[1]; s.yg = h[2]; s.d2y2 = h[3]; s.nonfinite = h[4]; s.diff_ss = h[5]; s.diff_max = h[6]; s.xnorm_ss = h[7]; s.gd = h[8];
+}
+
+// residuals + Jacobians + normal equations at X (+ NCCL all-reduce of {H, g, cost} across the data-parallel ranks)
+static void linearize(lvi_problem* p) {
+  problem_linearize(p, nullptr);
+  lvi_ctx* ctx = p->ctx;
+  if (ctx->world > 1) {
+    allreduce_sum(ctx, p->H_tiles.p, p->H_tiles.n);
+    allreduce_sum(ctx, p->H_C.p, p->H_C.n);
+    allreduce_sum(ctx, p->g.p, p->g.n);
+    allreduce_sum(ctx, p->scal.p, 1);
+  }
+}
+static void trial_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active, bool inactive) {
+  problem_cost(p, x_d, cost_d, active, inactive);
+  allreduce_sum(p->ctx, cost_d, 1);
+}
+
+static inline int blocks_for(int n) { return std::max(1, (n + 255) / 256); }
+
+static void compute_step(lvi_problem* p, double radius) {  // A = S H S + D^2 ; factor ; solve ; y, delta, scalars
+  lvi_ctx* ctx = p->ctx;
+  const int ntile = p->A.NT * p->A.TPC;
+  const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
+  LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, 1.0 / radius, p->g.p);
+  band_factor_solve(ctx, p->A);
+  LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), ctx->stream));
+  LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p, 1.0 / radius, p->g.p,
+             p->y.p, p->delta.p, p->scal.p);
+}
+
+static void apply_plus(lvi_problem* p, const double* delta_d, double step, double sign) {
+  cudaStream_t st = p->ctx->stream;
+  LVI_CUDA(cudaMemcpyAsync(p->XC.p, p->X.p, sizeof(double) * p->nx, cudaMemcpyDeviceToDevice, st));
+  if (p->n_blocks) LVI_LAUNCH(p->ctx, plus_kernel, blocks_for(p->n_blocks), 256, 0, p->blocks.p, p->n_blocks, p->X.p, delta_d, step, sign, p->XC.p);
+}
+static void diff_norms(lvi_problem* p) {  // scal[5..7]
+  LVI_CUDA(cudaMemsetAsync(p->scal.p + 5, 0, 3 * sizeof(double), p->ctx->stream));
+  if (p->n_blocks) LVI_LAUNCH(p->ctx, diff_kernel, std::min(blocks_for(p->n_blocks), p->ctx->sm_count * 4), 256, 0, p->blocks.p, p->n_blocks, p->X.p, p->XC.p, p->scal.p);
+}
+
+static void refresh_diag(lvi_problem* p, DBuf<double>& dH, const lvi_solve_options& o) {
+  LVI_LAUNCH(p->ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->nt, dH.p);
+  LVI_LAUNCH(p->ctx, lm_diag_kernel, blocks_for(p->nt), 256, 0, dH.p, p->scale.p, p->nt, o.min_lm_diagonal, o.max_lm_diagonal, p->diag.p);
+}
+
+static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summary& S) {
+  const auto T0 = std::chrono::steady_clock::now();
+  std::memset(&S, 0, sizeof(S));
+  lvi_ctx* ctx = p->ctx;
+  cudaStream_t st = ctx->stream;
+  problem_ensure_solver_buffers(p);
+  const int nt = p->nt;
+  DBuf<double> dH(std::max(nt, 1));
+  Scalars sc{};
+  cudaEvent_t e0, e1;
+  LVI_CUDA(cudaEventCreate(&e0)); LVI_CUDA(cudaEventCreate(&e1));
+  float tj = 0, tl = 0, ms = 0;
+  auto tic = [&] { LVI_CUDA(cudaEventRecord(e0, st)); };
+  auto toc = [&](float& accu) { LVI_CUDA(cudaEventRecord(e1, st)); LVI_CUDA(cudaEventSynchronize(e1)); LVI_CUDA(cudaEventElapsedTime(&ms, e0, e1)); accu += ms; };
+
+  // fixed cost of the residual blocks whose parameter blocks are all constant (dropped from the reduced program)
+  trial_cost(p, p->X.p, p->scal.p + 1, false, true);
+  read_scalars(p, sc);
+  const double fixed_cost = sc.cand_cost;
+  tic(); linearize(p); toc(tj);
+  read_scalars(p, sc);
+  double x_cost = sc.cost;
+  S.initial_cost = x_cost + fixed_cost; S.fixed_cost = fixed_cost;
+  S.num_residual_blocks = p->L.n_res_blocks; S.num_residuals = p->L.n_res; S.num_effective_parameters = nt;
+  S.band_width = p->L.bw; S.border_width = p->L.nbo;
+  // Jacobi scaling at iteration 0
+  LVI_LAUNCH(ctx, diag_kernel, blocks_for(nt), 256, 0, p->H, nt, dH.p);
+  LVI_LAUNCH(ctx, scale_init_kernel, blocks_for(nt), 256, 0, dH.p, nt, o.jacobi_scaling, p->scale.p);
+  auto grad_max_norm = [&]() {  // || x - Plus(x, -g) ||_inf (with bounds projection)
+    apply_plus(p, p->g.p, 1.0, -1.0);
+    diff_norms(p);
+    read_scalars(p, sc);
+    return sc.diff_max;
+  };
+  double gmax = grad_max_norm();
+  double x_norm = std::sqrt(sc.xnorm_ss);
+  double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int it = 0, invalid = 0;
+  auto log_iter = [&](double cost, double change, double gm, double step, bool ok) {
+    if (S.n_log < LVI_MAX_ITER_LOG) {
+      const int k = S.n_log++;
+      S.log_cost[k] = cost; S.log_cost_change[k] = change; S.log_gradient_max_norm[k] = gm; S.log_step_norm[k] = step; S.log_radius[k] = radius; S.log_successful[k] = ok;
+    }
+  };
+  log_iter(x_cost + fixed_cost, 0, gmax, 0, true);
+  S.termination_type = LVI_NO_CONVERGENCE;
+  if (o.verbose) std::printf("[lvi] iter %3d cost %.9e |g| %.3e\n", 0, x_cost, gmax);
+  bool done = gmax <= o.gradient_tolerance;
+  if (done) S.termination_type = LVI_CONVERGENCE;
+  while (!done) {
+    if (it >= o.max_num_iterations) break;
+    ++it;
+    if (!reuse_diagonal) refresh_diag(p, dH, o);
+    tic();
+    compute_step(p, radius);
+    toc(tl);
+    read_scalars(p, sc);
+    int failed = 0;
+    LVI_CUDA(cudaMemcpy(&failed, p->fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+    reuse_diagonal = true;
+    bool step_valid = !failed && sc.nonfinite == 0.0;
+    // model_cost_change = -(J y).(r + J y / 2) = -y.g_s - y^T H_s y / 2, with H_s y = -g_s - D^2 y
+    const double model_cost_change = -0.5 * sc.yg + 0.5 * sc.d2y2;
+    if (step_valid && !(model_cost_change > 0.0)) step_valid = false;
+    if (!step_valid) {  // HandleInvalidStep
+      ++invalid;
+      if (invalid >= o.max_num_consecutive_invalid_steps) { S.termination_type = LVI_FAILURE; break; }
+      radius *= 0.5;
+      ++S.num_unsuccessful_steps;
+      log_iter(x_cost + fixed_cost, 0, gmax, 0, false);
+      continue;
+    }
+    invalid = 0;
+    apply_plus(p, p->delta.p, 1.0, 1.0);
+    tic();
+    trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
+    toc(tj);
+    read_scalars(p, sc);
+    double cand_cost = sc.cand_cost;
+    if (p->L.constrained) {  // projected step: Armijo check along delta (ceres DoLineSearch)
+      LVI_CUDA(cudaMemsetAsync(p->scal.p + 8, 0, sizeof(double), st));
+      LVI_LAUNCH(ctx, dot_kernel, std::min(blocks_for(nt), ctx->sm_count * 4), 256, 0, p->g.p, p->delta.p, nt, p->scal.p + 8);
+      read_scalars(p, sc);
+      const double gd = sc.gd;
+      double step = 1.0;
+      int ls = 0;
+      while (cand_cost > x_cost + 1e-4 * step * gd && ls < 20 && step > 1e-9) {
+        double ns = -gd * step * step / (2.0 * (cand_cost - x_cost - gd * step));
+        ns = std::min(std::max(ns, 1e-3 * step), 0.6 * step);
+        step = ns; ++ls;
+        apply_plus(p, p->delta.p, step, 1.0);
+        trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
+        read_scalars(p, sc);
+        cand_cost = sc.cand_cost;
+      }
+    }
+    diff_norms(p);
+    read_scalars(p, sc);
+    const double step_norm = std::sqrt(sc.diff_ss);
+    const double cost_change = x_cost - cand_cost;
+    if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
+      S.termination_type = LVI_CONVERGENCE; log_iter(x_cost + fixed_cost, cost_change, gmax, step_norm, false); break;
+    }
+    if (std::fabs(cost_change) <= o.function_tolerance * x_cost) {
+      S.termination_type = LVI_CONVERGENCE; log_iter(x_cost + fixed_cost, cost_change, gmax, step_norm, false); break;
+    }
+    const double rel = cost_change / model_cost_change;
+    if (rel > o.min_relative_decrease) {  // HandleSuccessfulStep
+      LVI_CUDA(cudaMemcpyAsync(p->X.p, p->XC.p, sizeof(double) * p->nx, cudaMemcpyDeviceToDevice, st));
+      x_cost = cand_cost;
+      tic(); linearize(p); toc(tj);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(o.max_trust_region_radius, radius);
+      decrease_factor = 2.0; reuse_diagonal = false;
+      ++S.num_successful_steps;
+      gmax = grad_max_norm();
+      x_norm = std::sqrt(sc.xnorm_ss);
+      log_iter(x_cost + fixed_cost, cost_change, gmax, step_norm, true);
+      if (o.verbose) std::printf("[lvi] iter %3d cost %.9e change %.3e |g| %.3e |step| %.3e radius %.3e\n", it, x_cost, cost_change, gmax, step_norm, radius);
+      if (gmax <= o.gradient_tolerance) { S.termination_type = LVI_CONVERGENCE; break; }
+    } else {  // HandleUnsuccessfulStep
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      ++S.num_unsuccessful_steps;
+      log_iter(x_cost + fixed_cost, cost_change, gmax, step_norm, false);
+      if (o.verbose) std::printf("[lvi] iter %3d REJECTED cost %.9e change %.3e radius %.3e\n", it, cand_cost, cost_change, radius);
+    }
+    if (radius <= o.min_trust_region_radius) { S.termination_type = LVI_CONVERGENCE; break; }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  problem_download_params(p);
+  S.num_iterations = it;
+  S.final_cost = x_cost + fixed_cost;
+  S.time_jacobian_ms = tj; S.time_linear_solve_ms = tl;
+  S.time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+}
+
+}  // namespace lvi
+
+using namespace lvi;
+
+extern "C" {
+
+int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary) {
+  return guarded([&] {
+    LVI_REQUIRE(p && opt && summary, LVI_ERR_INVALID, "lvi_problem_solve: null argument");
+    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    solve_lm(p, *opt, *summary);
+  });
+}
+
+// One LM iteration's worth of work, `iters` times, without acceptance: linearise, damped system, factor + solve, candidate, trial cost.
+int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase) {
+  return guarded([&] {
+    LVI_REQUIRE(p && iters > 0, LVI_ERR_INVALID, "lvi_problem_bench_iterations: bad argument");
+    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    lvi_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    problem_ensure_solver_buffers(p);
+    lvi_solve_options o;
+    lvi_solve_options_default(&o);
+    DBuf<double> dH(std::max(p->nt, 1));
+    cudaEvent_t ev[5];
+    for (auto& e : ev) LVI_CUDA(cudaEventCreate(&e));
+    float acc[4] = {0, 0, 0, 0};
+    linearize(p);
+    LVI_LAUNCH(ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->nt, dH.p);
+    LVI_LAUNCH(ctx, scale_init_kernel, blocks_for(p->nt), 256, 0, dH.p, p->nt, 1, p->scale.p);
+    for (int it = 0; it < iters; ++it) {
+      LVI_CUDA(cudaEventRecord(ev[0], st));
+      linearize(p);
+      LVI_CUDA(cudaEventRecord(ev[1], st));
+      refresh_diag(p, dH, o);
+      const int ntile = p->A.NT * p->A.TPC;
+      const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
+      LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, 1.0 / o.initial_trust_region_radius, p->g.p);
+      LVI_CUDA(cudaEventRecord(ev[2], st));
+      band_factor_solve(ctx, p->A);
+      LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), st));
+      LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p,
+                 1.0 / o.initial_trust_region_radius, p->g.p, p->y.p, p->delta.p, p->scal.p);
+      LVI_CUDA(cudaEventRecord(ev[3], st));
+      apply_plus(p, p->delta.p, 1.0, 1.0);
+      trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
+      diff_norms(p);
+      LVI_CUDA(cudaEventRecord(ev[4], st));
+      Scalars sc;
+      read_scalars(p, sc);  // the per-iteration host decision point of the LM loop
+      for (int k = 0; k < 4; ++k) { float ms = 0; LVI_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_per_phase) for (int k = 0; k < 4; ++k) ms_per_phase[k] = acc[k] / iters;
+  });
+}
+
+// test hook: solve a dense SPD system given in band+border form through the tile solver.
+//   A_dense [n x n] row-major symmetric, n = nb + nbo, entries outside the band (|i-j| > bw within the first nb) must be zero.
+int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_dense, const double* rhs, double* x_out) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && A_dense && rhs && x_out && nb >= 0 && nbo >= 0 && nb + nbo > 0, LVI_ERR_INVALID, "lvi_band_solve_dense: bad argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Lowered L;
+    L.nb = nb; L.nbo = nbo; L.bw = bw;
+    BandSys S{};
+    S.nb = nb; S.nbo = nbo;
+    S.NT = (nb + 31) / 32;
+    S.T = S.NT > 0 ? std::min(S.NT - 1, (bw + 31) / 32) : 0;
+    S.RB = (nbo + 1 + 31) / 32; S.TPC = S.T + 1 + S.RB; S.ldc = S.RB * 32;
+    const size_t ntile = static_cast<size_t>(S.NT) * S.TPC;
+    std::vector<double> ht(std::max<size_t>(ntile * kTileElems, 1), 0.0), hc(static_cast<size_t>(S.ldc) * S.ldc, 0.0);
+    const int n = nb + nbo;
+    auto at = [&](int i, int j) { return A_dense[static_cast<size_t>(i) * n + j]; };
+    for (int J = 0; J < S.NT; ++J)
+      for (int q = 0; q < S.TPC; ++q)
+        for (int b = 0; b < 32; ++b)
+          for (int a = 0; a < 32; ++a) {
+            const int j = J * 32 + b;
+            double v = 0.0;
+            if (q <= S.T) {
+              const int i = (J + q) * 32 + a;
+              if (J + q >= S.NT) continue;
+              if (i < nb && j < nb) { if (i >= j) v = at(i, j); }
+              else if (i == j) v = 1.0;
+            } else if (j < nb) {
+              const int bi = (q - S.T - 1) * 32 + a;
+              if (bi < nbo) v = at(nb + bi, j);
+              else if (bi == nbo) v = rhs[j];
+            }
+            ht[((static_cast<size_t>(J) * S.TPC + q) << 10) + (b << 5) + a] = v;
+          }
+    for (int bj = 0; bj < S.ldc; ++bj)
+      for (int bi = 0; bi < S.ldc; ++bi) {
+        double v = 0.0;
+        if (bi < nbo && bj < nbo) { if (bi >= bj) v = at(nb + bi, nb + bj); }
+        else if (bi == nbo && bj < nbo) v = rhs[nb + bj];
+        else if (bi == bj) v = 1.0;
+        hc[bi + static_cast<size_t>(S.ldc) * bj] = v;
+      }
+    DBuf<double> tiles(ht.size()), C(hc.size()), Linv(std::max<size_t>(static_cast<size_t>(S.NT) * kTileElems, 1)), x(static_cast<size_t>(S.NT) * 32 + S.ldc);
+    DBuf<int> fail(4);
+    tiles.upload(ht.data(), ht.size(), st); C.upload(hc.data(), hc.size(), st);
+    S.tiles = tiles.p; S.C = C.p; S.Linv = Linv.p; S.x = x.p; S.fail = fail.p;
+    band_factor_solve(ctx, S);
+    std::vector<double> hx(x.n);
+    int hf = 0;
+    x.download(hx.data(), x.n, st);
+    LVI_CUDA(cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LVI_CUDA(cudaStreamSynchronize(st));
+    LVI_REQUIRE(hf == 0, LVI_ERR_NUMERIC, "Cholesky breakdown");
+    for (int t = 0; t < n; ++t) x_out[t] = t < nb ? hx[t] : hx[static_cast<size_t>(S.NT) * 32 + (t - nb)];
+  });
+}
+
+}  // extern "C"

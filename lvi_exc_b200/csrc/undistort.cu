@@ -1,0 +1,223 @@
+// undistort.cu — scan de-skew / map assembly on sm_100a (the step right before the map build).
+//
+// Replaces ScanUndistortion::undistort (L/include/core/scan_undistortion.h:132-180) with
+// TrajectoryManagerLVI::evaluateLidarPose (L/src/core/trajectory_manager_lvi.cpp:398-408): one spline pose evaluation
+// per raw point (17 M per pass at 60 s; serial, heap-allocating on the CPU), and pcl::transformPointCloud with a float
+// 4x4 (scan_undistortion.h:111, L/src/core/lidar_odometry.cpp:98).
+//   undistort_target_kernel : pose of the LiDAR at each scan's target time (own stamp or the map time)
+//   undistort_kernel        : thread per point, 32 B coalesced load (PointXYZIT) -> closed-form SO3/R3 spline pose ->
+//                             32 B coalesced store (PointXYZI).  HBM-bound: 64 B/point + cache-resident knots.
+//   transform_kernel        : float 4x4 per scan, evaluated left to right without FMA (bit-exact with Eigen's float path).
+// Compiled with -fmad=false.
+#include "common.cuh"
+#include "spline_math.cuh"
+
+namespace lvi {
+
+struct TrajView {
+  double t0, dt, dt_inv, t_max, toff;
+  int n_knots;
+  const double* r3;   // [n*3]
+  const double* so3;  // [n*4]
+  Q4 qL; V3 pL;
+};
+
+__device__ __forceinline__ bool lidar_pose(const TrajView& T, double t, Q4& q, V3& p) {
+  const double tt = t + T.toff;
+  if (T.t0 > tt || T.t_max <= tt || !(tt == tt)) return false;  // evaluateLidarPose range test (trajectory_manager_lvi.cpp:401-403)
+  const double s = (tt - T.t0) / T.dt;
+  int i0 = static_cast<int>(floor(s));
+  if (i0 < 0 || i0 > T.n_knots - 4) return false;
+  const double u = s - i0;
+  So3Eval e;
+  so3_spline_eval(T.so3 + 4 * i0, u, T.dt_inv, false, false, e);
+  double B[4];
+  basis_pos(u, B);
+  const V3 pI = r3_spline(T.r3 + 3 * i0, B);
+  q = qmul(e.q, T.qL);                 // q_LtoG = q_ItoG * q_LtoI
+  p = qrot(e.q, T.pL) + pI;            // p_LinG = q_ItoG * p_LinI + p_IinG
+  return true;
+}
+
+struct TargetPose { Q4 q; V3 p; int ok; int pad; };
+
+__global__ void undistort_target_kernel(TrajView T, const double* __restrict__ target_time, int n_scans, TargetPose* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  TargetPose tp;
+  tp.q = q4(0, 0, 0, 1); tp.p = v3(0, 0, 0); tp.pad = 0;
+  tp.ok = lidar_pose(T, target_time[s], tp.q, tp.p) ? 1 : 0;
+  out[s] = tp;
+}
+
+__global__ void __launch_bounds__(256) undistort_kernel(TrajView T, const lvi_point_xyzit* __restrict__ raw, int64_t n, int64_t pts_per_scan,
+                                                        const TargetPose* __restrict__ target, int correct_position, float4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(raw + i));       // x y z pad
+    const float4 b = __ldg(reinterpret_cast<const float4*>(raw + i) + 1);   // intensity pad2 timestamp(lo,hi)
+    const double ts = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));
+    const TargetPose tp = target[i / pts_per_scan];
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 1.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!tp.ok || isnan(a.x)) {
+      const float nanv = __int_as_float(0x7fc00000);
+      o0.x = nanv; o0.y = nanv; o0.z = nanv;
+    } else {
+      Q4 qk; V3 pk;
+      if (lidar_pose(T, ts, qk, pk)) {
+        const Q4 q0c = qconj(tp.q);
+        const Q4 q = qmul(q0c, qk);
+        V3 po = qrot(q, v3(a.x, a.y, a.z));
+        if (correct_position) po = po + qrot(q0c, pk - tp.p);
+        o0.x = static_cast<float>(po.x); o0.y = static_cast<float>(po.y); o0.z = static_cast<float>(po.z);
+        o1.x = b.x;
+      }  // else: the reference leaves the default-constructed point (zeros)
+    }
+    out[2 * i] = o0;
+    out[2 * i + 1] = o1;
+  }
+}
+
+// IMU pose of the trajectory at arbitrary times (SplitTrajectory::Evaluate, K/trajectories/split_trajectory.h:41-58), used by
+// the landmark association (L/src/core/surfel_association.cpp:161-195 evaluates the camera pose per landmark).
+__global__ void traj_eval_kernel(TrajView T, const double* __restrict__ t, int64_t n, double* __restrict__ pos, double* __restrict__ quat,
+                                 unsigned char* __restrict__ valid) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  TrajView Ti = T;
+  Ti.qL = q4(0, 0, 0, 1); Ti.pL = v3(0, 0, 0); Ti.toff = 0.0;
+  Q4 q = q4(0, 0, 0, 1); V3 p = v3(0, 0, 0);
+  const bool ok = lidar_pose(Ti, t[i], q, p);
+  pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
+  quat[4 * i] = q.x; quat[4 * i + 1] = q.y; quat[4 * i + 2] = q.z; quat[4 * i + 3] = q.w;
+  valid[i] = ok ? 1 : 0;
+}
+
+struct Mat34f { float m[12]; };
+
+__global__ void __launch_bounds__(256) transform_kernel(const float4* __restrict__ in, int64_t n, int64_t pts_per_scan, const Mat34f* __restrict__ poses,
+                                                        float4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(in + 2 * i);
+    const float4 b = __ldg(in + 2 * i + 1);
+    const Mat34f& M = poses[i / pts_per_scan];
+    float4 o;
+    o.x = M.m[0] * a.x + M.m[1] * a.y + M.m[2] * a.z + M.m[3];
+    o.y = M.m[4] * a.x + M.m[5] * a.y + M.m[6] * a.z + M.m[7];
+    o.z = M.m[8] * a.x + M.m[9] * a.y + M.m[10] * a.z + M.m[11];
+    o.w = 1.f;
+    out[2 * i] = o;
+    out[2 * i + 1] = make_float4(b.x, 0.f, 0.f, 0.f);
+  }
+}
+
+static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_point_xyzit* raw_d, int n_scans, int64_t pts_per_scan,
+                             const double* target_time_h, int correct_position, void* out_d, int* n_bad_targets) {
+  LVI_REQUIRE(d->r3_knots && d->so3_knots && d->n_knots >= 4, LVI_ERR_INVALID, "lvi_undistort: trajectory needs both splines and >= 4 knots");
+  LVI_REQUIRE(n_scans > 0 && pts_per_scan > 0, LVI_ERR_INVALID, "lvi_undistort: empty batch");
+  cudaStream_t st = ctx->stream;
+  const int n = d->n_knots;
+  DBuf<double> r3(3 * static_cast<size_t>(n)), so3(4 * static_cast<size_t>(n)), tt(n_scans);
+  r3.upload(d->r3_knots, r3.n, st); so3.upload(d->so3_knots, so3.n, st); tt.upload(target_time_h, n_scans, st);
+  TrajView T;
+  T.t0 = d->t0; T.dt = d->dt; T.dt_inv = 1.0 / d->dt; T.t_max = d->t0 + (n - 3) * d->dt; T.toff = d->lidar_toff; T.n_knots = n;
+  T.r3 = r3.p; T.so3 = so3.p;
+  static const double ident[4] = {0, 0, 0, 1}, zero[3] = {0, 0, 0};
+  const double* lq = d->lidar_q ? d->lidar_q : ident; const double* lp = d->lidar_p ? d->lidar_p : zero;
+  T.qL = q4(lq[0], lq[1], lq[2], lq[3]); T.pL = v3(lp[0], lp[1], lp[2]);
+  DBuf<TargetPose> tp(n_scans);
+  LVI_LAUNCH(ctx, undistort_target_kernel, (n_scans + 127) / 128, 128, 0, T, tt.p, n_scans, tp.p);
+  const int64_t np = static_cast<int64_t>(n_scans) * pts_per_scan;
+  LVI_LAUNCH(ctx, undistort_kernel, grid_for(np, 256, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
+             static_cast<float4*>(out_d));
+  std::vector<TargetPose> h(n_scans);
+  tp.download(h.data(), n_scans, st);
+  LVI_CUDA(cudaStreamSynchronize(st));
+  int bad = 0;
+  for (const auto& t : h) bad += t.ok ? 0 : 1;
+  if (n_bad_targets) *n_bad_targets = bad;
+}
+
+static void transform_device(lvi_ctx* ctx, const void* in_d, int n_scans, int64_t pts_per_scan, const double* poses_h, void* out_d) {
+  LVI_REQUIRE(n_scans > 0 && pts_per_scan > 0, LVI_ERR_INVALID, "lvi_transform_scans: empty batch");
+  std::vector<Mat34f> hm(n_scans);
+  for (int s = 0; s < n_scans; ++s)
+    for (int k = 0; k < 12; ++k) hm[s].m[k] = static_cast<float>(poses_h[16 * s + k]);  // odom_data.pose double -> float
+  DBuf<Mat34f> pm(n_scans);
+  pm.upload(hm.data(), n_scans, ctx->stream);
+  const int64_t np = static_cast<int64_t>(n_scans) * pts_per_scan;
+  LVI_LAUNCH(ctx, transform_kernel, grid_for(np, 256, ctx->sm_count, 8), 256, 0, static_cast<const float4*>(in_d), np, pts_per_scan, pm.p,
+             static_cast<float4*>(out_d));
+  LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace lvi
+
+using namespace lvi;
+
+extern "C" {
+
+int lvi_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw_d, int32_t n_scans, int64_t pts_per_scan,
+                    const double* target_time, int correct_position, void* out_xyzi_d, int32_t* n_bad_targets) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && traj && scans_raw_d && target_time && out_xyzi_d, LVI_ERR_INVALID, "lvi_undistort_d: null argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    undistort_device(ctx, traj, scans_raw_d, n_scans, pts_per_scan, target_time, correct_position, out_xyzi_d, n_bad_targets);
+  });
+}
+
+int lvi_undistort(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw, int32_t n_scans, int64_t pts_per_scan,
+                  const double* target_time, int correct_position, void* out_xyzi, int32_t* n_bad_targets) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && traj && scans_raw && target_time && out_xyzi, LVI_ERR_INVALID, "lvi_undistort: null argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    const size_t np = static_cast<size_t>(n_scans) * pts_per_scan;
+    DBuf<lvi_point_xyzit> raw_d(np);
+    DBuf<char> out_d(np * 32);
+    LVI_CUDA(cudaMemcpyAsync(raw_d.p, scans_raw, np * sizeof(lvi_point_xyzit), cudaMemcpyHostToDevice, ctx->stream));
+    undistort_device(ctx, traj, raw_d.p, n_scans, pts_per_scan, target_time, correct_position, out_d.p, n_bad_targets);
+    LVI_CUDA(cudaMemcpyAsync(out_xyzi, out_d.p, np * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const double* t, int64_t n, double* pos, double* quat, uint8_t* valid) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && d && t && pos && quat && valid && n > 0, LVI_ERR_INVALID, "lvi_trajectory_evaluate: bad argument");
+    LVI_REQUIRE(d->r3_knots && d->so3_knots && d->n_knots >= 4, LVI_ERR_INVALID, "lvi_trajectory_evaluate: trajectory needs both splines and >= 4 knots");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nk = d->n_knots;
+    DBuf<double> r3(3 * static_cast<size_t>(nk)), so3(4 * static_cast<size_t>(nk)), td(n), pd(3 * static_cast<size_t>(n)), qd(4 * static_cast<size_t>(n));
+    DBuf<unsigned char> vd(n);
+    r3.upload(d->r3_knots, r3.n, st); so3.upload(d->so3_knots, so3.n, st); td.upload(t, n, st);
+    TrajView T;
+    T.t0 = d->t0; T.dt = d->dt; T.dt_inv = 1.0 / d->dt; T.t_max = d->t0 + (nk - 3) * d->dt; T.toff = 0.0; T.n_knots = nk;
+    T.r3 = r3.p; T.so3 = so3.p; T.qL = q4(0, 0, 0, 1); T.pL = v3(0, 0, 0);
+    LVI_LAUNCH(ctx, traj_eval_kernel, static_cast<int>((n + 127) / 128), 128, 0, T, td.p, n, pd.p, qd.p, vd.p);
+    pd.download(pos, pd.n, st); qd.download(quat, qd.n, st); vd.download(valid, n, st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scans, int64_t pts_per_scan, const double* poses, void* out_xyzi_d) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && scans_xyzi_d && poses && out_xyzi_d, LVI_ERR_INVALID, "lvi_transform_scans_d: null argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    transform_device(ctx, scans_xyzi_d, n_scans, pts_per_scan, poses, out_xyzi_d);
+  });
+}
+
+int lvi_transform_scans(lvi_ctx* ctx, const void* scans_xyzi, int32_t n_scans, int64_t pts_per_scan, const double* poses, void* out_xyzi) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && scans_xyzi && poses && out_xyzi, LVI_ERR_INVALID, "lvi_transform_scans: null argument");
+    LVI_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = static_cast<size_t>(n_scans) * pts_per_scan * 32;
+    DBuf<char> in_d(bytes), out_d(bytes);
+    LVI_CUDA(cudaMemcpyAsync(in_d.p, scans_xyzi, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    transform_device(ctx, in_d.p, n_scans, pts_per_scan, poses, out_d.p);
+    LVI_CUDA(cudaMemcpyAsync(out_xyzi, out_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+}  // extern "C"

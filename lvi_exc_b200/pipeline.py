@@ -175,6 +175,15 @@ def extrinsic_errors(calib: CalibParams, gt: dict) -> dict:
                 rot_C=quat_angle(calib.q_CtoI, gt["q_CtoI"]), pos_C=float(np.linalg.norm(calib.p_CinI - gt["p_CinI"])))
 
 
+def _take_scans(scans, keys: np.ndarray):
+    """rows of a [S, ...] scan batch (numpy array or device tensor) selected by a boolean key-scan mask"""
+    idx = np.nonzero(keys)[0]
+    if isinstance(scans, np.ndarray):
+        return scans[idx]
+    import torch  # device tensors are only held, never computed on, by the product path
+    return scans[torch.as_tensor(idx, device=scans.device)]
+
+
 def check_key_scan(poses: np.ndarray) -> np.ndarray:
     """LiDAROdometry::checkKeyScan (L/src/core/lidar_odometry.cpp:107-128): first scan, or moved > 0.2 m, or any of
     yaw/pitch/roll changed by more than 5 (degrees; mathutils::R2ypr returns degrees)."""
@@ -234,7 +243,7 @@ def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bo
     scans_rot = backend.undistort(traj_pd(), seq.scans_raw, None, False)
     scans_in_map = backend.transform(scans_rot, seq.loam_poses)
     keys = check_key_scan(seq.loam_poses)
-    smap = backend.build_surfel_map(scans_in_map[keys].reshape(-1, 8), cfg.ndt_resolution, cfg.plane_lambda_first)
+    smap = backend.build_surfel_map(_take_scans(scans_in_map, keys).reshape(-1, 8), cfg.ndt_resolution, cfg.plane_lambda_first)
     spoints = backend.associate(smap, scans_in_map, seq.scans_raw, cfg.associated_radius, cfg.k_per_ring, cfg.time_downsample)
     out["assoc_counts"] = [len(spoints)]
     # S1
@@ -273,33 +282,37 @@ def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bo
 
 
 def associate_landmarks(mgr: TrajectoryManager, backend, smap, seq, cam_obs, rho, map_time, radius) -> dict:
-    """associateVisualPointsWithPlanes: landmark (ref uv, rho >= 0.05) -> 3-D in the L0 frame -> bbox + dist <= 2*radius;
-    last matching plane wins.  The per-landmark pose evaluations are host-side (<= 1e4 landmarks)."""
+    """associateVisualPointsWithPlanes (L/src/core/surfel_association.cpp:161-214): landmark (ref uv, rho >= 0.05) -> 3-D in
+    the L0 frame via the camera pose at its reference time and the L0 pose -> bbox + dist <= 2*radius; the last matching
+    plane wins.  Pose evaluations and the plane test run on the backend (batched)."""
     c = mgr.calib
     cam = mgr.cam
     q_LtoC = quat_mul(quat_conj(c.q_CtoI), c.q_LtoI)
     t_LinC = quat_rot(quat_conj(c.q_CtoI), c.p_LinI - c.p_CinI)
+    lms = np.nonzero((seq.lm_ref_obs >= 0))[0]
+    t_ref = cam_obs["lm_ref_t0"][lms]
+    keep = (rho[lms] >= 0.05) & (t_ref >= mgr.min_time) & (t_ref < mgr.max_time)
+    lms, t_ref = lms[keep], t_ref[keep]
+    if len(lms) == 0:
+        return {}
+    pd = mgr._base()
+    pos, quat, valid = backend.traj_eval_many(pd, np.concatenate([[map_time], t_ref]))
+    if not valid[0]:
+        return {}
 
-    def cam_pose(t):
-        e = backend.traj_eval(mgr._base(), t)
-        q = quat_mul(e["q"], c.q_CtoI)
-        p = quat_rot(e["q"], c.p_CinI) + e["p"]
-        return q, p
+    def cam_pose(i):   # evaluateCameraPose: q_CtoG = q_ItoG * q_CtoI ; p_CinG = q_ItoG * p_CinI + p_IinG
+        return quat_mul(quat[i], c.q_CtoI), quat_rot(quat[i], c.p_CinI) + pos[i]
 
-    q_CtoG, p_CinG = cam_pose(map_time)
+    q_CtoG, p_CinG = cam_pose(0)
     q_L0_G = quat_mul(q_CtoG, q_LtoC)
     t_L0_G = quat_rot(q_CtoG, t_LinC) + p_CinG
-    lms = np.nonzero((seq.lm_ref_obs >= 0))[0]
     pts, ids = [], []
-    for l in lms:
-        if rho[l] < 0.05:
-            continue
-        t = cam_obs["lm_ref_t0"][l]
-        if not (mgr.min_time <= t < mgr.max_time):
+    for k, l in enumerate(lms):
+        if not valid[k + 1]:
             continue
         uv = cam_obs["lm_ref_uv"][l]
         p_c = np.array([(uv[0] - cam.cx) / cam.fx, (uv[1] - cam.cy) / cam.fy, 1.0]) / rho[l]
-        q, p = cam_pose(t)
+        q, p = cam_pose(k + 1)
         p_g = quat_rot(q, p_c) + p
         pts.append(quat_rot(quat_conj(q_L0_G), p_g - t_L0_G))
         ids.append(int(l))

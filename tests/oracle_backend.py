@@ -63,6 +63,18 @@ class OracleBackend:
     def traj_eval(self, pd, t):
         return ob.traj_eval(pd, t)
 
+    def traj_eval_many(self, pd, times):
+        n = len(times)
+        pos, quat, valid = np.zeros((n, 3)), np.zeros((n, 4)), np.zeros(n, bool)
+        quat[:, 3] = 1.0
+        for i, t in enumerate(times):
+            try:
+                e = ob.traj_eval(pd, float(t))
+            except IndexError:
+                continue
+            pos[i], quat[i], valid[i] = e["p"], e["q"], True
+        return pos, quat, valid
+
     def associate_landmarks(self, smap, pts, radius):
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         out = np.zeros(len(pts), np.int32)

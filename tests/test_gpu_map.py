@@ -1,0 +1,179 @@
+"""GPU parity tests of the LiDAR-map path (SURVEY §8 a-1, a-2, a-3, a-3', f-1) against the CPU oracle, through the C-ABI.
+Integer / index results must be bit-exact; fp64 statistics agree to round-off (the summation order differs)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from lvi_exc_b200 import pipeline, synth
+from lvi_exc_b200._capi import LviError
+from tests import oracle_binding as ob
+from tests.oracle_backend import OracleBackend
+from tests.problems import _manager, _sequence, gt_trajectory
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _cloud_synth(duration=2.0):
+    seq = _sequence(duration, 400)
+    orc = OracleBackend()
+    mgr = _manager(seq)
+    scans_map = orc.transform(orc.undistort(mgr._base(), seq.scans_raw, None, False), seq.loam_poses)
+    return seq, scans_map
+
+
+def _compare_maps(gmap, omap_v, omap_s):
+    gl, ol = gmap.export_leaves(), omap_v.export()
+    assert np.array_equal(gl["keys"], ol["keys"])
+    assert np.array_equal(gl["nr_points"], ol["nr_points"])
+    assert np.array_equal(gl["leaf_start"], ol["leaf_start"])
+    assert np.array_equal(gl["point_index"], ol["point_index"])      # Leaf::pointList_ order
+    mn_g, dv_g = gmap.grid(); mn_o, dv_o = omap_v.grid()
+    assert np.array_equal(mn_g, mn_o) and np.array_equal(dv_g, dv_o)
+    assert np.allclose(gl["mean"], ol["mean"], rtol=1e-12, atol=1e-12)
+    ok = ol["nr_points"] >= 6
+    scale = np.abs(ol["cov"][ok]).max() if ok.any() else 1.0
+    assert np.abs(gl["cov"][ok] - ol["cov"][ok]).max() <= 1e-10 * scale
+    assert np.abs(gl["evals"][ok] - ol["evals"][ok]).max() <= 1e-10 * scale
+    if omap_s is not None:
+        gp, op = gmap.planes, omap_s.export()
+        assert np.array_equal(gp["leaf_key"], op["leaf_key"])         # same plane set, same plane ids
+        assert np.array_equal(gp["n_inliers"], op["n_inliers"])
+        assert np.array_equal(gp["box_min"], op["box_min"]) and np.array_equal(gp["box_max"], op["box_max"])
+        assert np.abs(gp["p4"] - op["p4"]).max() <= 1e-6                # float-rounded PCA of fp64 sums
+
+
+def test_voxel_surfel_synthetic(cuda_backend):
+    seq, scans_map = _cloud_synth()
+    cloud = scans_map.reshape(-1, 8)
+    for lam in (0.6, 0.7):
+        gmap = cuda_backend.build_surfel_map(cloud, 0.5, lam)
+        ov = ob.OracleVoxelMap(cloud, 0.5)
+        osf = ob.OracleSurfels(ov, lam)
+        assert gmap.num_planes > 50
+        _compare_maps(gmap, ov, osf)
+        gmap.close()
+
+
+def test_voxel_real_velodyne_fixture(cuda_backend):
+    """20k-point subset of the reference's own ndt_omp/data/251370668.pcd (tests/golden/make_pcd_fixture.py)"""
+    pts = np.load(GOLDEN / "velodyne_251370668_20k.npy")
+    cloud = np.zeros((len(pts), 8), np.float32)
+    cloud[:, :3] = pts
+    for leaf in (0.5, 1.0, 2.0):
+        gmap = cuda_backend.build_surfel_map(cloud, leaf, 0.6)
+        ov = ob.OracleVoxelMap(cloud, leaf)
+        _compare_maps(gmap, ov, ob.OracleSurfels(ov, 0.6))
+        gmap.close()
+
+
+def test_voxel_edge_cases(cuda_backend):
+    rng = np.random.default_rng(5)
+    # NaN / inf points are skipped; a stride-12 (xyz only) cloud works; one occupied leaf
+    cloud = np.zeros((5000, 8), np.float32)
+    cloud[:, :3] = rng.uniform(-3, 3, (5000, 3)).astype(np.float32)
+    cloud[::7, 0] = np.nan
+    cloud[3::11, 2] = np.inf
+    gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
+    ov = ob.OracleVoxelMap(cloud, 0.5)
+    _compare_maps(gmap, ov, ob.OracleSurfels(ov, 0.6))
+    gmap.close()
+    xyz = np.ascontiguousarray(cloud[:, :3])
+    xyz = xyz[np.isfinite(xyz).all(axis=1)]
+    g2 = cuda_backend.build_surfel_map(xyz, 0.5, 0.6)
+    _compare_maps(g2, ob.OracleVoxelMap(xyz, 0.5), None)
+    g2.close()
+    one = np.zeros((64, 8), np.float32); one[:, :3] = 0.25 + 0.01 * rng.standard_normal((64, 3)).astype(np.float32)
+    g3 = cuda_backend.build_surfel_map(one, 0.5, 0.6)
+    assert g3.num_leaves == ob.OracleVoxelMap(one, 0.5).num_leaves
+    g3.close()
+    allnan = np.full((16, 8), np.nan, np.float32)
+    with pytest.raises(LviError):
+        cuda_backend.build_surfel_map(allnan, 0.5, 0.6)
+    huge = np.zeros((2, 8), np.float32); huge[1, :3] = 3e6
+    with pytest.raises(OverflowError):   # "Leaf size is too small for the input dataset" (N/voxel_grid_covariance_omp_impl.hpp:75-84)
+        cuda_backend.build_surfel_map(huge, 0.01, 0.6)
+
+
+@pytest.mark.parametrize("k,step", [(2, 10), (1, 1), (3, 4)])
+def test_association_bit_exact(cuda_backend, k, step):
+    seq, scans_map = _cloud_synth()
+    cloud = scans_map.reshape(-1, 8)
+    gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
+    ov = ob.OracleVoxelMap(cloud, 0.5)
+    osf = ob.OracleSurfels(ov, 0.6)
+    sp_g = cuda_backend.associate(gmap, scans_map, seq.scans_raw, 0.05, k, step)
+    sp_o, n_all = osf.associate(scans_map, seq.scans_raw, 0.05, k, step, mode=0)   # reference-faithful O(P*W*H) sweep
+    assert cuda_backend.last_n_all == n_all and len(sp_g) == len(sp_o) and len(sp_g) > 100
+    for f in ("timestamp", "point", "point_in_map", "plane_id"):
+        assert np.array_equal(sp_g[f], sp_o[f]), f
+    gmap.close()
+
+
+def test_association_ragged_scan(cuda_backend):
+    """rings with fewer than 2k hits, timestamp == 0 points and all-NaN scans"""
+    seq, scans_map = _cloud_synth()
+    cloud = scans_map.reshape(-1, 8)
+    gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
+    ov = ob.OracleVoxelMap(cloud, 0.5); osf = ob.OracleSurfels(ov, 0.6)
+    raw = seq.scans_raw.copy(); sm = scans_map.copy()
+    raw["timestamp"][0, :, ::3] = 0.0
+    sm[1] = np.nan
+    sm[2, :, 100:] = np.nan
+    sp_g = cuda_backend.associate(gmap, sm, raw, 0.05, 2, 1)
+    sp_o, _ = osf.associate(sm, raw, 0.05, 2, 1, mode=0)
+    assert len(sp_g) == len(sp_o)
+    assert np.array_equal(sp_g["timestamp"], sp_o["timestamp"]) and np.array_equal(sp_g["plane_id"], sp_o["plane_id"])
+    gmap.close()
+
+
+def test_undistort_transform_traj_eval(cuda_backend):
+    seq = _sequence(2.0, 400)
+    mgr = _manager(seq)
+    mgr.r3, mgr.so3 = gt_trajectory(seq, mgr)
+    orc = OracleBackend()
+    pd = mgr._base()
+    for target, corr in ((None, False), (seq.map_time, True)):
+        g = cuda_backend.undistort(pd, seq.scans_raw, target, corr).cpu().numpy()
+        o = orc.undistort(pd, seq.scans_raw, target, corr)
+        fin = np.isfinite(o[..., 0])
+        assert np.array_equal(fin, np.isfinite(g[..., 0]))
+        assert np.abs(g[fin] - o[fin]).max() < 1e-5
+    o = orc.undistort(pd, seq.scans_raw, None, False)
+    tg = cuda_backend.transform(o, seq.loam_poses).cpu().numpy()
+    to = orc.transform(o, seq.loam_poses)
+    assert np.array_equal(tg[np.isfinite(to)], to[np.isfinite(to)])     # float 4x4, no FMA: bit-exact
+    ts = np.linspace(mgr.min_time, mgr.max_time - 1e-6, 57)
+    pos, quat, valid = cuda_backend.traj_eval_many(pd, np.concatenate([ts, [mgr.max_time + 1.0]]))
+    assert valid[:-1].all() and not valid[-1]
+    for i, t in enumerate(ts):
+        e = ob.traj_eval(pd, float(t))
+        assert np.abs(pos[i] - e["p"]).max() < 1e-12 and np.abs(quat[i] - e["q"]).max() < 1e-12
+
+
+def test_landmark_association(cuda_backend):
+    seq, scans_map = _cloud_synth()
+    cloud = scans_map.reshape(-1, 8)
+    gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
+    ov = ob.OracleVoxelMap(cloud, 0.5); osf = ob.OracleSurfels(ov, 0.6)
+    pts = cloud[np.isfinite(cloud[:, 0])][::997, :3].astype(np.float64)
+    pts = np.concatenate([pts, pts + 0.04, [[1e3, 1e3, 1e3]]])
+    out_g = cuda_backend.associate_landmarks(gmap, pts, 0.05)
+    out_o = np.zeros(len(pts), np.int32)
+    ob.lib().orc_associate_landmarks(osf.h, ob.ptr(pts), len(pts), 0.05, ob.ptr(out_o))
+    assert np.array_equal(out_g, out_o) and (out_g >= 0).sum() > 10
+    gmap.close()
+
+
+def test_pipeline_matches_oracle(cuda_backend):
+    """LCIoptimize replay on 3 s of data: extrinsics within the north-star tolerance of the CPU path (1e-4 rad / 1e-3 m)"""
+    cfg = synth.default_config(duration=3.0, n_landmarks=400)
+    seq = synth.make_sequence(cfg)
+    pcfg = pipeline.PipelineConfig(iters_li=12, iters_lvi=12, n_refine=1)
+    og = pipeline.run_calibration(seq, cuda_backend, pcfg)
+    oo = pipeline.run_calibration(seq, OracleBackend(), pcfg)
+    cg, co = og["calib"], oo["calib"]
+    assert pipeline.quat_angle(cg.q_LtoI, co.q_LtoI) < 1e-4 and np.linalg.norm(cg.p_LinI - co.p_LinI) < 1e-3
+    assert pipeline.quat_angle(cg.q_CtoI, co.q_CtoI) < 1e-4 and np.linalg.norm(cg.p_CinI - co.p_CinI) < 1e-3
+    assert [s["iterations"] for s in og["stages"]] == [s["iterations"] for s in oo["stages"]]
