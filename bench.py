@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native LVI-ExC calibration hot path.
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo (CUDA library through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path (oracle port) on host cores
+
+Metric (BASELINE.json): calibration iters/sec — one step = one Levenberg-Marquardt iteration (residuals + Jacobians +
+J^T J / J^T r + damped band+arrow Cholesky solve + trial-step cost) of the full LVI problem (stage S4: gyro + accel +
+LiDAR-surfel + rolling-shutter camera residuals) on the 60 s synthetic VLP-16 10 Hz + 200 Hz IMU + 20 Hz mono sequence
+(BASELINE.json configs[1]).  `value` has the problem resident in HBM; `e2e` goes through lvi_problem_create /
+lvi_problem_solve with HOST buffers (tables + parameters uploaded, optimum downloaded inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "calibration iters/sec (residuals+JᵀJ+LM step) on 60 s VLP-16 synthetic; extrinsic err"
+UNIT = "iters/s"
+WORKLOAD = "C2: 60 s VLP-16 10 Hz + 200 Hz IMU + 20 Hz mono ORB track, full LVI B-spline solve (stage S4)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--duration", type=float, default=60.0, help="seconds of synthetic data (60 = BASELINE configs[1])")
+    ap.add_argument("--ref-duration", type=float, default=10.0, help="bounded sample (seconds of data) for the CPU reference arm")
+    ap.add_argument("--no-calibration", action="store_true", help="skip the full S0-S5 stage sequence (extrinsic error report)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, device: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def problem_bytes(pd) -> tuple[int, int]:
+    """bytes lvi_problem_create uploads (tables + parameters + planes) and lvi_problem_solve downloads (parameters)"""
+    up = sum(a.nbytes for tab in pd.tables.values() for a in tab)
+    params = sum(getattr(pd, k).nbytes for k in ("so3_knots", "lidar_q", "lidar_p", "cam_q", "cam_p", "gravity", "acc_bias", "gyr_bias", "rho"))
+    if pd.r3_knots is not None:
+        params += pd.r3_knots.nbytes
+    return up + params + pd.planes.nbytes, params
+
+
+def run_reference(args, rank: int):
+    """The reference's own CPU path for this metric: the oracle port of Kontiki + Ceres (the real reference cannot be built
+    here: no Eigen/Ceres/PCL), all host threads, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from lvi_exc_b200 import synth, workload
+    from tests import oracle_binding as ob           # bench.py's reference arm is one of the places allowed to run oracle/
+    from tests.oracle_backend import OracleBackend
+    cores = ob.lib().orc_num_threads()
+    dur = min(args.ref_duration, args.duration)
+    seq = synth.make_sequence(synth.default_config(duration=dur))
+    pd, info = workload.lvi_stage_problem(seq, OracleBackend())
+    tol0 = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+    saved = pd.clone_params()
+    if args.warmup > 0:
+        ob.OracleProblem(pd).solve(min(args.warmup, 1), **tol0)   # one warm-up iteration is enough on the CPU (no clocks/JIT to settle)
+        pd.restore_params(saved)
+    t0 = time.perf_counter()
+    s = ob.OracleProblem(pd).solve(args.steps, **tol0)
+    dt = time.perf_counter() - t0
+    iters = max(1, s.num_iterations)
+    scale = dur / args.duration     # iteration cost is linear in sequence length (residuals, knots; the bandwidth is fixed)
+    value = iters / dt * scale
+    sample = (f"{dur:g} s of the {args.duration:g} s sequence ({pd_sizes(pd)}), {iters} LM iterations, all {cores} host threads; "
+              f"value scaled by {scale:.4g} to the full sequence")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample_seconds": dur},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def pd_sizes(pd) -> str:
+    t = pd.tables
+    n = lambda k: len(t[k][0]) if k in t else 0
+    return f"{n('gyro')} gyro + {n('accel')} accel + {n('surfel')} surfel + {n('cam')} camera residual blocks, {pd.n_knots} knots"
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    from lvi_exc_b200 import _capi, pipeline, synth, workload
+    from lvi_exc_b200.backend import CudaBackend, CudaProblem
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this repo has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        lib = _capi.load()
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            _capi.check(lib.lvi_nccl_unique_id(raw))
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        nccl_id = bytes(idbuf.cpu().numpy().tobytes())
+    backend = CudaBackend(local_rank, nccl_id=nccl_id, rank=rank, world=world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        backend.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: identical on every rank (deterministic generator); the library shards the residual tables by time chunk
+    seq = synth.make_sequence(synth.default_config(duration=args.duration))
+    pd, info = workload.lvi_stage_problem(seq, backend)
+    saved = pd.clone_params()
+    prob = CudaProblem(backend, pd)
+    # ---- device-resident throughput
+    prob.bench_iterations(max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = backend.launches
+    ms = prob.bench_iterations(args.steps)        # CUDA events on the library's stream, per phase and whole loop
+    barrier()
+    launches = backend.launches - l0
+    ms_total = max_over_ranks(float(ms[5]))
+    # ---- end to end through the C-ABI with host buffers (H2D of tables/parameters and D2H of the optimum inside the timed region)
+    tol0 = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+    pd.restore_params(saved)
+    barrier()
+    t0 = time.perf_counter()
+    p2 = CudaProblem(backend, pd)
+    s = p2.solve(args.steps, **tol0)
+    p2.close()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    e2e_iters = max(1, s.num_iterations)
+    h2d, d2h = problem_bytes(pd)
+    pd.restore_params(saved)
+
+    if rank != 0:
+        return
+    value = 1e3 / ms_total
+    peaks, peak_kind = measured_peaks()
+    # ---- roofline of the dominant kernel: band_factor_kernel (blocked band+arrow Cholesky).  Algorithmic bytes per launch = every
+    # stored 32x32 fp64 tile of the damped normal matrix read once and its factor written once (+ the inverse diagonal blocks).
+    nt, nres = prob.num_tangent, prob.num_residuals
+    lay = np.zeros(8, np.int32)
+    _capi.check(backend.lib.lvi_problem_layout(prob.h, lay.ctypes.data_as(C.POINTER(C.c_int32))))
+    nb, nbo, bw, NT, T, RB = (int(x) for x in lay[:6])
+    tiles = sum(min(T, NT - 1 - k) + 1 + RB for k in range(NT))
+    algo_bytes = tiles * 8192 * 2 + NT * 8192
+    phase_names = ["linearize", "build_system", "band_factor", "corner_backsolve", "trial_cost"]
+    phases = {n: float(ms[i]) for i, n in enumerate(phase_names)}
+    fac_ms = phases["band_factor"]
+    achieved = algo_bytes / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
+    roofline = {"kernel": "band_factor_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fac_ms, "share_of_step": fac_ms / ms_total}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms_total, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "seconds": args.duration, "residual_blocks": pd_sizes(pd), "num_residuals": nres, "tangent_dims": nt,
+                      "band_dims": nb, "border_dims": nbo, "half_bandwidth": bw, "l2_policy": "inputs larger than L2: H+A tile stores %.0f MB > 126 MB" % (2 * tiles * 8192 / 1e6),
+                      "parallelism": f"dp{world}: residual tables sharded by time chunk, NCCL all-reduce of H/g"},
+           "phases_ms": phases,
+           "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
+                   "iterations": e2e_iters, "wall_s": e2e_s},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "map_path": info}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N = 1 only)
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_binding as ob            # bench.py's cpu_baseline leg may execute oracle/
+        from tests.oracle_backend import OracleBackend
+        dur = min(args.ref_duration, args.duration)
+        seq_s = seq if dur == args.duration else synth.make_sequence(synth.default_config(duration=dur))
+        pd_s, _ = workload.lvi_stage_problem(seq_s, OracleBackend())
+        t0 = time.perf_counter()
+        so = ob.OracleProblem(pd_s).solve(5, **tol0)
+        dt = time.perf_counter() - t0
+        scale = dur / args.duration
+        out["cpu_baseline"] = {"value": max(1, so.num_iterations) / dt * scale, "unit": UNIT, "cores": ob.lib().orc_num_threads(), "kind": "port",
+                               "sample": f"{dur:g} s of the {args.duration:g} s sequence ({pd_sizes(pd_s)}), {so.num_iterations} LM iterations of the CPU "
+                                         f"oracle (forward-mode AD in passes of 4 + band Cholesky, OpenMP), value scaled by {scale:.4g}"}
+    # ---- whole stage sequence (3 data associations + S0..S5) for the extrinsic-error half of the metric
+    if world == 1 and not args.no_calibration:
+        t0 = time.perf_counter()
+        res = pipeline.run_calibration(seq, backend)
+        backend.synchronize()
+        wall = time.perf_counter() - t0
+        err = pipeline.extrinsic_errors(res["calib"], seq.gt)
+        out["calibration"] = {"wall_s": wall, "extrinsic_err_vs_gt": err,
+                              "stages": [{k: st[k] for k in ("name", "iterations", "final_cost", "time_ms")} for st in res["stages"]],
+                              "assoc_counts": res["assoc_counts"]}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -243,7 +243,10 @@ int lvi_problem_tangent_offset_block(const lvi_problem* p, int which);
 int lvi_problem_jacobian_dense(lvi_problem* p, double* J);
 /* run `iters` LM iterations' worth of work without convergence tests (bench.py `value`): each = residuals +
  * Jacobians + normal equations + damped solve + trial-step cost. Parameters are restored afterwards. */
-int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase /* [4] jac, assemble, solve, trial */);
+int lvi_problem_bench_iterations(lvi_problem* p, int iters,
+                                 float* ms_per_phase /* [6] linearize, build_system, band_factor, corner+backsolve, trial cost, whole loop / iters */);
+/* linear-system layout: out[8] = band dims, border dims, half bandwidth, block columns, sub-diagonal tile rows, border tile rows, 0, 0 */
+int lvi_problem_layout(lvi_problem* p, int32_t* out);
 
 /* ---- (a-3') visual landmark -> surfel association ------------------------------------------------------- */
 /* Inner test of SurfelAssociation::associateVisualPointsWithPlanes (L/src/core/surfel_association.cpp:196-210) for

@@ -131,7 +131,7 @@ ABI_SYMBOLS = [
     "lvi_surfel_export", "lvi_associate", "lvi_associate_d", "lvi_solve_options_default", "lvi_problem_create",
     "lvi_problem_destroy", "lvi_problem_solve", "lvi_problem_evaluate", "lvi_problem_num_residuals",
     "lvi_problem_num_tangent", "lvi_problem_tangent_offset_knot", "lvi_problem_tangent_offset_block",
-    "lvi_problem_jacobian_dense", "lvi_problem_bench_iterations", "lvi_associate_landmarks", "lvi_undistort",
+    "lvi_problem_jacobian_dense", "lvi_problem_bench_iterations", "lvi_problem_layout", "lvi_associate_landmarks", "lvi_undistort",
     "lvi_undistort_d", "lvi_transform_scans", "lvi_transform_scans_d", "lvi_trajectory_evaluate", "lvi_band_solve_dense",
 ]
 
@@ -187,6 +187,7 @@ def load() -> C.CDLL:
     lib.lvi_problem_tangent_offset_block.argtypes = [vp, C.c_int]
     lib.lvi_problem_jacobian_dense.argtypes = [vp, c_double_p]
     lib.lvi_problem_bench_iterations.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.lvi_problem_layout.argtypes = [vp, c_int32_p]
     lib.lvi_associate_landmarks.argtypes = [vp, vp, c_double_p, C.c_int64, C.c_double, c_int32_p]
     for name in ("lvi_undistort", "lvi_undistort_d"):
         getattr(lib, name).argtypes = [vp, C.POINTER(ProblemDesc), vp, C.c_int32, C.c_int64, c_double_p, C.c_int, vp, c_int32_p]

@@ -114,7 +114,7 @@ class CudaProblem:
         return s
 
     def bench_iterations(self, iters: int) -> np.ndarray:
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 6)()
         check(self.b.lib.lvi_problem_bench_iterations(self.h, iters, ms))
         return np.array(list(ms), dtype=np.float64)
 

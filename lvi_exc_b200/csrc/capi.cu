@@ -1,9 +1,8 @@
 // capi.cu — context management and misc entry points of the C-ABI (include/lvi_exc_b200.h).
-#include <nccl.h>
-
 #include <cstring>
 
 #include "common.cuh"
+#include "nccl_dyn.hpp"
 
 namespace lvi {
 static thread_local std::string g_error;
@@ -51,7 +50,7 @@ int lvi_nccl_unique_id(void* id128) {
     LVI_REQUIRE(id128, LVI_ERR_INVALID, "null id");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId id;
-    LVI_REQUIRE(ncclGetUniqueId(&id) == ncclSuccess, LVI_ERR_NCCL, "ncclGetUniqueId failed");
+    LVI_REQUIRE(nccl().GetUniqueId(&id) == ncclSuccess, LVI_ERR_NCCL, "ncclGetUniqueId failed");
     std::memcpy(id128, &id, 128);
   });
 }
@@ -66,8 +65,8 @@ int lvi_ctx_create_nccl(int device, const void* id128, int rank, int world, lvi_
       ncclUniqueId id;
       std::memcpy(&id, id128, 128);
       ncclComm_t comm;
-      ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
-      LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+      ncclResult_t r = nccl().CommInitRank(&comm, world, id, rank);
+      LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
       c->nccl = comm; c->owns_nccl = true; c->rank = rank; c->world = world;
     } catch (...) { delete c; throw; }
     *out = c;
@@ -77,7 +76,7 @@ int lvi_ctx_create_nccl(int device, const void* id128, int rank, int world, lvi_
 int lvi_ctx_destroy(lvi_ctx* ctx) {
   if (!ctx) return LVI_OK;
   cudaSetDevice(ctx->device);
-  if (ctx->owns_nccl && ctx->nccl) ncclCommDestroy(static_cast<ncclComm_t>(ctx->nccl));
+  if (ctx->owns_nccl && ctx->nccl) nccl().CommDestroy(static_cast<ncclComm_t>(ctx->nccl));
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return LVI_OK;

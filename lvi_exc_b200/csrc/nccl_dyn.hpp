@@ -1,0 +1,45 @@
+// nccl_dyn.hpp — NCCL bound at run time (dlopen) instead of link time.
+// The host process usually already carries an NCCL (PyTorch bundles its own libnccl.so.2); linking a second copy by
+// DT_NEEDED makes the two fight over the SONAME.  dlopen("libnccl.so.2") returns whichever copy the process has loaded
+// (or loads the system one), and single-GPU runs never touch NCCL at all.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace lvi {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+inline const NcclApi& nccl() {
+  static NcclApi api;
+  static bool loaded = false;
+  if (!loaded) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    LVI_REQUIRE(h != nullptr, LVI_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* name) {
+      void* p = dlsym(h, name);
+      LVI_REQUIRE(p != nullptr, LVI_ERR_NCCL, std::string("libnccl is missing ") + name);
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    loaded = true;
+  }
+  return api;
+}
+
+}  // namespace lvi

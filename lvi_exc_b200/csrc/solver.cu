@@ -14,12 +14,12 @@
 //   band_backsolve_kernel  backward substitution, one CTA, 32 warps over the tiles of a block row.
 // All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
 #include <cooperative_groups.h>
-#include <nccl.h>
 
 #include <chrono>
 #include <cmath>
 #include <cstring>
 
+#include "nccl_dyn.hpp"
 #include "problem.cuh"
 
 namespace cg = cooperative_groups;
@@ -138,11 +138,10 @@ __global__ void __launch_bounds__(256) band_factor_kernel(BandSys S) {
       if (!ok && tid == 0 && blockIdx.x == 0) *S.fail = 1;
     }
     __syncthreads();
-    if (blockIdx.x == 0) {
-      double* Wg = S.Linv + static_cast<size_t>(k) * kTileElems;
+    if (blockIdx.x == 0) {  // only W = L_kk^-1 is kept (the back substitution multiplies by W^T); the diagonal tile itself
+      double* Wg = S.Linv + static_cast<size_t>(k) * kTileElems;  // must stay untouched: other CTAs may still be loading it
       for (int e = tid; e < kTileElems; e += 256) {
         const int r = e & 31, m = e >> 5;
-        col[e] = sL[r * kLP + m];
         Wg[e] = sW[r * kLP + m];
       }
     }
@@ -372,7 +371,7 @@ static int coop_grid_limit(lvi_ctx* ctx) {
   return limit;
 }
 
-void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
+static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   cudaStream_t st = ctx->stream;
   LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), st));
   if (A.NT > 0) {
@@ -382,8 +381,14 @@ void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
     LVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band_factor_kernel), dim3(grid), dim3(256), args, 0, st));
     ++ctx->launches;
   }
+}
+static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
   LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
   if (A.NT > 0) LVI_LAUNCH(ctx, band_backsolve_kernel, 1, 1024, 0, A);
+}
+void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
+  band_factor_only(ctx, A);
+  band_solve_only(ctx, A);
 }
 
 struct Scalars {  // mirrors p->scal
@@ -392,8 +397,8 @@ struct Scalars {  // mirrors p->scal
 
 static void allreduce_sum(lvi_ctx* ctx, double* buf, size_t count) {
   if (ctx->world <= 1 || count == 0) return;
-  ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl), ctx->stream);
-  LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+  ncclResult_t r = nccl().AllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl), ctx->stream);
+  LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
 }
 
 static void read_scalars(lvi_problem* p, Scalars& s) {
@@ -600,6 +605,7 @@ int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_su
 }
 
 // One LM iteration's worth of work, `iters` times, without acceptance: linearise, damped system, factor + solve, candidate, trial cost.
+// ms_per_phase[6]: linearize | build_system | band_factor | corner + backsolve + finish | candidate + trial cost | whole loop / iters
 int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase) {
   return guarded([&] {
     LVI_REQUIRE(p && iters > 0, LVI_ERR_INVALID, "lvi_problem_bench_iterations: bad argument");
@@ -610,12 +616,16 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
     lvi_solve_options o;
     lvi_solve_options_default(&o);
     DBuf<double> dH(std::max(p->nt, 1));
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[6], t0, t1;
     for (auto& e : ev) LVI_CUDA(cudaEventCreate(&e));
-    float acc[4] = {0, 0, 0, 0};
+    LVI_CUDA(cudaEventCreate(&t0)); LVI_CUDA(cudaEventCreate(&t1));
+    float acc[5] = {0, 0, 0, 0, 0};
     linearize(p);
     LVI_LAUNCH(ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->nt, dH.p);
     LVI_LAUNCH(ctx, scale_init_kernel, blocks_for(p->nt), 256, 0, dH.p, p->nt, 1, p->scale.p);
+    const double inv_radius = 1.0 / o.initial_trust_region_radius;
+    LVI_CUDA(cudaStreamSynchronize(st));
+    LVI_CUDA(cudaEventRecord(t0, st));
     for (int it = 0; it < iters; ++it) {
       LVI_CUDA(cudaEventRecord(ev[0], st));
       linearize(p);
@@ -623,23 +633,39 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
       refresh_diag(p, dH, o);
       const int ntile = p->A.NT * p->A.TPC;
       const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
-      LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, 1.0 / o.initial_trust_region_radius, p->g.p);
+      LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, inv_radius, p->g.p);
       LVI_CUDA(cudaEventRecord(ev[2], st));
-      band_factor_solve(ctx, p->A);
-      LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), st));
-      LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p,
-                 1.0 / o.initial_trust_region_radius, p->g.p, p->y.p, p->delta.p, p->scal.p);
+      band_factor_only(ctx, p->A);
       LVI_CUDA(cudaEventRecord(ev[3], st));
+      band_solve_only(ctx, p->A);
+      LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), st));
+      LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p, inv_radius, p->g.p,
+                 p->y.p, p->delta.p, p->scal.p);
+      LVI_CUDA(cudaEventRecord(ev[4], st));
       apply_plus(p, p->delta.p, 1.0, 1.0);
       trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
       diff_norms(p);
-      LVI_CUDA(cudaEventRecord(ev[4], st));
+      LVI_CUDA(cudaEventRecord(ev[5], st));
       Scalars sc;
       read_scalars(p, sc);  // the per-iteration host decision point of the LM loop
-      for (int k = 0; k < 4; ++k) { float ms = 0; LVI_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
+      for (int k = 0; k < 5; ++k) { float ms = 0; LVI_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
     }
+    LVI_CUDA(cudaEventRecord(t1, st));
+    LVI_CUDA(cudaEventSynchronize(t1));
+    float total = 0;
+    LVI_CUDA(cudaEventElapsedTime(&total, t0, t1));
     for (auto& e : ev) cudaEventDestroy(e);
-    if (ms_per_phase) for (int k = 0; k < 4; ++k) ms_per_phase[k] = acc[k] / iters;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (ms_per_phase) { for (int k = 0; k < 5; ++k) ms_per_phase[k] = acc[k] / iters; ms_per_phase[5] = total / iters; }
+  });
+}
+
+// out[8]: band dims, border dims, half bandwidth, block columns NT, sub-diagonal tile rows T, border tile rows RB, 0, 0
+int lvi_problem_layout(lvi_problem* p, int32_t* out) {
+  return guarded([&] {
+    LVI_REQUIRE(p && out, LVI_ERR_INVALID, "lvi_problem_layout: null argument");
+    problem_ensure_solver_buffers(p);
+    out[0] = p->L.nb; out[1] = p->L.nbo; out[2] = p->L.bw; out[3] = p->A.NT; out[4] = p->A.T; out[5] = p->A.RB; out[6] = 0; out[7] = 0;
   });
 }
 
