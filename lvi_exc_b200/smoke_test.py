@@ -51,11 +51,12 @@ def run(verbose: bool = True) -> None:
     ev_g, ev_o = CudaProblem(cb, pd_g).evaluate(gradient=False), ob.OracleProblem(pd_o).evaluate(gradient=False)
     assert abs(ev_g["cost"] - ev_o["cost"]) <= 1e-9 * ev_o["cost"], (ev_g["cost"], ev_o["cost"])
     assert np.abs(ev_g["residuals"] - ev_o["residuals"]).max() <= 1e-7 * max(1.0, np.abs(ev_o["residuals"]).max())
-    s_g, s_o = cb.solve(pd_g, 8), orc.solve(pd_o, 8)
+    # 3 iterations: far from the optimum the LM path is chaotic beyond that (the oracle itself depends on its thread count there)
+    s_g, s_o = cb.solve(pd_g, 3), orc.solve(pd_o, 3)
     rel = abs(s_g.final_cost - s_o.final_cost) / s_o.final_cost
-    assert rel < 1e-3, (s_g.final_cost, s_o.final_cost)
+    assert rel < 1e-6, (s_g.final_cost, s_o.final_cost)
     if verbose:
         print(f"smoke ok: leaves {gmap.num_leaves}, planes {gmap.num_planes}, surfel points {len(sp_g)}, "
-              f"S0 cost {s_g.final_cost:.6e}, S1(8 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
+              f"S0 cost {s_g.final_cost:.6e}, S1(3 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
               f"kernel launches {cb.launches}")
     cb.close()

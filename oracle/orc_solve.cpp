@@ -1045,16 +1045,20 @@ int orc_problem_solve(void* p, const lvi_solve_options* o, lvi_solve_summary* s)
   catch (const std::range_error& e) { g_err = e.what(); return LVI_ERR_RANGE; }
   catch (const std::exception& e) { g_err = e.what(); return LVI_ERR_DOMAIN; }
 }
+// the owning SplitTrajectory as one segment per spline holding all n knots (what TrajectoryManagerLVI::evaluate*Pose evaluates)
+static void master_meta(const lvi_problem_desc& d, orc::TrajMeta& m, std::vector<const double*>& pp) {
+  m.r3.push_back({d.t0, d.dt, d.n_knots, 0}); m.n_r3 = d.n_knots;
+  m.so3.push_back({d.t0, d.dt, d.n_knots, 0}); m.n_so3 = d.n_knots;
+  for (int i = 0; i < d.n_knots; ++i) pp.push_back(d.r3_knots + 3 * i);
+  for (int i = 0; i < d.n_knots; ++i) pp.push_back(d.so3_knots + 4 * i);
+}
 // trajectory evaluation for tests: out = p[3] v[3] a[3] q[4] w[3]
 int orc_traj_eval(const lvi_problem_desc* d, double t, double* out) {
   using namespace orc;
   try {
-    TrajMeta m; std::vector<int> k;
-    build_segments(d->t0, d->dt, {{t, t}}, m.r3, k); m.n_r3 = static_cast<int>(k.size());
-    std::vector<const double*> pp;
-    for (int i : k) pp.push_back(d->r3_knots + 3 * i);
-    k.clear(); build_segments(d->t0, d->dt, {{t, t}}, m.so3, k); m.n_so3 = static_cast<int>(k.size());
-    for (int i : k) pp.push_back(d->so3_knots + 4 * i);
+    // Trajectory::Evaluate on the OWNING spline: one segment holding every knot (K/trajectories/spline_base.h:194-222,370-378)
+    TrajMeta m; std::vector<const double*> pp;
+    master_meta(*d, m, pp);
     Eval<double> e = traj_eval<double>(m, pp.data(), t, 31);
     const double o[16] = {e.p.x, e.p.y, e.p.z, e.v.x, e.v.y, e.v.z, e.a.x, e.a.y, e.a.z, e.q.x, e.q.y, e.q.z, e.q.w, e.w.x, e.w.y, e.w.z};
     std::copy(o, o + 16, out);
@@ -1072,15 +1076,12 @@ int orc_undistort(const lvi_problem_desc* d, const void* raw_v, int32_t n_scans,
   using namespace orc;
   struct Raw { float x, y, z, pad; float intensity; float pad2; double timestamp; };
   const Raw* raw = static_cast<const Raw*>(raw_v);
+  TrajMeta mm; std::vector<const double*> mpp;
+  master_meta(*d, mm, mpp);
   auto lidar_pose = [&](double t, Quat<double>& q, V3<double>& p) -> bool {
     const double tt = t + d->lidar_toff;
     if (d->t0 > tt || d->t0 + (d->n_knots - 3) * d->dt <= tt) return false;
-    TrajMeta m; std::vector<int> k; std::vector<const double*> pp;
-    build_segments(d->t0, d->dt, {{tt, tt}}, m.r3, k); m.n_r3 = static_cast<int>(k.size());
-    for (int i : k) pp.push_back(d->r3_knots + 3 * i);
-    k.clear(); build_segments(d->t0, d->dt, {{tt, tt}}, m.so3, k); m.n_so3 = static_cast<int>(k.size());
-    for (int i : k) pp.push_back(d->so3_knots + 4 * i);
-    Eval<double> e = traj_eval<double>(m, pp.data(), tt, EvalOrientation | EvalPosition);
+    Eval<double> e = traj_eval<double>(mm, mpp.data(), tt, EvalOrientation | EvalPosition);  // traj_->Evaluate on the whole spline
     Quat<double> qL(d->lidar_q[0], d->lidar_q[1], d->lidar_q[2], d->lidar_q[3]);
     q = e.q * qL;
     p = rot(e.q, V3<double>(d->lidar_p[0], d->lidar_p[1], d->lidar_p[2])) + e.p;

@@ -62,6 +62,11 @@ inline double gauss(uint64_t seed, uint64_t stream, uint64_t i) {
 
 struct Box { double lo[3], hi[3]; };
 
+// The three sensors free-run: their sample clocks have fixed phases against the LiDAR scan clock, so IMU / camera stamps are not
+// commensurate with the 0.02 s knot grid anchored at the first scan (Kontiki's per-residual segment lookup throws for a time
+// within round-off of a knot boundary, K/trajectories/spline_base.h:194-222).
+constexpr double kImuPhase = 0.00137, kCamPhase = 0.00411;
+
 }  // namespace
 
 extern "C" {
@@ -216,7 +221,7 @@ void synth_scans(const synth_config* c, int32_t first_scan, int32_t n_scans, uin
       const int scan = first_scan + s;
       const double t_scan = synth_scan_time(c, scan);
       for (int h = 0; h < H; ++h) {
-        const double t = t_scan + wi * az_dt + h * ring_dt;
+        const double t = t_scan + (wi + 0.5) * az_dt + h * ring_dt;  // firing centred in its azimuth slot: never on a knot boundary
         Pose L = lidar_pose_world(*c, t);
         const double az = -2.0 * M_PI * wi / W;  // clockwise like a Velodyne
         const double ce = std::cos(vert[h]);
@@ -260,7 +265,7 @@ void synth_imu(const synth_config* c, uint64_t seed, double* t, double* gyro, do
   double ql[4], pl[3], qc[4], pc[3], bg[3], ba[3];
   synth_gt_extrinsics(ql, pl, qc, pc, bg, ba);
   for (int i = 0; i < n; ++i) {
-    const double ti = c->t_start - c->pad_time - 0.1 + i / c->imu_rate;
+    const double ti = c->t_start - c->pad_time - 0.1 + kImuPhase + i / c->imu_rate;
     Kin k = gt_world(*c, ti);
     V3 f = mulT(k.R, k.a + V3{0, 0, 9.79});
     t[i] = ti;
@@ -308,7 +313,7 @@ int64_t synth_camera(const synth_config* c, uint64_t seed, double* view_t0, int3
   int64_t n_obs = 0;
   for (int l = 0; l < nl; ++l) if (lm_ref_obs) lm_ref_obs[l] = -1;
   for (int v = 0; v < nv; ++v) {
-    const double t0 = c->t_start + (v * c->keyframe_every) / c->cam_rate;
+    const double t0 = c->t_start + kCamPhase + (v * c->keyframe_every) / c->cam_rate;
     if (view_t0) view_t0[v] = t0;
     for (int l = 0; l < nl; ++l) {
       if (first_view[l] >= 0 && (v - first_view[l] >= c->max_track_views)) continue;
