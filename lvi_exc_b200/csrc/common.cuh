@@ -22,8 +22,8 @@ struct Error : std::runtime_error {
 #define LVI_CUDA(call)                                                                                        \
   do {                                                                                                        \
     cudaError_t e__ = (call);                                                                                 \
-    if (e__ != cudaSuccess)                                                                                   \
-      throw ::lvi::Error(LVI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+    if (e__ != cudaSuccess) { cudaGetLastError(); /* clear the sticky last-error so later launches do not report it */         \
+      throw ::lvi::Error(LVI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); } \
   } while (0)
 
 #define LVI_REQUIRE(cond, code, msg)                 \

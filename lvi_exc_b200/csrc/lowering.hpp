@@ -6,9 +6,11 @@
 //                                                                  constant_bias_imu.h:100-119}
 // by index tables: per evaluation the first knot i0 and the interpolation amount u (times are constants because
 // the time offsets are locked, cfg optimize_time_offset=false), and per parameter block its position in the linear
-// system.  Ordering: trajectory knots in time order [r3_i, so3_i] with each landmark's inverse depth placed right
-// after the last knot of its reference window (band part), then the "arrow" border: knots touched by the map-time
-// evaluation of every surfel residual + the sensor blocks (SURVEY §5 "long-context").  Pure host C++ (no CUDA).
+// system.  Ordering: trajectory knots in time order [r3_i, so3_i] (band part), then the "arrow" border: knots touched by
+// the map-time evaluation of every surfel residual + the sensor blocks (SURVEY §5 "long-context"), then the landmarks'
+// inverse depths, which are eliminated FIRST by a Schur complement (they are 1x1 diagonal blocks: what Ceres'
+// SPARSE_SCHUR does with them as e-blocks); each landmark's coupling row [ref window | camera q,p | obs windows...] is
+// laid out here.  Pure host C++ (no CUDA).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -38,10 +40,14 @@ struct Lowered {
   std::vector<int> pos_r3, pos_so3, pos_rho;
   int pos_sens[TB_COUNT];
   int nb = 0, nbo = 0, bw = 0;   // band dims, border dims, half bandwidth
+  int n_rho = 0;                 // free inverse depths; tangent positions nb+nbo .. nb+nbo+n_rho-1
+  // Schur rows of the inverse depths: landmark l couples to row_pos[row_start[l] .. row_start[l+1]) (-1: constant parameter);
+  // slots: [0,24) reference window (cols 0..23 of its camera residuals), [24,30) camera q,p, then 24 per observation
+  std::vector<int> row_start, row_pos;
   int n_res = 0, n_res_blocks = 0;
   int res_offset[RT_COUNT + 1];  // row offsets of each table in the residual vector
   bool constrained = false;      // a free block has bounds (rho >= 0) -> projected steps + Armijo check
-  int nt() const { return nb + nbo; }
+  int nt() const { return nb + nbo + n_rho; }
 };
 
 
@@ -230,18 +236,12 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   if (border_knots.size() > 16) border_knots.clear();  // not an arrow structure: leave those knots in the band
   // ---- positions
   L.pos_r3.assign(n, -1); L.pos_so3.assign(n, -1); L.pos_rho.assign(std::max(d.n_landmarks, 1), -1);
-  std::vector<std::vector<int>> rho_at(n);
-  for (int l = 0; l < d.n_landmarks; ++l) {
-    const bool locked = d.rho_locked && d.rho_locked[l];
-    if (rho_used[l] && !locked) { rho_at[std::min(std::max(rho_anchor[l], 0), n - 1)].push_back(l); L.constrained = true; }
-  }
   int pb = 0;
   for (int i = 0; i < n; ++i) {
     if (knot_used[i] && !border_knots.count(i)) {
       if (r3_free) { L.pos_r3[i] = pb; pb += 3; }
       if (so3_free) { L.pos_so3[i] = pb; pb += 3; }
     }
-    for (int l : rho_at[i]) L.pos_rho[l] = pb++;
   }
   L.nb = pb;
   for (int i : border_knots) {
@@ -256,6 +256,27 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     if (sens_used[b] && sens_free[b]) { L.pos_sens[b] = pb; pb += sens_dim[b]; }
   }
   L.nbo = pb - L.nb;
+  L.n_rho = 0;
+  for (int l = 0; l < d.n_landmarks; ++l) {
+    const bool locked = d.rho_locked && d.rho_locked[l];
+    if (rho_used[l] && !locked) { L.pos_rho[l] = pb++; ++L.n_rho; L.constrained = true; }
+  }
+  // Schur rows: slot base of every camera residual inside its landmark's row (stored in tab[RT_CAM].ib)
+  {
+    LoweredTable& T = L.tab[RT_CAM];
+    const int nl = std::max(d.n_landmarks, 1);
+    std::vector<int> cnt(nl, 0), ref_i0(nl, -1);
+    T.ib.assign(T.n, 0);
+    for (int i = 0; i < T.n; ++i) {
+      const int l = T.ia[i];
+      if (ref_i0[l] < 0) ref_i0[l] = T.i0a[i];
+      else if (ref_i0[l] != T.i0a[i]) throw std::invalid_argument("camera residuals of one landmark must share its reference observation (Landmark::reference())");
+      T.ib[i] = 30 + 24 * cnt[l]++;
+    }
+    L.row_start.assign(nl + 1, 0);
+    for (int l = 0; l < nl; ++l) L.row_start[l + 1] = L.row_start[l] + ((T.active && l < d.n_landmarks && L.pos_rho[l] >= 0 && cnt[l] > 0) ? 30 + 24 * cnt[l] : 0);
+    L.row_pos.assign(std::max(L.row_start[nl], 1), -1);
+  }
   // ---- residual vector layout + bandwidth
   int ro = 0, nblk = 0;
   for (int t = 0; t < RT_COUNT; ++t) { L.res_offset[t] = ro; ro += L.tab[t].n * rt_rows(t); nblk += L.tab[t].n; }
@@ -298,10 +319,26 @@ template <int TYPE> inline void bw_of_type(const ProblemView& P, int nb, int& bw
     if (hi >= 0) bw = std::max(bw, hi - lo);
   }
 }
+// second lowering pass (needs the column -> position map): positions of every Schur-row slot, and the half bandwidth of the
+// band part INCLUDING the fill the inverse-depth elimination creates between the windows of one landmark
 inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
   int bw = 0;
   bw_of_type<RT_GYRO>(P, L.nb, bw); bw_of_type<RT_ACCEL>(P, L.nb, bw); bw_of_type<RT_SURFEL>(P, L.nb, bw);
   bw_of_type<RT_CAM>(P, L.nb, bw); bw_of_type<RT_CAMSURF>(P, L.nb, bw); bw_of_type<RT_ORIENT>(P, L.nb, bw);
+  const LoweredTable& T = L.tab[RT_CAM];
+  for (int i = 0; i < T.n; ++i) {
+    const int l = T.ia[i];
+    const int rs = L.row_start[l];
+    if (L.row_start[l + 1] == rs) continue;
+    for (int c = 0; c < 24; ++c) L.row_pos[rs + c] = col_pos<RT_CAM>(P, i, c);
+    for (int c = 24; c < 48; ++c) L.row_pos[rs + T.ib[i] + (c - 24)] = col_pos<RT_CAM>(P, i, c);
+    for (int c = 48; c < 54; ++c) L.row_pos[rs + 24 + (c - 48)] = col_pos<RT_CAM>(P, i, c);
+  }
+  for (size_t l = 0; l + 1 < L.row_start.size(); ++l) {
+    int lo = 1 << 30, hi = -1;
+    for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) { const int p = L.row_pos[k]; if (p >= 0 && p < L.nb) { lo = std::min(lo, p); hi = std::max(hi, p); } }
+    if (hi >= 0) bw = std::max(bw, hi - lo);
+  }
   L.bw = bw;
 }
 

@@ -26,7 +26,7 @@ template <int TYPE> struct RTr {
 constexpr int kLinWarps = 2;
 
 template <int TYPE>
-__global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P, BandSys H, double* __restrict__ g, double* __restrict__ cost) {
+__global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P, BandSys H, SchurView SV, double* __restrict__ g, double* __restrict__ cost) {
   constexpr int ROWS = RTr<TYPE>::rows, COLS = RTr<TYPE>::cols, RC = ROWS * COLS, SC = RTr<TYPE>::shared_cols;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double smem[];
@@ -98,18 +98,21 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
           for (int k = 0; k < ROWS; ++k) acc += Jw[r * RC + k * COLS + c] * rw[r * ROWS + k];
         if (acc != 0.0) atomicAdd(g + pc, acc);
       }
-      if (TYPE == RT_CAM) {  // inverse-depth column: one parameter per landmark
+      if (TYPE == RT_CAM) {  // inverse-depth column: one parameter per landmark, kept out of the band (eliminated by Schur complement)
         for (int r = s; r < e; ++r) {
-          const int pr = P.pos_rho[T.ia[base + r]];
+          const int lm = T.ia[base + r];
+          const int pr = P.pos_rho[lm];
           if (pr < 0) continue;
           const double* Jr = Jw + r * RC;
+          const int rs = SV.row_start[lm], obs_base = T.ib[base + r];
           for (int c = lane; c <= SC; c += 32) {
-            const int pc = (c == SC) ? pr : posw[c];
-            if (pc < 0) continue;
+            if (c < SC && posw[c] < 0) continue;
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + SC] * Jr[k * COLS + c];
-            if (acc != 0.0) atomicAdd(band_addr(H, max(pr, pc), min(pr, pc)), acc);
+            if (acc == 0.0) continue;
+            if (c == SC) atomicAdd(SV.Hrr + (pr - SV.base), acc);
+            else atomicAdd(SV.Hrx + rs + (c < 24 ? c : c < 48 ? obs_base + (c - 24) : 24 + (c - 48)), acc);
           }
           if (lane == 0) {
             double acc = 0.0;
@@ -194,7 +197,7 @@ static void launch_linearize(lvi_problem* p) {
   int grid = std::max(1, (T.hi - T.lo + per_cta - 1) / per_cta);
   const int cap = p->ctx->sm_count * 8;
   if (grid > cap) grid = cap;
-  LVI_LAUNCH(p->ctx, linearize_kernel<TYPE>, grid, per_cta, smem, p->view, p->H, p->g.p, p->scal.p);
+  LVI_LAUNCH(p->ctx, linearize_kernel<TYPE>, grid, per_cta, smem, p->view, p->H, p->schur, p->g.p, p->scal.p);
 }
 
 template <int TYPE>
@@ -225,7 +228,7 @@ void problem_set_param_source(lvi_problem* p, const double* x) {
 void problem_linearize(lvi_problem* p, double* cost_d) {
   cudaStream_t st = p->ctx->stream;
   problem_ensure_solver_buffers(p);
-  p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st);
+  p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st); p->Hrx.zero(st); p->Hrr.zero(st);
   LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
   problem_set_param_source(p, p->X.p);
   launch_linearize<RT_GYRO>(p); launch_linearize<RT_ACCEL>(p); launch_linearize<RT_SURFEL>(p);
@@ -265,6 +268,17 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
   alloc_bandsys(p->H, L, p->H_tiles, p->H_C, nullptr, nullptr, nullptr);
   alloc_bandsys(p->A, L, p->A_tiles, p->A_C, p->A_Linv.p, p->A_x.p, p->fail.p);
   const size_t nt = std::max(p->nt, 1);
+  {  // Schur rows of the inverse depths
+    cudaStream_t st = p->ctx->stream;
+    std::vector<int> lm;
+    for (int l = 0; l < L.n_landmarks; ++l) if (L.pos_rho[l] >= 0) lm.push_back(l);
+    p->row_start.alloc(L.row_start.size()); p->row_start.upload(L.row_start.data(), L.row_start.size(), st);
+    p->row_pos.alloc(L.row_pos.size()); p->row_pos.upload(L.row_pos.data(), L.row_pos.size(), st);
+    p->lm_of_rho.alloc(std::max<size_t>(lm.size(), 1)); p->lm_of_rho.upload(lm.data(), lm.size(), st);
+    p->Hrx.alloc(L.row_pos.size()); p->Hrr.alloc(std::max(L.n_rho, 1)); p->yrho.alloc(std::max(L.n_rho, 1));
+    LVI_CUDA(cudaStreamSynchronize(st));
+    p->schur = SchurView{L.n_rho, L.nb + L.nbo, p->row_start.p, p->row_pos.p, p->lm_of_rho.p, p->Hrx.p, p->Hrr.p, p->yrho.p};
+  }
   p->g.alloc(nt); p->scale.alloc(nt); p->diag.alloc(nt); p->y.alloc(nt); p->delta.alloc(nt);
   p->has_solver_buffers = true;
 }

@@ -42,6 +42,17 @@ __device__ __forceinline__ double* band_addr(const BandSys& S, int i, int j) {
   return S.tiles + (tile << 10) + ((j & 31) << 5) + a;
 }
 
+// Schur rows of the inverse depths (lowering.hpp): H_rr (diagonal), H_rx as one dense row per landmark over its coupling slots
+struct SchurView {
+  int n_rho, base;          // base = nb + nbo: tangent position of the first inverse depth
+  const int* row_start;     // [n_landmarks + 1] by landmark id
+  const int* row_pos;       // [slots] band/border position of each slot (-1: constant)
+  const int* lm_of_rho;     // [n_rho] landmark id of the k-th free inverse depth
+  double* Hrx;              // [slots]
+  double* Hrr;              // [n_rho]
+  double* yrho;             // [n_rho] back-substituted step
+};
+
 // free parameter block (for Plus / norms): kind 0 Euclidean, 1 quaternion (x,y,z,w), 2 Euclidean with lower bound 0
 struct FreeBlock { int off; int pos; int size; int kind; };
 
@@ -65,6 +76,9 @@ struct lvi_problem {
   // normal equations
   lvi::BandSys H{}, A{};
   lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x;
+  lvi::SchurView schur{};
+  lvi::DBuf<int> row_start, row_pos, lm_of_rho;
+  lvi::DBuf<double> Hrx, Hrr, yrho;
   lvi::DBuf<int> fail;
   lvi::DBuf<double> g, scale, diag, y, delta, scal;  // scal: small scalar scratch (cost etc.)
   double* h_scal = nullptr;                          // pinned host mirror of scal

@@ -30,9 +30,9 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int kLP = 33;  // padded leading dimension of the 32x32 shared-memory tiles
 
 // ---- small elementwise kernels -------------------------------------------------------------------------------------
-__global__ void diag_kernel(BandSys H, int nt, double* __restrict__ d) {
+__global__ void diag_kernel(BandSys H, SchurView SV, int nt, double* __restrict__ d) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nt) d[t] = *band_addr(H, t, t);
+  if (t < nt) d[t] = t < SV.base ? *band_addr(H, t, t) : SV.Hrr[t - SV.base];
 }
 __global__ void scale_init_kernel(const double* __restrict__ dH, int nt, int jacobi, double* __restrict__ scale) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,6 +83,69 @@ __global__ void __launch_bounds__(256) build_system_kernel(BandSys H, BandSys A,
       A.C[e] = v;
     }
   }
+}
+
+// ---- Schur complement on the inverse depths (1x1 diagonal blocks, eliminated first like Ceres' SPARSE_SCHUR e-blocks) ----------
+// One CTA per free inverse depth r:  A_xx -= h h^T / d,  rhs_x -= h b_r / d   with h = S_x H_xr s_r (scaled coupling row),
+// d = s_r^2 H_rr + D_r^2, b_r = -s_r g_r.  Rows are short (<= 30 + 24 x track length), updates go to the tile store with fp64 atomics.
+__global__ void __launch_bounds__(128) schur_eliminate_kernel(BandSys A, SchurView SV, const double* __restrict__ scale, const double* __restrict__ diag,
+                                                              double inv_radius, const double* __restrict__ g) {
+  extern __shared__ double sm[];
+  const int k = blockIdx.x;
+  const int lm = SV.lm_of_rho[k];
+  const int rs = SV.row_start[lm], len = SV.row_start[lm + 1] - rs;
+  if (len == 0) return;
+  double* hv = sm;
+  int* hp = reinterpret_cast<int*>(sm + len);
+  const int t = SV.base + k;
+  const double sr = scale[t];
+  const double d = SV.Hrr[k] * sr * sr + diag[t] * inv_radius;
+  const double dinv = 1.0 / d;
+  const double br = -g[t] * sr;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int p = SV.row_pos[rs + i];
+    hp[i] = p;
+    hv[i] = p >= 0 ? SV.Hrx[rs + i] * scale[p] * sr : 0.0;
+  }
+  __syncthreads();
+  const int rhs_row = A.nb + A.nbo;
+  for (int i = threadIdx.x; i < len; i += blockDim.x)
+    if (hp[i] >= 0 && hv[i] != 0.0) atomicAdd(band_addr(A, rhs_row, hp[i]), -hv[i] * br * dinv);
+  const int np = len * (len + 1) / 2;
+  for (int q = threadIdx.x; q < np; q += blockDim.x) {
+    int i = static_cast<int>((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+    while (i * (i + 1) / 2 > q) --i;
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    const int j = q - i * (i + 1) / 2;
+    const int pi = hp[i], pj = hp[j];
+    if (pi < 0 || pj < 0) continue;
+    double v = hv[i] * hv[j] * dinv;
+    if (v == 0.0) continue;
+    if (i != j && pi == pj) v += v;
+    atomicAdd(band_addr(A, max(pi, pj), min(pi, pj)), -v);
+  }
+}
+
+// y_r = (b_r - h . x) / d  after the reduced system has been solved
+__global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV, const double* __restrict__ scale, const double* __restrict__ diag,
+                                                         double inv_radius, const double* __restrict__ g) {
+  const int k = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= SV.n_rho) return;
+  const int lm = SV.lm_of_rho[k];
+  const int rs = SV.row_start[lm], len = SV.row_start[lm + 1] - rs;
+  const int t = SV.base + k;
+  const double sr = scale[t];
+  const double d = SV.Hrr[k] * sr * sr + diag[t] * inv_radius;
+  double acc = 0.0;
+  for (int i = lane; i < len; i += 32) {
+    const int p = SV.row_pos[rs + i];
+    if (p < 0) continue;
+    const double xv = p < A.nb ? A.x[p] : A.x[static_cast<size_t>(A.NT) * 32 + (p - A.nb)];
+    acc += SV.Hrx[rs + i] * scale[p] * sr * xv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  if (lane == 0) SV.yrho[k] = (-g[t] * sr - acc) / d;
 }
 
 // ---- 32x32 Cholesky + inverse in one warp ----------------------------------------------------------------------------
@@ -289,12 +352,12 @@ __global__ void __launch_bounds__(1024) band_backsolve_kernel(BandSys S) {
 }
 
 // y (tangent order) from the solver's x, delta = S y, and the scalars of the step: [2] y.g_s  [3] sum D2 y^2  [4] #non-finite
-__global__ void __launch_bounds__(256) finish_step_kernel(BandSys A, int nt, const double* __restrict__ scale, const double* __restrict__ diag,
+__global__ void __launch_bounds__(256) finish_step_kernel(BandSys A, SchurView SV, int nt, const double* __restrict__ scale, const double* __restrict__ diag,
                                                           double inv_radius, const double* __restrict__ g, double* __restrict__ y,
                                                           double* __restrict__ delta, double* __restrict__ scal) {
   double yg = 0.0, dy = 0.0, nf = 0.0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
-    const double v = t < A.nb ? A.x[t] : A.x[static_cast<size_t>(A.NT) * 32 + (t - A.nb)];
+    const double v = t < A.nb ? A.x[t] : t < SV.base ? A.x[static_cast<size_t>(A.NT) * 32 + (t - A.nb)] : SV.yrho[t - SV.base];
     y[t] = v;
     delta[t] = v * scale[t];
     if (!isfinite(v)) nf += 1.0;
@@ -417,6 +480,8 @@ static void linearize(lvi_problem* p) {
     allreduce_sum(ctx, p->H_tiles.p, p->H_tiles.n);
     allreduce_sum(ctx, p->H_C.p, p->H_C.n);
     allreduce_sum(ctx, p->g.p, p->g.n);
+    allreduce_sum(ctx, p->Hrx.p, p->Hrx.n);
+    allreduce_sum(ctx, p->Hrr.p, p->Hrr.n);
     allreduce_sum(ctx, p->scal.p, 1);
   }
 }
@@ -427,14 +492,33 @@ static void trial_cost(lvi_problem* p, const double* x_d, double* cost_d, bool a
 
 static inline int blocks_for(int n) { return std::max(1, (n + 255) / 256); }
 
+static size_t max_row_len(const lvi_problem* p) {
+  size_t m = 0;
+  for (size_t l = 0; l + 1 < p->L.row_start.size(); ++l) m = std::max<size_t>(m, p->L.row_start[l + 1] - p->L.row_start[l]);
+  return m;
+}
+static void schur_eliminate(lvi_problem* p, double inv_radius) {
+  if (p->L.n_rho == 0) return;
+  static size_t attr = 48 * 1024;
+  const size_t smem = max_row_len(p) * 12 + 16;
+  if (smem > attr) { LVI_CUDA(cudaFuncSetAttribute(schur_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = smem; }
+  LVI_LAUNCH(p->ctx, schur_eliminate_kernel, p->L.n_rho, 128, smem, p->A, p->schur, p->scale.p, p->diag.p, inv_radius, p->g.p);
+}
+static void schur_back(lvi_problem* p, double inv_radius) {
+  if (p->L.n_rho == 0) return;
+  LVI_LAUNCH(p->ctx, schur_back_kernel, (p->L.n_rho + 3) / 4, 128, 0, p->A, p->schur, p->scale.p, p->diag.p, inv_radius, p->g.p);
+}
+
 static void compute_step(lvi_problem* p, double radius) {  // A = S H S + D^2 ; factor ; solve ; y, delta, scalars
   lvi_ctx* ctx = p->ctx;
   const int ntile = p->A.NT * p->A.TPC;
   const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
   LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, 1.0 / radius, p->g.p);
+  schur_eliminate(p, 1.0 / radius);
   band_factor_solve(ctx, p->A);
+  schur_back(p, 1.0 / radius);
   LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), ctx->stream));
-  LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p, 1.0 / radius, p->g.p,
+  LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->schur, p->nt, p->scale.p, p->diag.p, 1.0 / radius, p->g.p,
              p->y.p, p->delta.p, p->scal.p);
 }
 
@@ -449,7 +533,7 @@ static void diff_norms(lvi_problem* p) {  // scal[5..7]
 }
 
 static void refresh_diag(lvi_problem* p, DBuf<double>& dH, const lvi_solve_options& o) {
-  LVI_LAUNCH(p->ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->nt, dH.p);
+  LVI_LAUNCH(p->ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->schur, p->nt, dH.p);
   LVI_LAUNCH(p->ctx, lm_diag_kernel, blocks_for(p->nt), 256, 0, dH.p, p->scale.p, p->nt, o.min_lm_diagonal, o.max_lm_diagonal, p->diag.p);
 }
 
@@ -479,7 +563,7 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   S.num_residual_blocks = p->L.n_res_blocks; S.num_residuals = p->L.n_res; S.num_effective_parameters = nt;
   S.band_width = p->L.bw; S.border_width = p->L.nbo;
   // Jacobi scaling at iteration 0
-  LVI_LAUNCH(ctx, diag_kernel, blocks_for(nt), 256, 0, p->H, nt, dH.p);
+  LVI_LAUNCH(ctx, diag_kernel, blocks_for(nt), 256, 0, p->H, p->schur, nt, dH.p);
   LVI_LAUNCH(ctx, scale_init_kernel, blocks_for(nt), 256, 0, dH.p, nt, o.jacobi_scaling, p->scale.p);
   auto grad_max_norm = [&]() {  // || x - Plus(x, -g) ||_inf (with bounds projection)
     apply_plus(p, p->g.p, 1.0, -1.0);
@@ -621,7 +705,7 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
     LVI_CUDA(cudaEventCreate(&t0)); LVI_CUDA(cudaEventCreate(&t1));
     float acc[5] = {0, 0, 0, 0, 0};
     linearize(p);
-    LVI_LAUNCH(ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->nt, dH.p);
+    LVI_LAUNCH(ctx, diag_kernel, blocks_for(p->nt), 256, 0, p->H, p->schur, p->nt, dH.p);
     LVI_LAUNCH(ctx, scale_init_kernel, blocks_for(p->nt), 256, 0, dH.p, p->nt, 1, p->scale.p);
     const double inv_radius = 1.0 / o.initial_trust_region_radius;
     LVI_CUDA(cudaStreamSynchronize(st));
@@ -634,12 +718,14 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
       const int ntile = p->A.NT * p->A.TPC;
       const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
       LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, inv_radius, p->g.p);
+      schur_eliminate(p, inv_radius);
       LVI_CUDA(cudaEventRecord(ev[2], st));
       band_factor_only(ctx, p->A);
       LVI_CUDA(cudaEventRecord(ev[3], st));
       band_solve_only(ctx, p->A);
+      schur_back(p, inv_radius);
       LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), st));
-      LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->nt, p->scale.p, p->diag.p, inv_radius, p->g.p,
+      LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->schur, p->nt, p->scale.p, p->diag.p, inv_radius, p->g.p,
                  p->y.p, p->delta.p, p->scal.p);
       LVI_CUDA(cudaEventRecord(ev[4], st));
       apply_plus(p, p->delta.p, 1.0, 1.0);

@@ -69,7 +69,8 @@ __global__ void voxel_grid_params_kernel(const int* __restrict__ mm, float leaf,
   const long long dx = static_cast<long long>((p.mx[0] - p.mn[0]) * inv) + 1;  // impl.hpp:75-77
   const long long dy = static_cast<long long>((p.mx[1] - p.mn[1]) * inv) + 1;
   const long long dz = static_cast<long long>((p.mx[2] - p.mn[2]) * inv) + 1;
-  if (dx * dy * dz > 2147483647LL) { p.status = 2; *g = p; return; }
+  // the reference multiplies in int64 (:80); the double product guards the cases where that itself would wrap
+  if (static_cast<double>(dx) * static_cast<double>(dy) * static_cast<double>(dz) > 2147483647.0 || dx * dy * dz > 2147483647LL) { p.status = 2; *g = p; return; }
   for (int k = 0; k < 3; ++k) {
     p.min_b[k] = static_cast<int>(floorf(p.mn[k] * inv));  // :87-92
     const int max_b = static_cast<int>(floorf(p.mx[k] * inv));

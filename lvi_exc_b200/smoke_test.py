@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import pipeline, synth
+from . import pipeline, synth, workload
 from .backend import CudaBackend, CudaProblem
 
 
@@ -45,18 +45,20 @@ def run(verbose: bool = True) -> None:
     s_g, s_o = cb.solve(pd_g, 30), orc.solve(pd_o, 30)
     assert abs(s_g.final_cost - s_o.final_cost) <= 1e-6 * max(1.0, s_o.final_cost), (s_g.final_cost, s_o.final_cost)
     assert np.abs(pd_g.so3_knots - pd_o.so3_knots).max() < 1e-6
-    mgr._copy_back(pd_o)
-    pd_g = mgr.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
-    pd_o = mgr.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
+    # S1 from a state near the optimum (control points sampled from the ground truth): far from it the 2 s problem is so
+    # ill-conditioned that the LM path is chaotic (the oracle's own path then depends on its thread count)
+    mgr1 = workload.make_manager(seq)
+    pd_g = mgr1.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
+    pd_o = mgr1.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
     ev_g, ev_o = CudaProblem(cb, pd_g).evaluate(gradient=False), ob.OracleProblem(pd_o).evaluate(gradient=False)
     assert abs(ev_g["cost"] - ev_o["cost"]) <= 1e-9 * ev_o["cost"], (ev_g["cost"], ev_o["cost"])
     assert np.abs(ev_g["residuals"] - ev_o["residuals"]).max() <= 1e-7 * max(1.0, np.abs(ev_o["residuals"]).max())
-    # 3 iterations: far from the optimum the LM path is chaotic beyond that (the oracle itself depends on its thread count there)
-    s_g, s_o = cb.solve(pd_g, 3), orc.solve(pd_o, 3)
+    s_g, s_o = cb.solve(pd_g, 5), orc.solve(pd_o, 5)
     rel = abs(s_g.final_cost - s_o.final_cost) / s_o.final_cost
     assert rel < 1e-6, (s_g.final_cost, s_o.final_cost)
+    assert pipeline.quat_angle(pd_g.lidar_q, pd_o.lidar_q) < 1e-4 and np.abs(pd_g.lidar_p - pd_o.lidar_p).max() < 1e-3
     if verbose:
         print(f"smoke ok: leaves {gmap.num_leaves}, planes {gmap.num_planes}, surfel points {len(sp_g)}, "
-              f"S0 cost {s_g.final_cost:.6e}, S1(3 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
+              f"S0 cost {s_g.final_cost:.6e}, S1(5 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
               f"kernel launches {cb.launches}")
     cb.close()

@@ -155,7 +155,8 @@ VoxelMap* voxel_build(const float* pts, size_t stride_floats, int64_t n, float l
   const int64_t dx = static_cast<int64_t>((mx[0] - mn[0]) * inv) + 1;
   const int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv) + 1;
   const int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv) + 1;
-  if (dx * dy * dz > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) { m->status = 2; return m; }
+  if (static_cast<double>(dx) * static_cast<double>(dy) * static_cast<double>(dz) > 2147483647.0 ||
+      dx * dy * dz > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) { m->status = 2; return m; }
   for (int k = 0; k < 3; ++k) {  // impl.hpp:87-92
     m->min_b[k] = static_cast<int>(std::floor(mn[k] * inv));
     m->max_b[k] = static_cast<int>(std::floor(mx[k] * inv));

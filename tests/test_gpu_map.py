@@ -168,13 +168,16 @@ def test_landmark_association(cuda_backend):
 
 
 def test_pipeline_matches_oracle(cuda_backend):
-    """LCIoptimize replay on 3 s of data: extrinsics within the north-star tolerance of the CPU path (1e-4 rad / 1e-3 m)"""
-    cfg = synth.default_config(duration=3.0, n_landmarks=400)
+    """LCIoptimize replay (3 data associations + S0..S5, default iteration limits) on 6 s of data: extrinsics within the north-star
+    tolerance of the CPU path (1e-4 rad / 1e-3 m), same association counts, same iteration counts"""
+    cfg = synth.default_config(duration=6.0, n_landmarks=800)
     seq = synth.make_sequence(cfg)
-    pcfg = pipeline.PipelineConfig(iters_li=12, iters_lvi=12, n_refine=1)
-    og = pipeline.run_calibration(seq, cuda_backend, pcfg)
-    oo = pipeline.run_calibration(seq, OracleBackend(), pcfg)
+    og = pipeline.run_calibration(seq, cuda_backend)
+    oo = pipeline.run_calibration(seq, OracleBackend())
     cg, co = og["calib"], oo["calib"]
+    assert og["assoc_counts"] == oo["assoc_counts"] and og.get("n_lm_plane") == oo.get("n_lm_plane")
     assert pipeline.quat_angle(cg.q_LtoI, co.q_LtoI) < 1e-4 and np.linalg.norm(cg.p_LinI - co.p_LinI) < 1e-3
     assert pipeline.quat_angle(cg.q_CtoI, co.q_CtoI) < 1e-4 and np.linalg.norm(cg.p_CinI - co.p_CinI) < 1e-3
     assert [s["iterations"] for s in og["stages"]] == [s["iterations"] for s in oo["stages"]]
+    for a, b in zip(og["stages"], oo["stages"]):
+        assert a["final_cost"] == pytest.approx(b["final_cost"], rel=1e-5)
