@@ -254,7 +254,7 @@ static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBu
   S.ldc = S.RB * kTile;
   tiles.alloc(std::max<size_t>(static_cast<size_t>(S.NT) * S.TPC * kTileElems, 1));
   C.alloc(static_cast<size_t>(S.ldc) * S.ldc);
-  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail;
+  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail; S.work_i = nullptr; S.work_d = nullptr;
 }
 
 void problem_ensure_solver_buffers(lvi_problem* p) {
@@ -267,6 +267,9 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
   p->A_x.alloc(static_cast<size_t>(NT) * kTile + static_cast<size_t>(RB) * kTile);
   alloc_bandsys(p->H, L, p->H_tiles, p->H_C, nullptr, nullptr, nullptr);
   alloc_bandsys(p->A, L, p->A_tiles, p->A_C, p->A_Linv.p, p->A_x.p, p->fail.p);
+  p->A_work_i.alloc(p->A.work_i_count()); p->A_work_d.alloc(std::max<size_t>(p->A.work_d_count(), 1));
+  p->A.work_i = p->A_work_i.p; p->A.work_d = p->A_work_d.p;
+  LVI_REQUIRE(p->A.ldc <= 1024, LVI_ERR_INVALID, "arrow border wider than 1023 dims is not supported");
   const size_t nt = std::max(p->nt, 1);
   {  // Schur rows of the inverse depths
     cudaStream_t st = p->ctx->stream;

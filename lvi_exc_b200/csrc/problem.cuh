@@ -27,6 +27,10 @@ struct BandSys {
   double* Linv;      // [NT * 1024] inverse of each diagonal Cholesky block (filled by the factorisation)
   double* x;         // [NT*32 + ldc] solution (band part then border part)
   int* fail;         // != 0: Cholesky breakdown
+  int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters] (zeroed per solve)
+  double* work_d;    // [NT*32] partial sums of the back substitution
+  size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
+  size_t work_d_count() const { return static_cast<size_t>(NT) * 32; }
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row
@@ -75,7 +79,8 @@ struct lvi_problem {
   lvi::ProblemView view{};   // device pointers, parameters -> X
   // normal equations
   lvi::BandSys H{}, A{};
-  lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x;
+  lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x, A_work_d;
+  lvi::DBuf<int> A_work_i;
   lvi::SchurView schur{};
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;

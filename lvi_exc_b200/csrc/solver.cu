@@ -17,7 +17,9 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "nccl_dyn.hpp"
 #include "problem.cuh"
@@ -273,6 +275,192 @@ __global__ void __launch_bounds__(256) band_factor_kernel(BandSys S) {
   }
 }
 
+// ---- flag-driven left-looking band Cholesky (default) -----------------------------------------------------------------------
+// The cooperative kernel above pays two grid-wide barriers per 32-column block step (567 steps at 60 s) and leaves the SMs idle while
+// one warp factors the diagonal tile.  Here every 32x32 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a
+// global counter, keeps the tile's accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source
+// tiles are published (per-tile ready flags, ld.acquire / st.release), then finishes it (diagonal: warp Cholesky + inverse; else
+// X = P W_j^T) and publishes it.  Each tile is written once by one CTA (no read-modify-write on HBM), only the dependency chain
+// potrf(j) -> trsm(j+1,j) -> potrf(j+1) is serial, and everything off the chain overlaps it.  Tasks are fetched in dependency order,
+// so a fetched task only ever waits on tasks already held by running CTAs: no deadlock for any grid size.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void spin_until_set(const int* f) {
+  while (ld_acquire(f) == 0) __nanosleep(32);
+}
+
+__global__ void __launch_bounds__(256) band_factor_ll_kernel(BandSys S) {
+  __shared__ double sL[32 * kLP], sW[32 * kLP], sA[kTileElems], sB[kTileElems];
+  __shared__ int s_q;
+  int* flags = S.work_i;
+  int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
+  const int ntask = S.NT * S.TPC;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a = tid & 31, c0 = tid >> 5;
+  while (true) {
+    if (tid == 0) s_q = atomicAdd(counter, 1);
+    __syncthreads();
+    const int q = s_q;
+    __syncthreads();
+    if (q >= ntask) break;
+    const int j = q / S.TPC, s = q - j * S.TPC;
+    const bool band = s <= S.T;
+    const int i = j + s;
+    if (band && i >= S.NT) continue;  // tile below the end of the band: never referenced
+    double* tile = S.tiles + (static_cast<size_t>(q) << 10);
+    double acc[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
+    const int kmin = band ? max(0, i - S.T) : max(0, j - S.T);
+    for (int k = kmin; k < j; ++k) {
+      const int fi = k * S.TPC + (band ? (i - k) : s);
+      const int fj = k * S.TPC + (j - k);
+      if (tid == 0) spin_until_set(flags + fi);
+      if (tid == 32 && fj != fi) spin_until_set(flags + fj);
+      __syncthreads();  // sources published; previous k-step's reads of sA/sB are complete
+      const double* Li = S.tiles + (static_cast<size_t>(fi) << 10);
+      const double* Lj = S.tiles + (static_cast<size_t>(fj) << 10);
+#pragma unroll
+      for (int e = tid; e < kTileElems; e += 256) { sA[e] = __ldcg(Li + e); sB[e] = __ldcg(Lj + e); }
+      __syncthreads();
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) {
+        const double xa = sA[a + 32 * m];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[jj] -= xa * sB[c0 + 8 * jj + 32 * m];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = acc[jj];
+    if (s == 0) {  // diagonal tile: L_jj and W_j = L_jj^-1 (only W is kept: panel solves and back substitution multiply by it)
+      __syncthreads();
+      if (warp == 0) {
+        const bool ok = warp_potrf_inv(sA, sL, sW);
+        if (!ok && tid == 0) *S.fail = 1;
+      }
+      __syncthreads();
+      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      for (int e = tid; e < kTileElems; e += 256) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(flags + q, 1);
+    } else {
+      if (tid == 0) spin_until_set(flags + j * S.TPC);
+      __syncthreads();
+      const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      for (int e = tid; e < kTileElems; e += 256) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
+      __syncthreads();
+      double out[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c = c0 + 8 * jj;
+        double v = 0.0;
+        for (int m = 0; m <= c; ++m) v += sA[a + 32 * m] * sW[c * kLP + m];
+        out[jj] = v;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(flags + q, 1);
+      if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
+        for (int bi = 0; bi < S.RB; ++bi)
+          for (int bj = 0; bj <= bi; ++bj) {
+            const int fa = j * S.TPC + S.T + 1 + bi, fb = j * S.TPC + S.T + 1 + bj;
+            if (tid == 0) { spin_until_set(flags + fa); spin_until_set(flags + fb); }
+            __syncthreads();
+            const double* Xa = S.tiles + (static_cast<size_t>(fa) << 10);
+            const double* Xb = S.tiles + (static_cast<size_t>(fb) << 10);
+            for (int e = tid; e < kTileElems; e += 256) { sA[e] = __ldcg(Xa + e); sB[e] = __ldcg(Xb + e); }
+            __syncthreads();
+            double pr[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int m = 0; m < 32; ++m) {
+              const double xa = sA[a + 32 * m];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) pr[jj] += xa * sB[c0 + 8 * jj + 32 * m];
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (pr[jj] != 0.0) atomicAdd(S.C + 32 * bi + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
+            __syncthreads();
+          }
+      }
+    }
+  }
+}
+
+// ---- flag-driven backward substitution: x_m = W_m^T (z_m - Lb(:,m)^T x2 - sum_d L(m+d,m)^T x_{m+d}) ------------------------------------
+// One task per block column, fetched in descending order.  A task prefetches W_m and its first sub-diagonal tile while it waits for the
+// contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of k = m-1 (first: it is
+// the dependency chain), m-2, ... m-T with one warp per tile.
+__global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
+  __shared__ double sW[kTileElems], sT[kTileElems], sx[32], sv[32], x2s[1024];
+  __shared__ int s_q;
+  int* arrivals = S.work_i + static_cast<size_t>(S.NT) * S.TPC;
+  int* counter = arrivals + S.NT + 1;
+  double* vsum = S.work_d;
+  double* x = S.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < S.ldc; i += 256) x2s[i] = x[static_cast<size_t>(S.NT) * 32 + i];
+  const int zrb = S.nbo >> 5, zrow = S.nbo & 31;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(counter, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= S.NT) break;
+    const int m = S.NT - 1 - q;
+    const int Tm = min(S.T, S.NT - 1 - m);
+    const double* col = S.tiles + static_cast<size_t>(m) * S.TPC * kTileElems;
+    const double* Wg = S.Linv + static_cast<size_t>(m) * kTileElems;
+    for (int e = tid; e < kTileElems; e += 256) sW[e] = Wg[e];
+    if (m >= 1) {
+      const double* t1 = S.tiles + (static_cast<size_t>(m - 1) * S.TPC + 1) * kTileElems;
+      for (int e = tid; e < kTileElems; e += 256) sT[e] = t1[e];
+    }
+    // border part of the right-hand side (independent of the chain)
+    double bsum = 0.0;
+    if (warp == 0) {
+      for (int rb = 0; rb < S.RB; ++rb) {
+        const double* bt = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems + 32 * lane;
+        const double* xv = x2s + 32 * rb;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) bsum += bt[r] * xv[r];
+      }
+      bsum = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + 32 * lane] - bsum;  // z_m - Lb^T x2
+      if (lane == 0) while (ld_acquire(arrivals + m) < Tm) __nanosleep(32);
+      __syncwarp();
+      sv[lane] = bsum - __ldcg(vsum + static_cast<size_t>(m) * 32 + lane);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xk = 0.0;
+      for (int r = lane; r < 32; ++r) xk += sW[r + 32 * lane] * sv[r];  // column `lane` of W (lower triangular)
+      sx[lane] = xk;
+      x[static_cast<size_t>(m) * 32 + lane] = xk;
+    }
+    __syncthreads();
+    const int nd = min(S.T, m);
+    for (int d = 1 + warp; d <= nd; d += 8) {
+      const int k = m - d;
+      const double* tl = (d == 1) ? sT : S.tiles + (static_cast<size_t>(k) * S.TPC + d) * kTileElems;
+      double u = 0.0;
+      const double* tc = tl + 32 * lane;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) u += tc[r] * sx[r];
+      atomicAdd(vsum + static_cast<size_t>(k) * 32 + lane, u);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(arrivals + k, 1);
+    }
+  }
+}
+
 // dense Cholesky of the border Schur complement S (nbo x nbo, lower, column-major ld = ldc) with the rhs carried as row nbo,
 // then x2 = L^-T z2.  One CTA.
 __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
@@ -434,20 +622,42 @@ static int coop_grid_limit(lvi_ctx* ctx) {
   return limit;
 }
 
+static bool use_coop_solver() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("LVI_BAND_SOLVER"); v = (e && std::string(e) == "coop") ? 1 : 0; }
+  return v == 1;
+}
+static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads) {
+  int per_sm = 0;
+  LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  return std::max(1, per_sm) * ctx->sm_count;
+}
 static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   cudaStream_t st = ctx->stream;
   LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), st));
-  if (A.NT > 0) {
+  if (A.NT == 0) return;
+  if (use_coop_solver() || !A.work_i) {
     const int ops = A.T * (A.T + 1) / 2 + A.RB * A.T + A.RB * (A.RB + 1) / 2;
     int grid = std::min(coop_grid_limit(ctx), std::max(1, ops));
     void* args[] = {&A};
     LVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band_factor_kernel), dim3(grid), dim3(256), args, 0, st));
     ++ctx->launches;
+    return;
   }
+  LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
+  LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
+  static int resident = 0;
+  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), 256);
+  const int grid = std::min(resident, A.NT * A.TPC);
+  LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, 256, 0, A);
 }
 static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
   LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
-  if (A.NT > 0) LVI_LAUNCH(ctx, band_backsolve_kernel, 1, 1024, 0, A);
+  if (A.NT == 0) return;
+  if (use_coop_solver() || !A.work_i) { LVI_LAUNCH(ctx, band_backsolve_kernel, 1, 1024, 0, A); return; }
+  static int resident = 0;
+  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256);
+  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(resident, A.NT), 256, 0, A);
 }
 void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
   band_factor_only(ctx, A);
@@ -803,6 +1013,9 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
     DBuf<int> fail(4);
     tiles.upload(ht.data(), ht.size(), st); C.upload(hc.data(), hc.size(), st);
     S.tiles = tiles.p; S.C = C.p; S.Linv = Linv.p; S.x = x.p; S.fail = fail.p;
+    DBuf<int> wi(S.work_i_count());
+    DBuf<double> wd(std::max<size_t>(S.work_d_count(), 1));
+    S.work_i = wi.p; S.work_d = wd.p;
     band_factor_solve(ctx, S);
     std::vector<double> hx(x.n);
     int hf = 0;
