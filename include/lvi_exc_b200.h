@@ -45,6 +45,9 @@ typedef struct lvi_problem lvi_problem; /* replaces kontiki::TrajectoryEstimator
 
 const char* lvi_last_error(void);
 int lvi_abi_version(void);
+/* sizeof of the ABI structures, for binding generators: 0 lvi_problem_desc, 1 lvi_solve_options, 2 lvi_solve_summary,
+ * 3 lvi_point_xyzit, 4 lvi_surfel_point (defined below); -1 otherwise */
+int64_t lvi_abi_sizeof(int which);
 /* number of CUDA devices visible (0 on a CPU-only host; never an error) */
 int lvi_device_count(void);
 

@@ -124,7 +124,7 @@ _lib = None
 
 # every symbol include/lvi_exc_b200.h declares (tests/test_abi.py checks the built library exports all of them)
 ABI_SYMBOLS = [
-    "lvi_last_error", "lvi_abi_version", "lvi_device_count", "lvi_ctx_create", "lvi_ctx_destroy", "lvi_ctx_synchronize",
+    "lvi_last_error", "lvi_abi_version", "lvi_abi_sizeof", "lvi_device_count", "lvi_ctx_create", "lvi_ctx_destroy", "lvi_ctx_synchronize",
     "lvi_ctx_stream", "lvi_ctx_launch_count", "lvi_nccl_unique_id", "lvi_ctx_create_nccl",
     "lvi_voxel_build", "lvi_voxel_build_d", "lvi_voxel_destroy", "lvi_voxel_num_leaves", "lvi_voxel_num_points",
     "lvi_voxel_grid", "lvi_voxel_export", "lvi_surfel_extract", "lvi_surfel_destroy", "lvi_surfel_count",

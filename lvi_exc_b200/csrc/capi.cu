@@ -15,6 +15,17 @@ extern "C" {
 
 const char* lvi_last_error(void) { return g_error.c_str(); }
 int lvi_abi_version(void) { return LVI_ABI_VERSION; }
+/* sizeof of the ABI structures, for binding generators: 0 problem_desc, 1 solve_options, 2 solve_summary, 3 point_xyzit, 4 surfel_point */
+int64_t lvi_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(lvi_problem_desc);
+    case 1: return sizeof(lvi_solve_options);
+    case 2: return sizeof(lvi_solve_summary);
+    case 3: return sizeof(lvi_point_xyzit);
+    case 4: return sizeof(lvi_surfel_point);
+    default: return -1;
+  }
+}
 int lvi_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

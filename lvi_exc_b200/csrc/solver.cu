@@ -151,37 +151,41 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
 }
 
 // ---- 32x32 Cholesky + inverse in one warp ----------------------------------------------------------------------------
-// lane a owns row a of the tile (column-major in global).  Writes L (lower, zero upper) to sL[r*33+c] and W = L^-1 to sW[r*33+m].
-__device__ __forceinline__ bool warp_potrf_inv(const double* tile, double* sL, double* sW) {
+// lane a owns row a of the tile (column-major source, global or shared).  Everything stays in registers (fully unrolled, constant
+// indices): Cholesky right-looking with one rsqrt per column, then W = L^-1 column-parallel and right-looking so that the 496 FMAs of
+// a lane are independent.  Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].
+__device__ __noinline__ bool warp_potrf_inv(const double* tile, double* sL, double* sW) {
   const int a = threadIdx.x & 31;
   double A[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) A[c] = tile[a + 32 * c];
   bool bad = false;
+  double rinv = 0.0;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     double d = __shfl_sync(FULL, A[j], j);
     if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-    const double s = sqrt(d);
-    const double l = (a == j) ? s : A[j] / s;
+    const double ri = rsqrt(d);
+    const double l = A[j] * ri;  // row j: d / sqrt(d) = sqrt(d)
     A[j] = l;
+    if (a == j) rinv = ri;
 #pragma unroll
     for (int c = j + 1; c < 32; ++c) {
       const double lc = __shfl_sync(FULL, l, c);
-      if (a >= c) A[c] -= l * lc;
+      A[c] = (a >= c) ? fma(-l, lc, A[c]) : A[c];
     }
   }
 #pragma unroll
   for (int c = 0; c < 32; ++c) sL[a * kLP + c] = (c <= a) ? A[c] : 0.0;
   __syncwarp();
-  // column a of W: forward substitution L w = e_a
   double w[32];
 #pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    double acc = (r == a) ? 1.0 : 0.0;
+  for (int r = 0; r < 32; ++r) w[r] = (r == a) ? 1.0 : 0.0;
 #pragma unroll
-    for (int t = 0; t < r; ++t) acc -= sL[r * kLP + t] * w[t];
-    w[r] = acc / sL[r * kLP + r];
+  for (int t = 0; t < 32; ++t) {
+    w[t] *= __shfl_sync(FULL, rinv, t);
+#pragma unroll
+    for (int r = t + 1; r < 32; ++r) w[r] = fma(-sL[r * kLP + t], w[t], w[r]);
   }
 #pragma unroll
   for (int r = 0; r < 32; ++r) sW[r * kLP + a] = w[r];
@@ -290,10 +294,10 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void spin_until_set(const int* f) {
-  while (ld_acquire(f) == 0) __nanosleep(32);
+  while (ld_acquire(f) == 0) {}
 }
 
-__global__ void __launch_bounds__(256) band_factor_ll_kernel(BandSys S) {
+__global__ void __launch_bounds__(256, 1) band_factor_ll_kernel(BandSys S) {
   __shared__ double sL[32 * kLP], sW[32 * kLP], sA[kTileElems], sB[kTileElems];
   __shared__ int s_q;
   int* flags = S.work_i;
@@ -346,9 +350,8 @@ __global__ void __launch_bounds__(256) band_factor_ll_kernel(BandSys S) {
       __syncthreads();
       double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
       for (int e = tid; e < kTileElems; e += 256) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release(flags + q, 1);
+      __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
+      if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
     } else {
       if (tid == 0) spin_until_set(flags + j * S.TPC);
       __syncthreads();
@@ -365,9 +368,8 @@ __global__ void __launch_bounds__(256) band_factor_ll_kernel(BandSys S) {
       }
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
-      __threadfence();
       __syncthreads();
-      if (tid == 0) st_release(flags + q, 1);
+      if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
       if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
         for (int bi = 0; bi < S.RB; ++bi)
           for (int bj = 0; bj <= bi; ++bj) {
