@@ -3,7 +3,7 @@
 // HBM layout:
 //   X        one flat fp64 parameter vector [r3 3n | so3 4n | sens 22 | rho nl]; a second copy XC holds the LM candidate
 //   tables   per residual type SoA (ResTable, residuals.cuh), in the caller's (chronological) order
-//   H / A    normal equations in 32x32 TILE storage: block column J holds tiles d = 0..T (band, rows 32(J+d)..) followed by
+//   H / A    normal equations in 64x64 TILE storage: block column J holds tiles d = 0..T (band, rows 64(J+d)..) followed by
 //            RB border tiles (arrow rows: map-time knots + sensor blocks + one extra row carrying the right-hand side);
 //            the border x border corner is a small dense matrix C.  Never dense n^2 (SURVEY §5 "long-context").
 #pragma once
@@ -14,23 +14,24 @@
 
 namespace lvi {
 
-constexpr int kTile = 32;
+constexpr int kTileLog = 6;
+constexpr int kTile = 1 << kTileLog;      // 64 x 64 fp64 tiles (32 KB)
 constexpr int kTileElems = kTile * kTile;
 
 struct BandSys {
   int nb, nbo;       // band dims, border dims (without the rhs row)
   int NT, T, RB;     // block columns, sub-diagonal tile rows, border tile rows
   int TPC;           // tiles per block column = T + 1 + RB
-  int ldc;           // RB * 32
-  double* tiles;     // [NT * TPC * 1024]
+  int ldc;           // RB * kTile
+  double* tiles;     // [NT * TPC * kTileElems], each tile column-major
   double* C;         // [ldc * ldc] column-major, lower
-  double* Linv;      // [NT * 1024] inverse of each diagonal Cholesky block (filled by the factorisation)
-  double* x;         // [NT*32 + ldc] solution (band part then border part)
+  double* Linv;      // [NT * kTileElems] inverse of each diagonal Cholesky block (filled by the factorisation)
+  double* x;         // [NT*kTile + ldc] solution (band part then border part)
   int* fail;         // != 0: Cholesky breakdown
   int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters] (zeroed per solve)
-  double* work_d;    // [NT*32] partial sums of the back substitution
+  double* work_d;    // [NT*kTile] partial sums of the back substitution
   size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
-  size_t work_d_count() const { return static_cast<size_t>(NT) * 32; }
+  size_t work_d_count() const { return static_cast<size_t>(NT) * kTile; }
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row
@@ -38,12 +39,12 @@ __device__ __forceinline__ double* band_addr(const BandSys& S, int i, int j) {
   if (j >= S.nb) {
     return S.C + (i - S.nb) + static_cast<size_t>(S.ldc) * (j - S.nb);
   }
-  const int J = j >> 5;
+  const int J = j >> kTileLog;
   size_t tile;
   int a;
-  if (i >= S.nb) { const int b = i - S.nb; tile = static_cast<size_t>(J) * S.TPC + S.T + 1 + (b >> 5); a = b & 31; }
-  else { tile = static_cast<size_t>(J) * S.TPC + ((i >> 5) - J); a = i & 31; }
-  return S.tiles + (tile << 10) + ((j & 31) << 5) + a;
+  if (i >= S.nb) { const int b = i - S.nb; tile = static_cast<size_t>(J) * S.TPC + S.T + 1 + (b >> kTileLog); a = b & (kTile - 1); }
+  else { tile = static_cast<size_t>(J) * S.TPC + ((i >> kTileLog) - J); a = i & (kTile - 1); }
+  return S.tiles + (tile << (2 * kTileLog)) + ((j & (kTile - 1)) << kTileLog) + a;
 }
 
 // Schur rows of the inverse depths (lowering.hpp): H_rr (diagonal), H_rx as one dense row per landmark over its coupling slots

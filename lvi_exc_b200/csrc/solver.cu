@@ -5,16 +5,15 @@
 // tolerances.  Ceres is not vendored; the loop below restates TrustRegionMinimizer +
 // LevenbergMarquardtStrategy step by step and is kept line-for-line comparable with the CPU oracle (oracle/orc_solve.cpp).
 //
-// Linear algebra: (S H S + D^2) y = -S g with H in 32x32 tile storage (problem.cuh).
-//   band_factor_kernel   cooperative persistent kernel, right-looking blocked Cholesky.  Per block column: every CTA factors the
-//                        32x32 diagonal tile in ONE WARP (rows in registers, shuffles, no barriers) and inverts it; the panel
-//                        (band tiles + arrow-border tiles + the rhs row, so the forward substitution comes for free) is solved
-//                        as a small GEMM against the inverse; grid.sync; trailing tiles are updated X_i X_j^T; grid.sync.
-//   corner_solve_kernel  dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
-//   band_backsolve_kernel  backward substitution, one CTA, 32 warps over the tiles of a block row.
+// Linear algebra: (S H S + D^2) y = -S g with H in 64x64 tile storage (problem.cuh), inverse depths eliminated first (Schur).
+//   band_factor_ll_kernel     flag-driven left-looking tile Cholesky: one task per 64x64 tile of the factor, fetched in column-major
+//                             order; the accumulator lives in registers and L(i,k) L(j,k)^T is subtracted as soon as both source tiles
+//                             are published (ld.acquire / st.release flags).  The diagonal task factors its 64x64 block entirely in
+//                             shared memory (two warp-level 32x32 Choleskys + glue GEMMs) and publishes W = L_jj^-1; panel tiles
+//                             (band + arrow border + the rhs row, so the forward substitution comes for free) finish as X = P W^T.
+//   corner_solve_kernel       dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
+//   band_backsolve_ll_kernel  flag-driven backward substitution, one task per block column.
 // All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
-#include <cooperative_groups.h>
-
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -23,8 +22,6 @@
 
 #include "nccl_dyn.hpp"
 #include "problem.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace lvi {
 
@@ -53,20 +50,20 @@ __global__ void __launch_bounds__(256) build_system_kernel(BandSys H, BandSys A,
   if (static_cast<int>(blockIdx.x) < ntile) {
     const int J = blockIdx.x / A.TPC, q = blockIdx.x % A.TPC;
     if (q <= A.T && J + q >= A.NT) return;
-    const double* src = H.tiles + (static_cast<size_t>(blockIdx.x) << 10);
-    double* dst = A.tiles + (static_cast<size_t>(blockIdx.x) << 10);
+    const double* src = H.tiles + static_cast<size_t>(blockIdx.x) * kTileElems;
+    double* dst = A.tiles + static_cast<size_t>(blockIdx.x) * kTileElems;
     for (int e = threadIdx.x; e < kTileElems; e += blockDim.x) {
-      const int a = e & 31, b = e >> 5;
-      const int j = J * 32 + b;
+      const int a = e & (kTile - 1), b = e >> kTileLog;
+      const int j = J * kTile + b;
       double v = 0.0;
       if (q <= A.T) {
-        const int i = (J + q) * 32 + a;
+        const int i = (J + q) * kTile + a;
         if (i < nb && j < nb) {
           if (i >= j) v = src[e] * scale[i] * scale[j];
           if (i == j) v += diag[i] * inv_radius;
         } else if (i == j) v = 1.0;  // padding rows keep the factorisation well defined
       } else if (j < nb) {
-        const int bi = (q - A.T - 1) * 32 + a;
+        const int bi = (q - A.T - 1) * kTile + a;
         if (bi < nbo) v = src[e] * scale[nb + bi] * scale[j];
         else if (bi == nbo) v = -g[j] * scale[j];
       }
@@ -142,7 +139,7 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
   for (int i = lane; i < len; i += 32) {
     const int p = SV.row_pos[rs + i];
     if (p < 0) continue;
-    const double xv = p < A.nb ? A.x[p] : A.x[static_cast<size_t>(A.NT) * 32 + (p - A.nb)];
+    const double xv = p < A.nb ? A.x[p] : A.x[static_cast<size_t>(A.NT) * kTile + (p - A.nb)];
     acc += SV.Hrx[rs + i] * scale[p] * sr * xv;
   }
 #pragma unroll
@@ -151,14 +148,15 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
 }
 
 // ---- 32x32 Cholesky + inverse in one warp ----------------------------------------------------------------------------
-// lane a owns row a of the tile (column-major source, global or shared).  Everything stays in registers (fully unrolled, constant
-// indices): Cholesky right-looking with one rsqrt per column, then W = L^-1 column-parallel and right-looking so that the 496 FMAs of
-// a lane are independent.  Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].
-__device__ __noinline__ bool warp_potrf_inv(const double* tile, double* sL, double* sW) {
+// lane a owns row a of the block (column-major source with leading dimension ld, shared or global).  Everything stays in registers
+// (fully unrolled, constant indices; __noinline__ keeps the unroller from giving up inside the big kernel): right-looking Cholesky
+// with one rsqrt per column, then W = L^-1 column-parallel and right-looking so that the 496 FMAs of a lane are independent.
+// Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].
+__device__ __noinline__ bool warp_potrf_inv(const double* tile, int ld, double* sL, double* sW) {
   const int a = threadIdx.x & 31;
   double A[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) A[c] = tile[a + 32 * c];
+  for (int c = 0; c < 32; ++c) A[c] = tile[a + ld * c];
   bool bad = false;
   double rinv = 0.0;
 #pragma unroll
@@ -193,100 +191,13 @@ __device__ __noinline__ bool warp_potrf_inv(const double* tile, double* sL, doub
   return !bad;
 }
 
-__global__ void __launch_bounds__(256) band_factor_kernel(BandSys S) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double sL[32 * kLP], sW[32 * kLP], sA[kTileElems], sB[kTileElems];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int a = tid & 31, c0 = tid >> 5;
-  for (int k = 0; k < S.NT; ++k) {
-    const int Tk = min(S.T, S.NT - 1 - k);
-    double* col = S.tiles + static_cast<size_t>(k) * S.TPC * kTileElems;
-    // ---- phase A: diagonal block (redundantly in every CTA) + panel solve X = P L^-T = P W^T
-    if (warp == 0) {
-      const bool ok = warp_potrf_inv(col, sL, sW);
-      if (!ok && tid == 0 && blockIdx.x == 0) *S.fail = 1;
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {  // only W = L_kk^-1 is kept (the back substitution multiplies by W^T); the diagonal tile itself
-      double* Wg = S.Linv + static_cast<size_t>(k) * kTileElems;  // must stay untouched: other CTAs may still be loading it
-      for (int e = tid; e < kTileElems; e += 256) {
-        const int r = e & 31, m = e >> 5;
-        Wg[e] = sW[r * kLP + m];
-      }
-    }
-    const int npanel = Tk + S.RB;
-    for (int q = blockIdx.x; q < npanel; q += gridDim.x) {
-      double* tile = col + static_cast<size_t>(q < Tk ? q + 1 : S.T + 1 + (q - Tk)) * kTileElems;
-      for (int e = tid; e < kTileElems; e += 256) sA[e] = tile[e];
-      __syncthreads();
-      double out[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c0 + 8 * j;
-        double acc = 0.0;
-        for (int m = 0; m <= c; ++m) acc += sA[a + 32 * m] * sW[c * kLP + m];
-        out[j] = acc;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tile[a + 32 * (c0 + 8 * j)] = out[j];
-    }
-    grid.sync();
-    // ---- phase B: trailing update
-    const int nband = Tk * (Tk + 1) / 2, nbord = S.RB * Tk, ncorn = S.RB * (S.RB + 1) / 2;
-    for (int o = blockIdx.x; o < nband + nbord + ncorn; o += gridDim.x) {
-      const double *Xi, *Xj;
-      double* dst;
-      int ld = 32;
-      if (o < nband) {
-        int i = static_cast<int>((sqrtf(8.f * o + 1.f) - 1.f) * 0.5f);
-        while (i * (i + 1) / 2 > o) --i;
-        while ((i + 1) * (i + 2) / 2 <= o) ++i;
-        const int j = o - i * (i + 1) / 2;  // 0 <= j <= i < Tk ; tile rows i+1, j+1
-        Xi = col + static_cast<size_t>(i + 1) * kTileElems;
-        Xj = col + static_cast<size_t>(j + 1) * kTileElems;
-        dst = S.tiles + (static_cast<size_t>(k + j + 1) * S.TPC + (i - j)) * kTileElems;
-      } else if (o < nband + nbord) {
-        const int oo = o - nband;
-        const int rb = oo / Tk, j = oo % Tk;
-        Xi = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems;
-        Xj = col + static_cast<size_t>(j + 1) * kTileElems;
-        dst = S.tiles + (static_cast<size_t>(k + j + 1) * S.TPC + S.T + 1 + rb) * kTileElems;
-      } else {
-        const int oo = o - nband - nbord;
-        int i = static_cast<int>((sqrtf(8.f * oo + 1.f) - 1.f) * 0.5f);
-        while (i * (i + 1) / 2 > oo) --i;
-        while ((i + 1) * (i + 2) / 2 <= oo) ++i;
-        const int j = oo - i * (i + 1) / 2;
-        Xi = col + static_cast<size_t>(S.T + 1 + i) * kTileElems;
-        Xj = col + static_cast<size_t>(S.T + 1 + j) * kTileElems;
-        dst = S.C + 32 * i + static_cast<size_t>(S.ldc) * 32 * j;
-        ld = S.ldc;
-      }
-      for (int e = tid; e < kTileElems; e += 256) { sA[e] = Xi[e]; sB[e] = Xj[e]; }
-      __syncthreads();
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int m = 0; m < 32; ++m) {
-        const double xa = sA[a + 32 * m];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += xa * sB[c0 + 8 * j + 32 * m];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[a + static_cast<size_t>(ld) * (c0 + 8 * j)] -= acc[j];
-      __syncthreads();
-    }
-    grid.sync();
-  }
-}
-
-// ---- flag-driven left-looking band Cholesky (default) -----------------------------------------------------------------------
-// The cooperative kernel above pays two grid-wide barriers per 32-column block step (567 steps at 60 s) and leaves the SMs idle while
-// one warp factors the diagonal tile.  Here every 32x32 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a
-// global counter, keeps the tile's accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source
-// tiles are published (per-tile ready flags, ld.acquire / st.release), then finishes it (diagonal: warp Cholesky + inverse; else
-// X = P W_j^T) and publishes it.  Each tile is written once by one CTA (no read-modify-write on HBM), only the dependency chain
-// potrf(j) -> trsm(j+1,j) -> potrf(j+1) is serial, and everything off the chain overlaps it.  Tasks are fetched in dependency order,
-// so a fetched task only ever waits on tasks already held by running CTAs: no deadlock for any grid size.
+// ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
+// Every 64x64 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a global counter, keeps the tile's
+// accumulator in registers (4x4 per thread) and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are published
+// (per-tile ready flags, ld.acquire / st.release), then finishes it and publishes it.  Each tile is written once by one CTA (no
+// read-modify-write on HBM, no grid-wide barrier); only the chain potrf(j) -> panel(j+1,j) -> potrf(j+1) is serial and everything
+// off the chain overlaps it.  Tasks are fetched in dependency order, so a fetched task only ever waits on tasks already held by running
+// CTAs: no deadlock for any grid size.
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -297,14 +208,53 @@ __device__ __forceinline__ void spin_until_set(const int* f) {
   while (ld_acquire(f) == 0) {}
 }
 
-__global__ void __launch_bounds__(256, 1) band_factor_ll_kernel(BandSys S) {
-  __shared__ double sL[32 * kLP], sW[32 * kLP], sA[kTileElems], sB[kTileElems];
+constexpr int kFacThreads = 256;
+// dynamic shared memory of band_factor_ll_kernel (doubles): two source tiles, W (64x64), 2 x (L, W) scratch of the 32x32 factorisations
+constexpr int kFacSmemDoubles = 3 * kTileElems + 4 * 32 * kLP;
+
+// acc(4x4 per thread: rows tx+16i, cols ty+16j) -= A B^T for two 64x64 column-major tiles in shared memory
+__device__ __forceinline__ void tile_sub_abt(double (&acc)[4][4], const double* sA, const double* sB, int tx, int ty) {
+#pragma unroll 4
+  for (int m = 0; m < kTile; ++m) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { av[i] = sA[tx + 16 * i + kTile * m]; bv[i] = sB[ty + 16 * i + kTile * m]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(-av[i], bv[j], acc[i][j]);
+  }
+}
+
+// 32x32 (sub)block helpers for the diagonal task, 256 threads, 4 outputs each: out(a, c0+8jj)
+//   D(ro+a, co+c) -= sum_m X(a,m) Y(c,m)   with X, Y 32x32 blocks given by (pointer, leading dimension)
+__device__ __forceinline__ void blk32_sub_abt(double* D, int ldd, const double* X, int ldx, const double* Y, int ldy, int a, int c0) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int m = 0; m < 32; ++m) {
+    const double xa = X[a + ldx * m];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[jj] = fma(xa, Y[c0 + 8 * jj + ldy * m], acc[jj]);
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) D[a + ldd * (c0 + 8 * jj)] -= acc[jj];
+}
+
+__global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys S) {
+  extern __shared__ double smem[];
+  double* sA = smem;                      // source tile L(i,k) / accumulator staging / diagonal block
+  double* sB = sA + kTileElems;           // source tile L(j,k)
+  double* sW = sB + kTileElems;           // W_j = L_jj^-1, column-major 64x64 (zero above the diagonal)
+  double* sL1 = sW + kTileElems;          // 32x32 scratch: L11, W11, L22, W22 (row-major, ld 33)
+  double* sW1 = sL1 + 32 * kLP;
+  double* sL2 = sW1 + 32 * kLP;
+  double* sW2 = sL2 + 32 * kLP;
   __shared__ int s_q;
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
   const int ntask = S.NT * S.TPC;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int a = tid & 31, c0 = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;   // 4x4 register block: rows tx+16i, cols ty+16j
+  const int a32 = tid & 31, c32 = tid >> 5; // 32x32 block helpers
   while (true) {
     if (tid == 0) s_q = atomicAdd(counter, 1);
     __syncthreads();
@@ -315,59 +265,113 @@ __global__ void __launch_bounds__(256, 1) band_factor_ll_kernel(BandSys S) {
     const bool band = s <= S.T;
     const int i = j + s;
     if (band && i >= S.NT) continue;  // tile below the end of the band: never referenced
-    double* tile = S.tiles + (static_cast<size_t>(q) << 10);
-    double acc[4];
+    double* tile = S.tiles + static_cast<size_t>(q) * kTileElems;
+    double acc[4][4];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = tile[tx + 16 * ii + kTile * (ty + 16 * jj)];
     const int kmin = band ? max(0, i - S.T) : max(0, j - S.T);
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
       const int fj = k * S.TPC + (j - k);
       if (tid == 0) spin_until_set(flags + fi);
       if (tid == 32 && fj != fi) spin_until_set(flags + fj);
-      __syncthreads();  // sources published; previous k-step's reads of sA/sB are complete
-      const double* Li = S.tiles + (static_cast<size_t>(fi) << 10);
-      const double* Lj = S.tiles + (static_cast<size_t>(fj) << 10);
+      __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
+      const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
+      const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
+      double2* dA = reinterpret_cast<double2*>(sA);
+      double2* dB = reinterpret_cast<double2*>(sB);
 #pragma unroll
-      for (int e = tid; e < kTileElems; e += 256) { sA[e] = __ldcg(Li + e); sB[e] = __ldcg(Lj + e); }
+      for (int e = tid; e < kTileElems / 2; e += kFacThreads) { dA[e] = __ldcg(Li + e); dB[e] = __ldcg(Lj + e); }
       __syncthreads();
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) {
-        const double xa = sA[a + 32 * m];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[jj] -= xa * sB[c0 + 8 * jj + 32 * m];
-      }
+      tile_sub_abt(acc, sA, sB, tx, ty);
     }
     __syncthreads();
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = acc[jj];
-    if (s == 0) {  // diagonal tile: L_jj and W_j = L_jj^-1 (only W is kept: panel solves and back substitution multiply by it)
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) sA[tx + 16 * ii + kTile * (ty + 16 * jj)] = acc[ii][jj];
+    __syncthreads();
+    if (s == 0) {
+      // ---- diagonal task: 64x64 Cholesky in shared memory.  D = [D11 . ; D21 D22] (lower), blocks of 32.
+      bool ok = true;
+      if (warp == 0) ok = warp_potrf_inv(sA, kTile, sL1, sW1);                               // L11, W11
       __syncthreads();
-      if (warp == 0) {
-        const bool ok = warp_potrf_inv(sA, sL, sW);
-        if (!ok && tid == 0) *S.fail = 1;
+      {  // L21 = D21 W11^T  -> overwrite D21 in sA (rows 32.., cols 0..31); out(a,c) = sum_{m<=c} D21(a,m) W11(c,m)
+        double out[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int c = c32 + 8 * jj;
+          double v = 0.0;
+          for (int m = 0; m <= c; ++m) v = fma(sA[32 + a32 + kTile * m], sW1[c * kLP + m], v);
+          out[jj] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) sA[32 + a32 + kTile * (c32 + 8 * jj)] = out[jj];
       }
       __syncthreads();
-      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
-      for (int e = tid; e < kTileElems; e += 256) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
+      blk32_sub_abt(sA + 32 + kTile * 32, kTile, sA + 32, kTile, sA + 32, kTile, a32, c32);   // D22 -= L21 L21^T
+      __syncthreads();
+      if (warp == 0) ok = warp_potrf_inv(sA + 32 + kTile * 32, kTile, sL2, sW2) && ok;        // L22, W22
+      if (warp == 0 && !ok && tid == 0) *S.fail = 1;
+      __syncthreads();
+      // W = [W11 0 ; -W22 (L21 W11) W22].  M = L21 W11 -> sB (32x32, ld 32): M(a,c) = sum_{m>=c} L21(a,m) W11(m,c)
+      {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int c = c32 + 8 * jj;
+          double v = 0.0;
+          for (int m = c; m < 32; ++m) v = fma(sA[32 + a32 + kTile * m], sW1[m * kLP + c], v);
+          sB[a32 + 32 * c] = v;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < kTileElems; e += kFacThreads) {
+        const int r = e & (kTile - 1), c = e >> kTileLog;
+        double v = 0.0;
+        if (r < 32 && c < 32) v = sW1[r * kLP + c];
+        else if (r >= 32 && c >= 32) v = sW2[(r - 32) * kLP + (c - 32)];
+        else if (r >= 32) {  // -sum_{m<=r'} W22(r',m) M(m,c)
+          const int rr = r - 32;
+          for (int m = 0; m <= rr; ++m) v = fma(-sW2[rr * kLP + m], sB[m + 32 * c], v);
+        }
+        sW[e] = v;
+      }
+      __syncthreads();
+      double2* Wg = reinterpret_cast<double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
+      const double2* sW2v = reinterpret_cast<const double2*>(sW);
+      for (int e = tid; e < kTileElems / 2; e += kFacThreads) Wg[e] = sW2v[e];
       __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
     } else {
+      // ---- panel task: X = P W_j^T
       if (tid == 0) spin_until_set(flags + j * S.TPC);
       __syncthreads();
-      const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
-      for (int e = tid; e < kTileElems; e += 256) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
+      const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
+      double2* dW = reinterpret_cast<double2*>(sW);
+      for (int e = tid; e < kTileElems / 2; e += kFacThreads) dW[e] = __ldcg(Wg + e);
       __syncthreads();
-      double out[4];
+      double out[4][4];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int c = c0 + 8 * jj;
-        double v = 0.0;
-        for (int m = 0; m <= c; ++m) v += sA[a + 32 * m] * sW[c * kLP + m];
-        out[jj] = v;
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) out[ii][jj] = 0.0;
+      const int mmax = ty + 48;  // W is lower triangular: X(:,c) only needs m <= c
+      for (int m = 0; m <= mmax; ++m) {
+        double av[4], wv[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) { av[ii] = sA[tx + 16 * ii + kTile * m]; wv[ii] = sW[ty + 16 * ii + kTile * m]; }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) out[ii][jj] = fma(av[ii], wv[jj], out[ii][jj]);
       }
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) tile[tx + 16 * ii + kTile * (ty + 16 * jj)] = out[ii][jj];
       __syncthreads();
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
       if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
@@ -376,19 +380,22 @@ __global__ void __launch_bounds__(256, 1) band_factor_ll_kernel(BandSys S) {
             const int fa = j * S.TPC + S.T + 1 + bi, fb = j * S.TPC + S.T + 1 + bj;
             if (tid == 0) { spin_until_set(flags + fa); spin_until_set(flags + fb); }
             __syncthreads();
-            const double* Xa = S.tiles + (static_cast<size_t>(fa) << 10);
-            const double* Xb = S.tiles + (static_cast<size_t>(fb) << 10);
-            for (int e = tid; e < kTileElems; e += 256) { sA[e] = __ldcg(Xa + e); sB[e] = __ldcg(Xb + e); }
+            const double* Xa = S.tiles + static_cast<size_t>(fa) * kTileElems;
+            const double* Xb = S.tiles + static_cast<size_t>(fb) * kTileElems;
+            for (int e = tid; e < kTileElems; e += kFacThreads) { sA[e] = __ldcg(Xa + e); sB[e] = __ldcg(Xb + e); }
             __syncthreads();
-            double pr[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int m = 0; m < 32; ++m) {
-              const double xa = sA[a + 32 * m];
+            double pr[4][4];
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) pr[jj] += xa * sB[c0 + 8 * jj + 32 * m];
-            }
+            for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (pr[jj] != 0.0) atomicAdd(S.C + 32 * bi + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
+              for (int jj = 0; jj < 4; ++jj) pr[ii][jj] = 0.0;
+            tile_sub_abt(pr, sA, sB, tx, ty);  // pr = -Xa Xb^T
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (pr[ii][jj] != 0.0)
+                  atomicAdd(S.C + kTile * bi + tx + 16 * ii + static_cast<size_t>(S.ldc) * (kTile * bj + ty + 16 * jj), pr[ii][jj]);
             __syncthreads();
           }
       }
@@ -397,19 +404,24 @@ __global__ void __launch_bounds__(256, 1) band_factor_ll_kernel(BandSys S) {
 }
 
 // ---- flag-driven backward substitution: x_m = W_m^T (z_m - Lb(:,m)^T x2 - sum_d L(m+d,m)^T x_{m+d}) ------------------------------------
-// One task per block column, fetched in descending order.  A task prefetches W_m and its first sub-diagonal tile while it waits for the
-// contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of k = m-1 (first: it is
-// the dependency chain), m-2, ... m-T with one warp per tile.
+// One task per block column, fetched in descending order.  A task stages W_m and its first sub-diagonal tile in shared memory while it
+// waits for the contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of
+// k = m-1 (first: it is the dependency chain), m-2, ... m-T with one warp per tile.
 __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
-  __shared__ double sW[kTileElems], sT[kTileElems], sx[32], sv[32], x2s[1024];
+  extern __shared__ double smem[];
+  constexpr int kLD = kTile + 1;      // padded: thread c walks column c, so consecutive threads must hit different banks
+  double* sW = smem;                  // W_m, column-major 64 x 64 (ld 65)
+  double* sT = sW + kTile * kLD;      // tile (m, m-1) (ld 65)
+  double* x2s = sT + kTile * kLD;     // border solution [ldc <= 1024]
+  __shared__ double sx[kTile], sv[kTile];
   __shared__ int s_q;
   int* arrivals = S.work_i + static_cast<size_t>(S.NT) * S.TPC;
   int* counter = arrivals + S.NT + 1;
   double* vsum = S.work_d;
   double* x = S.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < S.ldc; i += 256) x2s[i] = x[static_cast<size_t>(S.NT) * 32 + i];
-  const int zrb = S.nbo >> 5, zrow = S.nbo & 31;
+  for (int i = tid; i < S.ldc; i += 256) x2s[i] = x[static_cast<size_t>(S.NT) * kTile + i];
+  const int zrb = S.nbo >> kTileLog, zrow = S.nbo & (kTile - 1);
   while (true) {
     __syncthreads();
     if (tid == 0) s_q = atomicAdd(counter, 1);
@@ -419,43 +431,57 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
     const int m = S.NT - 1 - q;
     const int Tm = min(S.T, S.NT - 1 - m);
     const double* col = S.tiles + static_cast<size_t>(m) * S.TPC * kTileElems;
-    const double* Wg = S.Linv + static_cast<size_t>(m) * kTileElems;
-    for (int e = tid; e < kTileElems; e += 256) sW[e] = Wg[e];
-    if (m >= 1) {
-      const double* t1 = S.tiles + (static_cast<size_t>(m - 1) * S.TPC + 1) * kTileElems;
-      for (int e = tid; e < kTileElems; e += 256) sT[e] = t1[e];
+    const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(m) * kTileElems);
+    for (int e = tid; e < kTileElems / 2; e += 256) {
+      const double2 v = Wg[e];
+      const int r = (2 * e) & (kTile - 1), c = (2 * e) >> kTileLog;
+      sW[r + kLD * c] = v.x; sW[r + 1 + kLD * c] = v.y;
     }
-    // border part of the right-hand side (independent of the chain)
-    double bsum = 0.0;
-    if (warp == 0) {
-      for (int rb = 0; rb < S.RB; ++rb) {
-        const double* bt = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems + 32 * lane;
-        const double* xv = x2s + 32 * rb;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) bsum += bt[r] * xv[r];
+    if (m >= 1) {
+      const double2* t1 = reinterpret_cast<const double2*>(S.tiles + (static_cast<size_t>(m - 1) * S.TPC + 1) * kTileElems);
+      for (int e = tid; e < kTileElems / 2; e += 256) {
+        const double2 v = t1[e];
+        const int r = (2 * e) & (kTile - 1), c = (2 * e) >> kTileLog;
+        sT[r + kLD * c] = v.x; sT[r + 1 + kLD * c] = v.y;
       }
-      bsum = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + 32 * lane] - bsum;  // z_m - Lb^T x2
-      if (lane == 0) while (ld_acquire(arrivals + m) < Tm) __nanosleep(32);
-      __syncwarp();
-      sv[lane] = bsum - __ldcg(vsum + static_cast<size_t>(m) * 32 + lane);
+    }
+    // right-hand side minus the border part (independent of the chain): warps 0,1 own columns c = tid (< 64)
+    if (tid < kTile) {
+      double bsum = 0.0;
+      for (int rb = 0; rb < S.RB; ++rb) {
+        const double* bt = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems + kTile * tid;
+        const double* xv = x2s + kTile * rb;
+#pragma unroll 8
+        for (int r = 0; r < kTile; ++r) bsum = fma(bt[r], xv[r], bsum);
+      }
+      bsum = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + kTile * tid] - bsum;  // z_m - Lb^T x2
+      if (tid == 0) while (ld_acquire(arrivals + m) < Tm) {}
+      sv[tid] = bsum;
     }
     __syncthreads();
-    if (warp == 0) {
+    if (tid < kTile) sv[tid] -= __ldcg(vsum + static_cast<size_t>(m) * kTile + tid);
+    __syncthreads();
+    if (tid < kTile) {
       double xk = 0.0;
-      for (int r = lane; r < 32; ++r) xk += sW[r + 32 * lane] * sv[r];  // column `lane` of W (lower triangular)
-      sx[lane] = xk;
-      x[static_cast<size_t>(m) * 32 + lane] = xk;
+      for (int r = tid; r < kTile; ++r) xk = fma(sW[r + kLD * tid], sv[r], xk);  // column tid of W (lower triangular): (W^T v)_tid
+      sx[tid] = xk;
+      x[static_cast<size_t>(m) * kTile + tid] = xk;
     }
     __syncthreads();
     const int nd = min(S.T, m);
     for (int d = 1 + warp; d <= nd; d += 8) {
       const int k = m - d;
       const double* tl = (d == 1) ? sT : S.tiles + (static_cast<size_t>(k) * S.TPC + d) * kTileElems;
-      double u = 0.0;
-      const double* tc = tl + 32 * lane;
+      const int ldt = (d == 1) ? kLD : kTile;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        const double* tc = tl + ldt * c;
+        double u = 0.0;
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) u += tc[r] * sx[r];
-      atomicAdd(vsum + static_cast<size_t>(k) * 32 + lane, u);
+        for (int r = 0; r < kTile; ++r) u = fma(tc[r], sx[r], u);
+        atomicAdd(vsum + static_cast<size_t>(k) * kTile + c, u);
+      }
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(arrivals + k, 1);
@@ -468,7 +494,7 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
 __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
   const int n = S.nbo, ld = S.ldc, tid = threadIdx.x;
   double* C = S.C;
-  double* x2 = S.x + static_cast<size_t>(S.NT) * 32;
+  double* x2 = S.x + static_cast<size_t>(S.NT) * kTile;
   __shared__ double xs[1024];
   __shared__ int bad;
   if (tid == 0) bad = 0;
@@ -505,49 +531,13 @@ __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
   if (tid == 0 && bad) *S.fail = 1;
 }
 
-// x1 = L11^-T (z1 - L21^T x2): backward block substitution.  One CTA of 32 warps.
-__global__ void __launch_bounds__(1024) band_backsolve_kernel(BandSys S) {
-  __shared__ double red[32 * 32], x2s[1024], sv[32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double* x = S.x;
-  for (int i = tid; i < S.ldc; i += 1024) x2s[i] = x[static_cast<size_t>(S.NT) * 32 + i];
-  __syncthreads();
-  const int zrb = S.nbo >> 5, zrow = S.nbo & 31;
-  for (int k = S.NT - 1; k >= 0; --k) {
-    const int Tk = min(S.T, S.NT - 1 - k);
-    const double* col = S.tiles + static_cast<size_t>(k) * S.TPC * kTileElems;
-    const int ntile = Tk + S.RB;
-    double acc = 0.0;
-    for (int q = warp; q < ntile; q += 32) {
-      const double* tile = col + static_cast<size_t>(q < Tk ? q + 1 : S.T + 1 + (q - Tk)) * kTileElems + 32 * lane;
-      const double* xv = q < Tk ? x + static_cast<size_t>(k + q + 1) * 32 : x2s + 32 * (q - Tk);
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) acc += tile[r] * xv[r];
-    }
-    red[warp * 32 + lane] = acc;
-    __syncthreads();
-    if (warp == 0) {
-      double v = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + 32 * lane];
-      const int nw = ntile < 32 ? ntile : 32;
-      for (int w = 0; w < nw; ++w) v -= red[w * 32 + lane];
-      sv[lane] = v;
-      __syncwarp();
-      const double* W = S.Linv + static_cast<size_t>(k) * kTileElems + 32 * lane;  // column `lane` of W
-      double xk = 0.0;
-      for (int m = lane; m < 32; ++m) xk += W[m] * sv[m];
-      x[static_cast<size_t>(k) * 32 + lane] = xk;
-    }
-    __syncthreads();
-  }
-}
-
 // y (tangent order) from the solver's x, delta = S y, and the scalars of the step: [2] y.g_s  [3] sum D2 y^2  [4] #non-finite
 __global__ void __launch_bounds__(256) finish_step_kernel(BandSys A, SchurView SV, int nt, const double* __restrict__ scale, const double* __restrict__ diag,
                                                           double inv_radius, const double* __restrict__ g, double* __restrict__ y,
                                                           double* __restrict__ delta, double* __restrict__ scal) {
   double yg = 0.0, dy = 0.0, nf = 0.0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
-    const double v = t < A.nb ? A.x[t] : t < SV.base ? A.x[static_cast<size_t>(A.NT) * 32 + (t - A.nb)] : SV.yrho[t - SV.base];
+    const double v = t < A.nb ? A.x[t] : t < SV.base ? A.x[static_cast<size_t>(A.NT) * kTile + (t - A.nb)] : SV.yrho[t - SV.base];
     y[t] = v;
     delta[t] = v * scale[t];
     if (!isfinite(v)) nf += 1.0;
@@ -614,52 +604,37 @@ __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ a, 
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-static int coop_grid_limit(lvi_ctx* ctx) {
-  static int limit = 0;
-  if (!limit) {
-    int per_sm = 0;
-    LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band_factor_kernel, 256, 0));
-    limit = std::max(1, std::min(per_sm, 1) * ctx->sm_count);
-  }
-  return limit;
-}
-
-static bool use_coop_solver() {
-  static int v = -1;
-  if (v < 0) { const char* e = std::getenv("LVI_BAND_SOLVER"); v = (e && std::string(e) == "coop") ? 1 : 0; }
-  return v == 1;
-}
-static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads) {
+static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads, size_t smem) {
   int per_sm = 0;
-  LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   return std::max(1, per_sm) * ctx->sm_count;
 }
 static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   cudaStream_t st = ctx->stream;
   LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), st));
   if (A.NT == 0) return;
-  if (use_coop_solver() || !A.work_i) {
-    const int ops = A.T * (A.T + 1) / 2 + A.RB * A.T + A.RB * (A.RB + 1) / 2;
-    int grid = std::min(coop_grid_limit(ctx), std::max(1, ops));
-    void* args[] = {&A};
-    LVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band_factor_kernel), dim3(grid), dim3(256), args, 0, st));
-    ++ctx->launches;
-    return;
-  }
+  LVI_REQUIRE(A.work_i && A.work_d, LVI_ERR_INVALID, "band solver workspace missing");
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
+  constexpr size_t smem = kFacSmemDoubles * sizeof(double);
   static int resident = 0;
-  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), 256);
+  if (!resident) {
+    LVI_CUDA(cudaFuncSetAttribute(band_factor_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
+  }
   const int grid = std::min(resident, A.NT * A.TPC);
-  LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, 256, 0, A);
+  LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, A);
 }
 static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
   LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
   if (A.NT == 0) return;
-  if (use_coop_solver() || !A.work_i) { LVI_LAUNCH(ctx, band_backsolve_kernel, 1, 1024, 0, A); return; }
+  constexpr size_t smem = (2 * kTile * (kTile + 1) + 1024) * sizeof(double);
   static int resident = 0;
-  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256);
-  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(resident, A.NT), 256, 0, A);
+  if (!resident) {
+    LVI_CUDA(cudaFuncSetAttribute(band_backsolve_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256, smem);
+  }
+  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(resident, A.NT), 256, smem, A);
 }
 void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
   band_factor_only(ctx, A);
@@ -974,34 +949,32 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
     LVI_REQUIRE(ctx && A_dense && rhs && x_out && nb >= 0 && nbo >= 0 && nb + nbo > 0, LVI_ERR_INVALID, "lvi_band_solve_dense: bad argument");
     LVI_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    Lowered L;
-    L.nb = nb; L.nbo = nbo; L.bw = bw;
     BandSys S{};
     S.nb = nb; S.nbo = nbo;
-    S.NT = (nb + 31) / 32;
-    S.T = S.NT > 0 ? std::min(S.NT - 1, (bw + 31) / 32) : 0;
-    S.RB = (nbo + 1 + 31) / 32; S.TPC = S.T + 1 + S.RB; S.ldc = S.RB * 32;
+    S.NT = (nb + kTile - 1) / kTile;
+    S.T = S.NT > 0 ? std::min(S.NT - 1, (bw + kTile - 1) / kTile) : 0;
+    S.RB = (nbo + 1 + kTile - 1) / kTile; S.TPC = S.T + 1 + S.RB; S.ldc = S.RB * kTile;
     const size_t ntile = static_cast<size_t>(S.NT) * S.TPC;
     std::vector<double> ht(std::max<size_t>(ntile * kTileElems, 1), 0.0), hc(static_cast<size_t>(S.ldc) * S.ldc, 0.0);
     const int n = nb + nbo;
     auto at = [&](int i, int j) { return A_dense[static_cast<size_t>(i) * n + j]; };
     for (int J = 0; J < S.NT; ++J)
       for (int q = 0; q < S.TPC; ++q)
-        for (int b = 0; b < 32; ++b)
-          for (int a = 0; a < 32; ++a) {
-            const int j = J * 32 + b;
+        for (int b = 0; b < kTile; ++b)
+          for (int a = 0; a < kTile; ++a) {
+            const int j = J * kTile + b;
             double v = 0.0;
             if (q <= S.T) {
-              const int i = (J + q) * 32 + a;
+              const int i = (J + q) * kTile + a;
               if (J + q >= S.NT) continue;
               if (i < nb && j < nb) { if (i >= j) v = at(i, j); }
               else if (i == j) v = 1.0;
             } else if (j < nb) {
-              const int bi = (q - S.T - 1) * 32 + a;
+              const int bi = (q - S.T - 1) * kTile + a;
               if (bi < nbo) v = at(nb + bi, j);
               else if (bi == nbo) v = rhs[j];
             }
-            ht[((static_cast<size_t>(J) * S.TPC + q) << 10) + (b << 5) + a] = v;
+            ht[(static_cast<size_t>(J) * S.TPC + q) * kTileElems + b * kTile + a] = v;
           }
     for (int bj = 0; bj < S.ldc; ++bj)
       for (int bi = 0; bi < S.ldc; ++bi) {
@@ -1011,7 +984,7 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
         else if (bi == bj) v = 1.0;
         hc[bi + static_cast<size_t>(S.ldc) * bj] = v;
       }
-    DBuf<double> tiles(ht.size()), C(hc.size()), Linv(std::max<size_t>(static_cast<size_t>(S.NT) * kTileElems, 1)), x(static_cast<size_t>(S.NT) * 32 + S.ldc);
+    DBuf<double> tiles(ht.size()), C(hc.size()), Linv(std::max<size_t>(static_cast<size_t>(S.NT) * kTileElems, 1)), x(static_cast<size_t>(S.NT) * kTile + S.ldc);
     DBuf<int> fail(4);
     tiles.upload(ht.data(), ht.size(), st); C.upload(hc.data(), hc.size(), st);
     S.tiles = tiles.p; S.C = C.p; S.Linv = Linv.p; S.x = x.p; S.fail = fail.p;
@@ -1025,7 +998,7 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
     LVI_CUDA(cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     LVI_CUDA(cudaStreamSynchronize(st));
     LVI_REQUIRE(hf == 0, LVI_ERR_NUMERIC, "Cholesky breakdown");
-    for (int t = 0; t < n; ++t) x_out[t] = t < nb ? hx[t] : hx[static_cast<size_t>(S.NT) * 32 + (t - nb)];
+    for (int t = 0; t < n; ++t) x_out[t] = t < nb ? hx[t] : hx[static_cast<size_t>(S.NT) * kTile + (t - nb)];
   });
 }
 
