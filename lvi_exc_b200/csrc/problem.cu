@@ -254,7 +254,7 @@ static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBu
   S.ldc = S.RB * kTile;
   tiles.alloc(std::max<size_t>(static_cast<size_t>(S.NT) * S.TPC * kTileElems, 1));
   C.alloc(static_cast<size_t>(S.ldc) * S.ldc);
-  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail; S.work_i = nullptr; S.work_d = nullptr;
+  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail; S.work_i = nullptr; S.work_d = nullptr; S.trace = nullptr;
 }
 
 void problem_ensure_solver_buffers(lvi_problem* p) {

@@ -29,6 +29,7 @@ struct BandSys {
   double* x;         // [NT*kTile + ldc] solution (band part then border part)
   int* fail;         // != 0: Cholesky breakdown
   int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters] (zeroed per solve)
+  unsigned long long* trace;  // optional [NT*TPC*8] per-task timestamps (LVI_TRACE_FACTOR=file), else nullptr
   double* work_d;    // [NT*kTile] partial sums of the back substitution
   size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
   size_t work_d_count() const { return static_cast<size_t>(NT) * kTile; }

@@ -147,48 +147,58 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
   if (lane == 0) SV.yrho[k] = (-g[t] * sr - acc) / d;
 }
 
-// ---- 32x32 Cholesky + inverse in one warp ----------------------------------------------------------------------------
-// lane a owns row a of the block (column-major source with leading dimension ld, shared or global).  Everything stays in registers
-// (fully unrolled, constant indices; __noinline__ keeps the unroller from giving up inside the big kernel): right-looking Cholesky
-// with one rsqrt per column, then W = L^-1 column-parallel and right-looking so that the 496 FMAs of a lane are independent.
-// Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].
-__device__ __noinline__ bool warp_potrf_inv(const double* tile, int ld, double* sL, double* sW) {
-  const int a = threadIdx.x & 31;
-  double A[32];
+// ---- 32x32 Cholesky + inverse by the whole CTA (256 threads) ----------------------------------------------------------
+// A single warp running this is a ~7k-instruction DEPENDENT chain (measured 30-140 us inside the factor kernel, whether as unrolled
+// register code - which also misses the instruction cache - or as a shared-memory loop).  Spread over 256 threads each step is one
+// shared-memory round trip + one barrier:
+//   factor : thread (a = tid & 31, c = tid>>5 + 8k) owns 4 elements.  Step j needs no column scaling pass:
+//            M(a,c) -= M(a,j) M(c,j) / M(j,j)   for a >= c > j   (one barrier per step); L(:,j) = M(:,j) rsqrt(M(j,j)) is applied at the end.
+//   inverse: W = L^-1 column-parallel, right-looking: W(r,a) -= L(r,t) W(t,a) for r > t, same ownership, one barrier per step.
+// sL / sW are 32x32 row-major with leading dimension 33.  Must be called by all threads of the CTA.  Returns false on breakdown.
+__device__ __forceinline__ bool cta_potrf_inv(const double* tile, int ld, double* sL, double* sW, double* sR /*[32]*/) {
+  const int tid = threadIdx.x;
+  const int a = tid & 31, c0 = tid >> 5;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) A[c] = tile[a + ld * c];
+  for (int k = 0; k < 4; ++k) { const int c = c0 + 8 * k; sL[a * kLP + c] = tile[a + ld * c]; }
+  __syncthreads();
   bool bad = false;
-  double rinv = 0.0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    double d = __shfl_sync(FULL, A[j], j);
+  for (int j = 0; j < 31; ++j) {
+    double d = sL[j * kLP + j];
     if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-    const double ri = rsqrt(d);
-    const double l = A[j] * ri;  // row j: d / sqrt(d) = sqrt(d)
-    A[j] = l;
-    if (a == j) rinv = ri;
+    const double di = 1.0 / d;
+    const double la = sL[a * kLP + j] * di;
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) {
-      const double lc = __shfl_sync(FULL, l, c);
-      A[c] = (a >= c) ? fma(-l, lc, A[c]) : A[c];
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + 8 * k;
+      if (c > j && a >= c) sL[a * kLP + c] = fma(-la, sL[c * kLP + j], sL[a * kLP + c]);
     }
+    __syncthreads();
   }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) sL[a * kLP + c] = (c <= a) ? A[c] : 0.0;
-  __syncwarp();
-  double w[32];
-#pragma unroll
-  for (int r = 0; r < 32; ++r) w[r] = (r == a) ? 1.0 : 0.0;
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    w[t] *= __shfl_sync(FULL, rinv, t);
-#pragma unroll
-    for (int r = t + 1; r < 32; ++r) w[r] = fma(-sL[r * kLP + t], w[t], w[r]);
+  if (tid < 32) {
+    double d = sL[tid * kLP + tid];
+    if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+    sR[tid] = rsqrt(d);
   }
+  __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 32; ++r) sW[r * kLP + a] = w[r];
-  __syncwarp();
-  return !bad;
+  for (int k = 0; k < 4; ++k) {  // scale the columns: L(a,c) = M(a,c) rsqrt(M(c,c)); zero the upper triangle; W = I
+    const int c = c0 + 8 * k;
+    sL[a * kLP + c] = (a >= c) ? sL[a * kLP + c] * sR[c] : 0.0;
+    sW[a * kLP + c] = (a == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int t = 0; t < 32; ++t) {  // thread owns W(r = c0+8k, col a)
+    const double wt = sW[t * kLP + a] * sR[t];
+    __syncthreads();
+    if (c0 == (t & 7)) sW[t * kLP + a] = wt;  // the owner of row t (t = c0 + 8k for some k) finalises it
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = c0 + 8 * k;
+      if (r > t) sW[r * kLP + a] = fma(-sL[r * kLP + t], wt, sW[r * kLP + a]);
+    }
+    __syncthreads();
+  }
+  return !__syncthreads_or(bad) ;
 }
 
 // ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
@@ -204,6 +214,12 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(q) * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void spin_until_set(const int* f) {
   while (ld_acquire(f) == 0) {}
 }
@@ -249,10 +265,11 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
   double* sL2 = sW1 + 32 * kLP;
   double* sW2 = sL2 + 32 * kLP;
   __shared__ int s_q;
+  __shared__ double sR[32];
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
   const int ntask = S.NT * S.TPC;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;   // 4x4 register block: rows tx+16i, cols ty+16j
   const int a32 = tid & 31, c32 = tid >> 5; // 32x32 block helpers
   while (true) {
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     const int i = j + s;
     if (band && i >= S.NT) continue;  // tile below the end of the band: never referenced
     double* tile = S.tiles + static_cast<size_t>(q) * kTileElems;
+    LVI_TRACE(0);
     double acc[4][4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       if (tid == 0) spin_until_set(flags + fi);
       if (tid == 32 && fj != fi) spin_until_set(flags + fj);
       __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
+      if (k == j - 1) LVI_TRACE(1);
       const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
       const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
       double2* dA = reinterpret_cast<double2*>(sA);
@@ -285,9 +304,11 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
 #pragma unroll
       for (int e = tid; e < kTileElems / 2; e += kFacThreads) { dA[e] = __ldcg(Li + e); dB[e] = __ldcg(Lj + e); }
       __syncthreads();
+      if (k == j - 1) { __syncthreads(); LVI_TRACE(2); }
       tile_sub_abt(acc, sA, sB, tx, ty);
     }
     __syncthreads();
+    LVI_TRACE(3);
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -295,9 +316,8 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     __syncthreads();
     if (s == 0) {
       // ---- diagonal task: 64x64 Cholesky in shared memory.  D = [D11 . ; D21 D22] (lower), blocks of 32.
-      bool ok = true;
-      if (warp == 0) ok = warp_potrf_inv(sA, kTile, sL1, sW1);                               // L11, W11
-      __syncthreads();
+      bool ok = cta_potrf_inv(sA, kTile, sL1, sW1, sR);                                       // L11, W11
+      LVI_TRACE(4);
       {  // L21 = D21 W11^T  -> overwrite D21 in sA (rows 32.., cols 0..31); out(a,c) = sum_{m<=c} D21(a,m) W11(c,m)
         double out[4];
 #pragma unroll
@@ -314,9 +334,10 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       __syncthreads();
       blk32_sub_abt(sA + 32 + kTile * 32, kTile, sA + 32, kTile, sA + 32, kTile, a32, c32);   // D22 -= L21 L21^T
       __syncthreads();
-      if (warp == 0) ok = warp_potrf_inv(sA + 32 + kTile * 32, kTile, sL2, sW2) && ok;        // L22, W22
-      if (warp == 0 && !ok && tid == 0) *S.fail = 1;
-      __syncthreads();
+      LVI_TRACE(5);
+      ok = cta_potrf_inv(sA + 32 + kTile * 32, kTile, sL2, sW2, sR) && ok;                    // L22, W22
+      if (!ok && tid == 0) *S.fail = 1;
+      LVI_TRACE(6);
       // W = [W11 0 ; -W22 (L21 W11) W22].  M = L21 W11 -> sB (32x32, ld 32): M(a,c) = sum_{m>=c} L21(a,m) W11(m,c)
       {
 #pragma unroll
@@ -328,16 +349,17 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
         }
       }
       __syncthreads();
-      for (int e = tid; e < kTileElems; e += kFacThreads) {
-        const int r = e & (kTile - 1), c = e >> kTileLog;
-        double v = 0.0;
-        if (r < 32 && c < 32) v = sW1[r * kLP + c];
-        else if (r >= 32 && c >= 32) v = sW2[(r - 32) * kLP + (c - 32)];
-        else if (r >= 32) {  // -sum_{m<=r'} W22(r',m) M(m,c)
-          const int rr = r - 32;
-          for (int m = 0; m <= rr; ++m) v = fma(-sW2[rr * kLP + m], sB[m + 32 * c], v);
+      {  // assemble W (column-major 64x64): each thread 4 elements of every 32x32 quadrant; W21(a,c) = -sum_m W22(a,m) M(m,c)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int c = c32 + 8 * jj;
+          double v = 0.0;
+          for (int m = 0; m <= a32; ++m) v = fma(-sW2[a32 * kLP + m], sB[m + 32 * c], v);
+          sW[a32 + kTile * c] = sW1[a32 * kLP + c];
+          sW[a32 + kTile * (32 + c)] = 0.0;
+          sW[32 + a32 + kTile * c] = v;
+          sW[32 + a32 + kTile * (32 + c)] = sW2[a32 * kLP + c];
         }
-        sW[e] = v;
       }
       __syncthreads();
       double2* Wg = reinterpret_cast<double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
@@ -345,14 +367,17 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       for (int e = tid; e < kTileElems / 2; e += kFacThreads) Wg[e] = sW2v[e];
       __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
+      LVI_TRACE(7);
     } else {
       // ---- panel task: X = P W_j^T
       if (tid == 0) spin_until_set(flags + j * S.TPC);
       __syncthreads();
+      LVI_TRACE(4);
       const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
       double2* dW = reinterpret_cast<double2*>(sW);
       for (int e = tid; e < kTileElems / 2; e += kFacThreads) dW[e] = __ldcg(Wg + e);
       __syncthreads();
+      LVI_TRACE(5);
       double out[4][4];
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
@@ -372,8 +397,10 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) tile[tx + 16 * ii + kTile * (ty + 16 * jj)] = out[ii][jj];
+      LVI_TRACE(6);
       __syncthreads();
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
+      LVI_TRACE(7);
       if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
         for (int bi = 0; bi < S.RB; ++bi)
           for (int bj = 0; bj <= bi; ++bj) {
@@ -623,6 +650,20 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
   }
   const int grid = std::min(resident, A.NT * A.TPC);
+  const char* trace_path = std::getenv("LVI_TRACE_FACTOR");
+  if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]
+    const size_t n = static_cast<size_t>(A.NT) * A.TPC * 8;
+    DBuf<unsigned long long> tr(n);
+    tr.zero(st);
+    BandSys At = A;
+    At.trace = tr.p;
+    LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, At);
+    std::vector<unsigned long long> h(n);
+    tr.download(h.data(), n, st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+    if (FILE* f = std::fopen(trace_path, "wb")) { const int hdr[4] = {A.NT, A.TPC, A.T, A.RB}; std::fwrite(hdr, sizeof(int), 4, f); std::fwrite(h.data(), 8, n, f); std::fclose(f); }
+    return;
+  }
   LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, A);
 }
 static void band_solve_only(lvi_ctx* ctx, BandSys& A) {

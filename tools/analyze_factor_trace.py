@@ -1,0 +1,24 @@
+"""Critical-path breakdown of band_factor_ll_kernel from an LVI_TRACE_FACTOR dump (diagnostics)."""
+import sys
+import numpy as np
+raw = open(sys.argv[1], "rb").read()
+NT, TPC, T, RB = np.frombuffer(raw[:16], np.int32)
+tr = np.frombuffer(raw[16:], np.uint64).reshape(NT, TPC, 8).astype(np.float64)
+t0 = tr[tr > 0].min()
+tr = np.where(tr > 0, (tr - t0) / 1e3, np.nan)   # us
+print(f"NT {NT} TPC {TPC} T {T} RB {RB}; total {np.nanmax(tr):.1f} us")
+d = tr[:, 0, :]          # diagonal tasks
+p = tr[:, 1, :] if T >= 1 else None  # first sub-diagonal panel tile
+names_d = ["fetch", "last dep seen", "last tiles loaded", "accum done", "potrf1 done", "glue done", "potrf2 done", "published"]
+sl = slice(20, NT - 20)
+print("diagonal task, mean us between marks:")
+for a in range(1, 8):
+    print(f"  {names_d[a-1]:>18} -> {names_d[a]:<18} {np.nanmean(d[sl, a] - d[sl, a-1]):8.2f}")
+if p is not None:
+    names_p = ["fetch", "last dep seen", "last tiles loaded", "accum done", "W flag seen", "W loaded", "X computed", "published"]
+    print("panel task (j+1,j), mean us between marks:")
+    for a in range(1, 8):
+        print(f"  {names_p[a-1]:>18} -> {names_p[a]:<18} {np.nanmean(p[sl, a] - p[sl, a-1]):8.2f}")
+    print("chain: diag publish(j) -> panel W seen(j)      %.2f" % np.nanmean(p[sl, 4] - d[sl, 7]))
+    print("chain: panel publish(j) -> diag(j+1) dep seen   %.2f" % np.nanmean(d[21:NT-19, 1] - p[sl, 7]))
+    print("column period (diag publish j+1 - j)            %.2f" % np.nanmean(np.diff(d[sl, 7])))
