@@ -218,13 +218,13 @@ def main():
     value = 1e3 / ms_total
     peaks, peak_kind = measured_peaks()
     # ---- roofline of the dominant kernel: band_factor_kernel (blocked band+arrow Cholesky).  Algorithmic bytes per launch = every
-    # stored 64x64 fp64 tile of the damped normal matrix read once and its factor written once (+ the inverse diagonal blocks).
+    # stored 32x32 fp64 tile of the damped normal matrix read once and its factor written once (+ the inverse diagonal blocks).
     nt, nres = prob.num_tangent, prob.num_residuals
     lay = np.zeros(8, np.int32)
     _capi.check(backend.lib.lvi_problem_layout(prob.h, lay.ctypes.data_as(C.POINTER(C.c_int32))))
     nb, nbo, bw, NT, T, RB = (int(x) for x in lay[:6])
     tiles = sum(min(T, NT - 1 - k) + 1 + RB for k in range(NT))
-    algo_bytes = tiles * 32768 * 2 + NT * 32768
+    algo_bytes = tiles * 8192 * 2 + NT * 8192
     phase_names = ["linearize", "build_system", "band_factor", "corner_backsolve", "trial_cost"]
     phases = {n: float(ms[i]) for i, n in enumerate(phase_names)}
     fac_ms = phases["band_factor"]
@@ -235,7 +235,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_total, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD, "seconds": args.duration, "residual_blocks": pd_sizes(pd), "num_residuals": nres, "tangent_dims": nt,
-                      "band_dims": nb, "border_dims": nbo, "half_bandwidth": bw, "l2_policy": "inputs larger than L2: H+A tile stores %.0f MB > 126 MB" % (2 * tiles * 32768 / 1e6),
+                      "band_dims": nb, "border_dims": nbo, "half_bandwidth": bw, "l2_policy": "inputs larger than L2: H+A tile stores %.0f MB > 126 MB" % (2 * tiles * 8192 / 1e6),
                       "parallelism": f"dp{world}: residual tables sharded by time chunk, NCCL all-reduce of H/g"},
            "phases_ms": phases,
            "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,

@@ -3,7 +3,7 @@
 // HBM layout:
 //   X        one flat fp64 parameter vector [r3 3n | so3 4n | sens 22 | rho nl]; a second copy XC holds the LM candidate
 //   tables   per residual type SoA (ResTable, residuals.cuh), in the caller's (chronological) order
-//   H / A    normal equations in 64x64 TILE storage: block column J holds tiles d = 0..T (band, rows 64(J+d)..) followed by
+//   H / A    normal equations in 32x32 TILE storage: block column J holds tiles d = 0..T (band, rows 32(J+d)..) followed by
 //            RB border tiles (arrow rows: map-time knots + sensor blocks + one extra row carrying the right-hand side);
 //            the border x border corner is a small dense matrix C.  Never dense n^2 (SURVEY §5 "long-context").
 #pragma once
@@ -14,8 +14,9 @@
 
 namespace lvi {
 
-constexpr int kTileLog = 6;
-constexpr int kTile = 1 << kTileLog;      // 64 x 64 fp64 tiles (32 KB)
+constexpr int kTileLog = 5;
+constexpr int kTile = 1 << kTileLog;      // 32 x 32 fp64 tiles (8 KB): measured best — the factorisation is bound by its serial
+                                          // pivot chain, and the per-column chain cost grows faster than the tile width
 constexpr int kTileElems = kTile * kTile;
 
 struct BandSys {

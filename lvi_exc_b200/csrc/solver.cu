@@ -5,12 +5,12 @@
 // tolerances.  Ceres is not vendored; the loop below restates TrustRegionMinimizer +
 // LevenbergMarquardtStrategy step by step and is kept line-for-line comparable with the CPU oracle (oracle/orc_solve.cpp).
 //
-// Linear algebra: (S H S + D^2) y = -S g with H in 64x64 tile storage (problem.cuh), inverse depths eliminated first (Schur).
-//   band_factor_ll_kernel     flag-driven left-looking tile Cholesky: one task per 64x64 tile of the factor, fetched in column-major
+// Linear algebra: (S H S + D^2) y = -S g with H in 32x32 tile storage (problem.cuh), inverse depths eliminated first (Schur).
+//   band_factor_ll_kernel     flag-driven left-looking tile Cholesky: one task per 32x32 tile of the factor, fetched in column-major
 //                             order; the accumulator lives in registers and L(i,k) L(j,k)^T is subtracted as soon as both source tiles
-//                             are published (ld.acquire / st.release flags).  The diagonal task factors its 64x64 block entirely in
-//                             shared memory (two warp-level 32x32 Choleskys + glue GEMMs) and publishes W = L_jj^-1; panel tiles
-//                             (band + arrow border + the rhs row, so the forward substitution comes for free) finish as X = P W^T.
+//                             are published (ld.acquire / st.release flags).  The diagonal task runs a fused Cholesky + inverse of its
+//                             block with the whole CTA in shared memory and publishes W = L_jj^-1; panel tiles (band + arrow border +
+//                             the rhs row, so the forward substitution comes for free) finish as X = P W^T.
 //   corner_solve_kernel       dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
 //   band_backsolve_ll_kernel  flag-driven backward substitution, one task per block column.
 // All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
@@ -147,67 +147,60 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
   if (lane == 0) SV.yrho[k] = (-g[t] * sr - acc) / d;
 }
 
-// ---- 32x32 Cholesky + inverse by the whole CTA (256 threads) ----------------------------------------------------------
-// A single warp running this is a ~7k-instruction DEPENDENT chain (measured 30-140 us inside the factor kernel, whether as unrolled
-// register code - which also misses the instruction cache - or as a shared-memory loop).  Spread over 256 threads each step is one
-// shared-memory round trip + one barrier:
-//   factor : thread (a = tid & 31, c = tid>>5 + 8k) owns 4 elements.  Step j needs no column scaling pass:
-//            M(a,c) -= M(a,j) M(c,j) / M(j,j)   for a >= c > j   (one barrier per step); L(:,j) = M(:,j) rsqrt(M(j,j)) is applied at the end.
-//   inverse: W = L^-1 column-parallel, right-looking: W(r,a) -= L(r,t) W(t,a) for r > t, same ownership, one barrier per step.
-// sL / sW are 32x32 row-major with leading dimension 33.  Must be called by all threads of the CTA.  Returns false on breakdown.
-__device__ __forceinline__ bool cta_potrf_inv(const double* tile, int ld, double* sL, double* sW, double* sR /*[32]*/) {
-  const int tid = threadIdx.x;
-  const int a = tid & 31, c0 = tid >> 5;
+// ---- 32x32 Cholesky + inverse in one warp ------------------------------------------------------------------------------
+// The diagonal block is the serial pivot chain of the whole factorisation, so this routine is latency-critical.  Measured on B200
+// inside the factor kernel (tools/analyze_factor_trace.py): a CTA-wide shared-memory version with one barrier per pivot costs 10.5 us,
+// a one-warp shared-memory loop 30+ us (a ~7k-instruction dependent chain); this one-warp REGISTER version is the fastest (~6 us):
+// lane a owns row a in registers (fully unrolled, constant indices; __noinline__ so the unroller does not give up inside the big
+// kernel), column j is broadcast through shared memory (one LDS per update instead of two shuffles, no predicates: entries above the
+// diagonal hold garbage that is never read), then W = L^-1 is built column-parallel, right-looking, so a lane's FMAs are independent.
+// Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].  Call with one full warp.
+__device__ __noinline__ bool warp_potrf_inv(const double* tile, int ld, double* sL, double* sW, double* sCol /*[32]*/) {
+  const int a = threadIdx.x & 31;
+  double A[32];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { const int c = c0 + 8 * k; sL[a * kLP + c] = tile[a + ld * c]; }
-  __syncthreads();
+  for (int c = 0; c < 32; ++c) A[c] = tile[a + ld * c];
   bool bad = false;
-  for (int j = 0; j < 31; ++j) {
-    double d = sL[j * kLP + j];
+  double rinv = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double d = __shfl_sync(FULL, A[j], j);
     if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-    const double di = 1.0 / d;
-    const double la = sL[a * kLP + j] * di;
+    const double ri = rsqrt(d);
+    const double l = A[j] * ri;  // row j: d / sqrt(d) = sqrt(d)
+    A[j] = l;
+    if (a == j) rinv = ri;
+    sCol[a] = l;
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c0 + 8 * k;
-      if (c > j && a >= c) sL[a * kLP + c] = fma(-la, sL[c * kLP + j], sL[a * kLP + c]);
-    }
-    __syncthreads();
+    for (int c = j + 1; c < 32; ++c) A[c] = fma(-l, sCol[c], A[c]);
+    __syncwarp();
   }
-  if (tid < 32) {
-    double d = sL[tid * kLP + tid];
-    if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-    sR[tid] = rsqrt(d);
-  }
-  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {  // scale the columns: L(a,c) = M(a,c) rsqrt(M(c,c)); zero the upper triangle; W = I
-    const int c = c0 + 8 * k;
-    sL[a * kLP + c] = (a >= c) ? sL[a * kLP + c] * sR[c] : 0.0;
-    sW[a * kLP + c] = (a == c) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  for (int t = 0; t < 32; ++t) {  // thread owns W(r = c0+8k, col a)
-    const double wt = sW[t * kLP + a] * sR[t];
-    __syncthreads();
-    if (c0 == (t & 7)) sW[t * kLP + a] = wt;  // the owner of row t (t = c0 + 8k for some k) finalises it
+  for (int c = 0; c < 32; ++c) sL[a * kLP + c] = (c <= a) ? A[c] : 0.0;
+  __syncwarp();
+  double w[32];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = c0 + 8 * k;
-      if (r > t) sW[r * kLP + a] = fma(-sL[r * kLP + t], wt, sW[r * kLP + a]);
-    }
-    __syncthreads();
+  for (int r = 0; r < 32; ++r) w[r] = (r == a) ? 1.0 : 0.0;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    w[t] *= __shfl_sync(FULL, rinv, t);
+#pragma unroll
+    for (int r = t + 1; r < 32; ++r) w[r] = fma(-sL[r * kLP + t], w[t], w[r]);
   }
-  return !__syncthreads_or(bad) ;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) sW[r * kLP + a] = w[r];
+  __syncwarp();
+  return !bad;
 }
 
 // ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
-// Every 64x64 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a global counter, keeps the tile's
-// accumulator in registers (4x4 per thread) and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are published
-// (per-tile ready flags, ld.acquire / st.release), then finishes it and publishes it.  Each tile is written once by one CTA (no
-// read-modify-write on HBM, no grid-wide barrier); only the chain potrf(j) -> panel(j+1,j) -> potrf(j+1) is serial and everything
-// off the chain overlaps it.  Tasks are fetched in dependency order, so a fetched task only ever waits on tasks already held by running
-// CTAs: no deadlock for any grid size.
+// Every 32x32 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a global counter, keeps the tile's
+// accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are published (per-tile ready
+// flags, ld.acquire / st.release), then finishes it and publishes it.  Each tile is written once by one CTA (no read-modify-write on
+// HBM, no grid-wide barrier); only the chain potrf(j) -> panel(j+1,j) -> potrf(j+1) is serial and everything off the chain overlaps it.
+// Tasks are fetched in dependency order, so a fetched task only ever waits on tasks already held by running CTAs: no deadlock for any
+// grid size.
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -225,53 +218,17 @@ __device__ __forceinline__ void spin_until_set(const int* f) {
 }
 
 constexpr int kFacThreads = 256;
-// dynamic shared memory of band_factor_ll_kernel (doubles): two source tiles, W (64x64), 2 x (L, W) scratch of the 32x32 factorisations
-constexpr int kFacSmemDoubles = 3 * kTileElems + 4 * 32 * kLP;
-
-// acc(4x4 per thread: rows tx+16i, cols ty+16j) -= A B^T for two 64x64 column-major tiles in shared memory
-__device__ __forceinline__ void tile_sub_abt(double (&acc)[4][4], const double* sA, const double* sB, int tx, int ty) {
-#pragma unroll 4
-  for (int m = 0; m < kTile; ++m) {
-    double av[4], bv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { av[i] = sA[tx + 16 * i + kTile * m]; bv[i] = sB[ty + 16 * i + kTile * m]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(-av[i], bv[j], acc[i][j]);
-  }
-}
-
-// 32x32 (sub)block helpers for the diagonal task, 256 threads, 4 outputs each: out(a, c0+8jj)
-//   D(ro+a, co+c) -= sum_m X(a,m) Y(c,m)   with X, Y 32x32 blocks given by (pointer, leading dimension)
-__device__ __forceinline__ void blk32_sub_abt(double* D, int ldd, const double* X, int ldx, const double* Y, int ldy, int a, int c0) {
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int m = 0; m < 32; ++m) {
-    const double xa = X[a + ldx * m];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[jj] = fma(xa, Y[c0 + 8 * jj + ldy * m], acc[jj]);
-  }
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) D[a + ldd * (c0 + 8 * jj)] -= acc[jj];
-}
+static_assert(kTile == 32, "band_factor_ll_kernel is written for 32x32 tiles (4 outputs per thread)");
 
 __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys S) {
-  extern __shared__ double smem[];
-  double* sA = smem;                      // source tile L(i,k) / accumulator staging / diagonal block
-  double* sB = sA + kTileElems;           // source tile L(j,k)
-  double* sW = sB + kTileElems;           // W_j = L_jj^-1, column-major 64x64 (zero above the diagonal)
-  double* sL1 = sW + kTileElems;          // 32x32 scratch: L11, W11, L22, W22 (row-major, ld 33)
-  double* sW1 = sL1 + 32 * kLP;
-  double* sL2 = sW1 + 32 * kLP;
-  double* sW2 = sL2 + 32 * kLP;
+  __shared__ __align__(16) double sA[kTileElems], sB[kTileElems];
+  __shared__ double sM[32 * kLP], sW[32 * kLP], sR[32];
   __shared__ int s_q;
-  __shared__ double sR[32];
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
   const int ntask = S.NT * S.TPC;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;   // 4x4 register block: rows tx+16i, cols ty+16j
-  const int a32 = tid & 31, c32 = tid >> 5; // 32x32 block helpers
+  const int a = tid & 31, c0 = tid >> 5;
   while (true) {
     if (tid == 0) s_q = atomicAdd(counter, 1);
     __syncthreads();
@@ -284,11 +241,9 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     if (band && i >= S.NT) continue;  // tile below the end of the band: never referenced
     double* tile = S.tiles + static_cast<size_t>(q) * kTileElems;
     LVI_TRACE(0);
-    double acc[4][4];
+    double acc[4];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = tile[tx + 16 * ii + kTile * (ty + 16 * jj)];
+    for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
     const int kmin = band ? max(0, i - S.T) : max(0, j - S.T);
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
@@ -299,104 +254,55 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       if (k == j - 1) LVI_TRACE(1);
       const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
       const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
-      double2* dA = reinterpret_cast<double2*>(sA);
-      double2* dB = reinterpret_cast<double2*>(sB);
 #pragma unroll
-      for (int e = tid; e < kTileElems / 2; e += kFacThreads) { dA[e] = __ldcg(Li + e); dB[e] = __ldcg(Lj + e); }
+      for (int e = tid; e < kTileElems / 2; e += kFacThreads) {
+        reinterpret_cast<double2*>(sA)[e] = __ldcg(Li + e);
+        reinterpret_cast<double2*>(sB)[e] = __ldcg(Lj + e);
+      }
       __syncthreads();
-      if (k == j - 1) { __syncthreads(); LVI_TRACE(2); }
-      tile_sub_abt(acc, sA, sB, tx, ty);
+      if (k == j - 1) LVI_TRACE(2);
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) {
+        const double xa = sA[a + 32 * m];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[jj] = fma(-xa, sB[c0 + 8 * jj + 32 * m], acc[jj]);
+      }
     }
     __syncthreads();
     LVI_TRACE(3);
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) sA[tx + 16 * ii + kTile * (ty + 16 * jj)] = acc[ii][jj];
+    for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = acc[jj];
     __syncthreads();
-    if (s == 0) {
-      // ---- diagonal task: 64x64 Cholesky in shared memory.  D = [D11 . ; D21 D22] (lower), blocks of 32.
-      bool ok = cta_potrf_inv(sA, kTile, sL1, sW1, sR);                                       // L11, W11
+    if (s == 0) {  // diagonal task: L_jj and W_j = L_jj^-1 (only W is kept: panel solves and the back substitution multiply by it)
+      if (tid < 32) {
+        const bool ok = warp_potrf_inv(sA, 32, sM, sW, sR);
+        if (!ok && tid == 0) *S.fail = 1;
+      }
+      __syncthreads();
       LVI_TRACE(4);
-      {  // L21 = D21 W11^T  -> overwrite D21 in sA (rows 32.., cols 0..31); out(a,c) = sum_{m<=c} D21(a,m) W11(c,m)
-        double out[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int c = c32 + 8 * jj;
-          double v = 0.0;
-          for (int m = 0; m <= c; ++m) v = fma(sA[32 + a32 + kTile * m], sW1[c * kLP + m], v);
-          out[jj] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) sA[32 + a32 + kTile * (c32 + 8 * jj)] = out[jj];
-      }
-      __syncthreads();
-      blk32_sub_abt(sA + 32 + kTile * 32, kTile, sA + 32, kTile, sA + 32, kTile, a32, c32);   // D22 -= L21 L21^T
-      __syncthreads();
-      LVI_TRACE(5);
-      ok = cta_potrf_inv(sA + 32 + kTile * 32, kTile, sL2, sW2, sR) && ok;                    // L22, W22
-      if (!ok && tid == 0) *S.fail = 1;
-      LVI_TRACE(6);
-      // W = [W11 0 ; -W22 (L21 W11) W22].  M = L21 W11 -> sB (32x32, ld 32): M(a,c) = sum_{m>=c} L21(a,m) W11(m,c)
-      {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int c = c32 + 8 * jj;
-          double v = 0.0;
-          for (int m = c; m < 32; ++m) v = fma(sA[32 + a32 + kTile * m], sW1[m * kLP + c], v);
-          sB[a32 + 32 * c] = v;
-        }
-      }
-      __syncthreads();
-      {  // assemble W (column-major 64x64): each thread 4 elements of every 32x32 quadrant; W21(a,c) = -sum_m W22(a,m) M(m,c)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int c = c32 + 8 * jj;
-          double v = 0.0;
-          for (int m = 0; m <= a32; ++m) v = fma(-sW2[a32 * kLP + m], sB[m + 32 * c], v);
-          sW[a32 + kTile * c] = sW1[a32 * kLP + c];
-          sW[a32 + kTile * (32 + c)] = 0.0;
-          sW[32 + a32 + kTile * c] = v;
-          sW[32 + a32 + kTile * (32 + c)] = sW2[a32 * kLP + c];
-        }
-      }
-      __syncthreads();
-      double2* Wg = reinterpret_cast<double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
-      const double2* sW2v = reinterpret_cast<const double2*>(sW);
-      for (int e = tid; e < kTileElems / 2; e += kFacThreads) Wg[e] = sW2v[e];
+      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      for (int e = tid; e < kTileElems; e += kFacThreads) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
       __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
       LVI_TRACE(7);
-    } else {
-      // ---- panel task: X = P W_j^T
+    } else {       // panel task: X = P W_j^T
       if (tid == 0) spin_until_set(flags + j * S.TPC);
       __syncthreads();
       LVI_TRACE(4);
-      const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(j) * kTileElems);
-      double2* dW = reinterpret_cast<double2*>(sW);
-      for (int e = tid; e < kTileElems / 2; e += kFacThreads) dW[e] = __ldcg(Wg + e);
+      const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
       __syncthreads();
       LVI_TRACE(5);
-      double out[4][4];
+      double out[4];
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) out[ii][jj] = 0.0;
-      const int mmax = ty + 48;  // W is lower triangular: X(:,c) only needs m <= c
-      for (int m = 0; m <= mmax; ++m) {
-        double av[4], wv[4];
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) { av[ii] = sA[tx + 16 * ii + kTile * m]; wv[ii] = sW[ty + 16 * ii + kTile * m]; }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) out[ii][jj] = fma(av[ii], wv[jj], out[ii][jj]);
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c = c0 + 8 * jj;
+        double v = 0.0;
+        for (int m = 0; m <= c; ++m) v = fma(sA[a + 32 * m], sW[c * kLP + m], v);
+        out[jj] = v;
       }
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) tile[tx + 16 * ii + kTile * (ty + 16 * jj)] = out[ii][jj];
+      for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
       LVI_TRACE(6);
       __syncthreads();
       if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
@@ -411,18 +317,15 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
             const double* Xb = S.tiles + static_cast<size_t>(fb) * kTileElems;
             for (int e = tid; e < kTileElems; e += kFacThreads) { sA[e] = __ldcg(Xa + e); sB[e] = __ldcg(Xb + e); }
             __syncthreads();
-            double pr[4][4];
+            double pr[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int m = 0; m < 32; ++m) {
+              const double xa = sA[a + 32 * m];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii)
+              for (int jj = 0; jj < 4; ++jj) pr[jj] = fma(xa, sB[c0 + 8 * jj + 32 * m], pr[jj]);
+            }
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) pr[ii][jj] = 0.0;
-            tile_sub_abt(pr, sA, sB, tx, ty);  // pr = -Xa Xb^T
-#pragma unroll
-            for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                if (pr[ii][jj] != 0.0)
-                  atomicAdd(S.C + kTile * bi + tx + 16 * ii + static_cast<size_t>(S.ldc) * (kTile * bj + ty + 16 * jj), pr[ii][jj]);
+            for (int jj = 0; jj < 4; ++jj)
+              if (pr[jj] != 0.0) atomicAdd(S.C + 32 * bi + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
             __syncthreads();
           }
       }
@@ -501,7 +404,7 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
       const double* tl = (d == 1) ? sT : S.tiles + (static_cast<size_t>(k) * S.TPC + d) * kTileElems;
       const int ldt = (d == 1) ? kLD : kTile;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < kTile / 32; ++h) {
         const int c = lane + 32 * h;
         const double* tc = tl + ldt * c;
         double u = 0.0;
@@ -643,12 +546,9 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   LVI_REQUIRE(A.work_i && A.work_d, LVI_ERR_INVALID, "band solver workspace missing");
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
-  constexpr size_t smem = kFacSmemDoubles * sizeof(double);
+  constexpr size_t smem = 0;
   static int resident = 0;
-  if (!resident) {
-    LVI_CUDA(cudaFuncSetAttribute(band_factor_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
-  }
+  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
   const int grid = std::min(resident, A.NT * A.TPC);
   const char* trace_path = std::getenv("LVI_TRACE_FACTOR");
   if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]

@@ -9,11 +9,11 @@ tr = np.where(tr > 0, (tr - t0) / 1e3, np.nan)   # us
 print(f"NT {NT} TPC {TPC} T {T} RB {RB}; total {np.nanmax(tr):.1f} us")
 d = tr[:, 0, :]          # diagonal tasks
 p = tr[:, 1, :] if T >= 1 else None  # first sub-diagonal panel tile
-names_d = ["fetch", "last dep seen", "last tiles loaded", "accum done", "potrf1 done", "glue done", "potrf2 done", "published"]
+names_d = ["fetch", "last dep seen", "last tiles loaded", "accum done", "potrf+inv done", "-", "-", "published"]
 sl = slice(20, NT - 20)
 print("diagonal task, mean us between marks:")
-for a in range(1, 8):
-    print(f"  {names_d[a-1]:>18} -> {names_d[a]:<18} {np.nanmean(d[sl, a] - d[sl, a-1]):8.2f}")
+for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 7)):
+    print(f"  {names_d[a]:>18} -> {names_d[b]:<18} {np.nanmean(d[sl, b] - d[sl, a]):8.2f}")
 if p is not None:
     names_p = ["fetch", "last dep seen", "last tiles loaded", "accum done", "W flag seen", "W loaded", "X computed", "published"]
     print("panel task (j+1,j), mean us between marks:")
