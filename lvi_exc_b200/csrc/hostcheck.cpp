@@ -2,8 +2,10 @@
 // (lowering.hpp, residuals.cuh, spline_math.cuh are __host__ __device__).  Built into liblvi_hostcheck.so and used ONLY
 // by the `-m "not gpu"` tests to validate the analytic Jacobians against the oracle's forward-mode Jets without a GPU.
 // It is not linked into liblvi_exc_b200.so and is not reachable from the C-ABI: the product has no CPU path.
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "lowering.hpp"
 
@@ -16,7 +18,7 @@ template <int TYPE>
 void eval_type(const ProblemView& P, const Lowered& L, double& cost, double& fixed, double* res, double* J, int nt) {
   const ResTable& T = P.tab[TYPE];
   const int rows = rt_rows(TYPE), cols = rt_cols(TYPE);
-  for (int i = 0; i < T.n; ++i) {
+  for (int i = T.lo; i < T.hi; ++i) {
     ResOut o;
     std::memset(&o, 0, sizeof(o));
     eval_residual<TYPE>(P, i, true, o);
@@ -85,6 +87,45 @@ int lvi_hostcheck_evaluate(const lvi_problem_desc* d, double* cost, double* fixe
 }
 
 }  // extern "C"
+
+// One rank's share of the normal equations under the library's data-parallel sharding (ResTable lo/hi from shard_range, exactly
+// as lvi_problem_create sets them): cost, g = J^T r [nt], H = J^T J [nt x nt, dense, row-major].  The layout comes from the FULL
+// problem, so the shares of all ranks add up to the single-rank result (tests/test_multi_gloo.py all-reduces them over gloo).
+extern "C" int lvi_hostcheck_normal_equations(const lvi_problem_desc* d, int rank, int world, double* cost, double* g, double* H) {
+  try {
+    Lowered L;
+    lower_problem(*d, L);
+    double sens[SENS_N];
+    pack_sens(*d, sens);
+    ProblemView P = host_view(*d, L, sens);
+    compute_bandwidth(P, L);
+    for (int t = 0; t < RT_COUNT; ++t) shard_range(P.tab[t].n, rank, world, P.tab[t].lo, P.tab[t].hi);
+    const int nt = L.nt();
+    std::vector<double> res(L.n_res, 0.0), J(static_cast<size_t>(L.n_res) * nt, 0.0);
+    double c = 0, f = 0;
+    eval_type<RT_GYRO>(P, L, c, f, res.data(), J.data(), nt);
+    eval_type<RT_ACCEL>(P, L, c, f, res.data(), J.data(), nt);
+    eval_type<RT_SURFEL>(P, L, c, f, res.data(), J.data(), nt);
+    eval_type<RT_CAM>(P, L, c, f, res.data(), J.data(), nt);
+    eval_type<RT_CAMSURF>(P, L, c, f, res.data(), J.data(), nt);
+    eval_type<RT_ORIENT>(P, L, c, f, res.data(), J.data(), nt);
+    *cost = c;
+    std::fill(g, g + nt, 0.0);
+    std::fill(H, H + static_cast<size_t>(nt) * nt, 0.0);
+    std::vector<int> nz;
+    for (int r = 0; r < L.n_res; ++r) {  // rows are sparse (<= 60 non-zeros): outer products over the non-zeros only
+      const double* row = J.data() + static_cast<size_t>(r) * nt;
+      nz.clear();
+      for (int a = 0; a < nt; ++a) if (row[a] != 0.0) nz.push_back(a);
+      for (int a : nz) {
+        g[a] += row[a] * res[r];
+        for (int b : nz) H[static_cast<size_t>(a) * nt + b] += row[a] * row[b];
+      }
+    }
+    return LVI_OK;
+  } catch (const RangeError& e) { g_err = e.what(); return LVI_ERR_RANGE; }
+  catch (const std::exception& e) { g_err = e.what(); return LVI_ERR_INVALID; }
+}
 
 // trajectory evaluation through the product's closed-form path: out = p[3] a[3] q[4] w_body[3]
 extern "C" int lvi_hostcheck_traj_eval(const lvi_problem_desc* d, double t, double* out) {

@@ -27,6 +27,13 @@ namespace lvi {
 
 struct RangeError : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// data-parallel sharding: rank r of `world` evaluates the contiguous (= time-contiguous, tables are chronological)
+// index range [lo, hi) of every residual table; the normal equations are summed across ranks (NCCL all-reduce).
+inline void shard_range(int n, int rank, int world, int& lo, int& hi) {
+  lo = static_cast<int>(static_cast<long long>(n) * rank / world);
+  hi = static_cast<int>(static_cast<long long>(n) * (rank + 1) / world);
+}
+
 struct LoweredTable {
   int n = 0, active = 1;
   std::vector<int> i0a, i0b, ia, ib;

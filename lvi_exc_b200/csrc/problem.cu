@@ -350,8 +350,7 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
     const LoweredTable& T = L.tab[t];
     ResTable& R = V.tab[t];
     R.n = T.n; R.active = T.active;
-    R.lo = static_cast<int>(static_cast<long long>(T.n) * ctx->rank / ctx->world);
-    R.hi = static_cast<int>(static_cast<long long>(T.n) * (ctx->rank + 1) / ctx->world);
+    shard_range(T.n, ctx->rank, ctx->world, R.lo, R.hi);
     R.i0a = up_i(p->tab_i[t][0], T.i0a); R.i0b = up_i(p->tab_i[t][1], T.i0b); R.ia = up_i(p->tab_i[t][2], T.ia); R.ib = up_i(p->tab_i[t][3], T.ib);
     R.ua = up_d(p->tab_d[t][0], T.ua); R.ub = up_d(p->tab_d[t][1], T.ub); R.v = up_d(p->tab_d[t][2], T.v);
     R.weight = up_d(p->tab_d[t][3], T.weight); R.huber = up_d(p->tab_d[t][4], T.huber);
