@@ -42,33 +42,47 @@ __global__ void lm_diag_kernel(const double* __restrict__ dH, const double* __re
   if (t < nt) diag[t] = fmin(fmax(dH[t] * scale[t] * scale[t], lo), hi);  // LevenbergMarquardtStrategy: clamp(diag(J^T J))
 }
 
-// A = S H S + diag(D2) in tile storage; the extra border row carries rhs = -S g.  One CTA per tile (+ corner CTAs).
+// A = S H S + diag(D2) in tile storage; the extra border row carries rhs = -S g.  One CTA per tile (+ corner CTAs): 228 MB of pure
+// streaming at C2, so each thread moves 4 consecutive rows of one column with two 16-byte loads/stores and reads its scale factors once.
 __global__ void __launch_bounds__(256) build_system_kernel(BandSys H, BandSys A, const double* __restrict__ scale, const double* __restrict__ diag,
                                                            double inv_radius, const double* __restrict__ g) {
+  static_assert(kTile == 32, "thread mapping below assumes 32x32 tiles");
   const int ntile = A.NT * A.TPC;
   const int nb = A.nb, nbo = A.nbo;
   if (static_cast<int>(blockIdx.x) < ntile) {
     const int J = blockIdx.x / A.TPC, q = blockIdx.x % A.TPC;
     if (q <= A.T && J + q >= A.NT) return;
-    const double* src = H.tiles + static_cast<size_t>(blockIdx.x) * kTileElems;
-    double* dst = A.tiles + static_cast<size_t>(blockIdx.x) * kTileElems;
-    for (int e = threadIdx.x; e < kTileElems; e += blockDim.x) {
-      const int a = e & (kTile - 1), b = e >> kTileLog;
-      const int j = J * kTile + b;
-      double v = 0.0;
-      if (q <= A.T) {
-        const int i = (J + q) * kTile + a;
+    const int b = threadIdx.x >> 3, a0 = (threadIdx.x & 7) * 4;   // column b, rows a0..a0+3
+    const size_t off = static_cast<size_t>(blockIdx.x) * kTileElems + b * kTile + a0;
+    const double2 s0 = __ldcs(reinterpret_cast<const double2*>(H.tiles + off));
+    const double2 s1 = __ldcs(reinterpret_cast<const double2*>(H.tiles + off) + 1);
+    const double src[4] = {s0.x, s0.y, s1.x, s1.y};
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    const int j = J * kTile + b;
+    if (q <= A.T) {
+      const int i0 = (J + q) * kTile + a0;
+      const double sj = j < nb ? scale[j] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
         if (i < nb && j < nb) {
-          if (i >= j) v = src[e] * scale[i] * scale[j];
-          if (i == j) v += diag[i] * inv_radius;
-        } else if (i == j) v = 1.0;  // padding rows keep the factorisation well defined
-      } else if (j < nb) {
-        const int bi = (q - A.T - 1) * kTile + a;
-        if (bi < nbo) v = src[e] * scale[nb + bi] * scale[j];
-        else if (bi == nbo) v = -g[j] * scale[j];
+          if (i >= j) v[k] = src[k] * scale[i] * sj;
+          if (i == j) v[k] += diag[i] * inv_radius;
+        } else if (i == j) v[k] = 1.0;  // padding rows keep the factorisation well defined
       }
-      dst[e] = v;
+    } else if (j < nb) {
+      const int bi0 = (q - A.T - 1) * kTile + a0;
+      const double sj = scale[j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int bi = bi0 + k;
+        if (bi < nbo) v[k] = src[k] * scale[nb + bi] * sj;
+        else if (bi == nbo) v[k] = -g[j] * sj;
+      }
     }
+    double2* dst = reinterpret_cast<double2*>(A.tiles + off);
+    __stcs(dst, make_double2(v[0], v[1]));
+    __stcs(dst + 1, make_double2(v[2], v[3]));
   } else {
     const int ldc = A.ldc;
     for (int e = (blockIdx.x - ntile) * blockDim.x + threadIdx.x; e < ldc * ldc; e += (gridDim.x - ntile) * blockDim.x) {
@@ -575,7 +589,8 @@ static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
     LVI_CUDA(cudaFuncSetAttribute(band_backsolve_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256, smem);
   }
-  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(resident, A.NT), 256, smem, A);
+  // one CTA per SM: co-resident CTAs that only spin on their arrival counters slow the working one down (measured 2x in the factorisation)
+  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(std::min(resident, ctx->sm_count), A.NT), 256, smem, A);
 }
 void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
   band_factor_only(ctx, A);

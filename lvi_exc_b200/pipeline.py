@@ -84,7 +84,8 @@ class TrajectoryManager:
 
     def _base(self, so3_only=False, **locks) -> ProblemData:
         c = self.calib
-        return ProblemData(self.t0, self.dt, self.n_knots, None if so3_only else self.r3, self.so3, lidar_q=c.q_LtoI, lidar_p=c.p_LinI,
+        # every problem owns its parameter memory (a solve updates it in place; _copy_back takes the result)
+        return ProblemData(self.t0, self.dt, self.n_knots, None if so3_only else self.r3.copy(), self.so3.copy(), lidar_q=c.q_LtoI, lidar_p=c.p_LinI,
                            cam_q=c.q_CtoI, cam_p=c.p_CinI, gravity=c.gravity_rp, acc_bias=c.acc_bias, gyr_bias=c.gyr_bias, cam=self.cam,
                            locks=locks)
 

@@ -45,22 +45,19 @@ def run(verbose: bool = True) -> None:
     s_g, s_o = cb.solve(pd_g, 30), orc.solve(pd_o, 30)
     assert abs(s_g.final_cost - s_o.final_cost) <= 1e-6 * max(1.0, s_o.final_cost), (s_g.final_cost, s_o.final_cost)
     assert np.abs(pd_g.so3_knots - pd_o.so3_knots).max() < 1e-6
-    # S1 from a state near the optimum (control points sampled from the ground truth): far from it the 2 s problem is so
-    # ill-conditioned that the LM path is chaotic (the oracle's own path then depends on its thread count)
+    # S1 from a state near the optimum (control points sampled from the ground truth)
     mgr1 = workload.make_manager(seq)
     pd_g = mgr1.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
     pd_o = mgr1.problem_surfel(omap.planes_Pi, sp_o, seq.map_time)
     ev_g, ev_o = CudaProblem(cb, pd_g).evaluate(gradient=False), ob.OracleProblem(pd_o).evaluate(gradient=False)
     assert abs(ev_g["cost"] - ev_o["cost"]) <= 1e-9 * ev_o["cost"], (ev_g["cost"], ev_o["cost"])
     assert np.abs(ev_g["residuals"] - ev_o["residuals"]).max() <= 1e-7 * max(1.0, np.abs(ev_o["residuals"]).max())
-    # one LM iteration: 2 s of data leave the LiDAR translation weakly observable, and along such directions the LM path amplifies
-    # summation-order round-off within a few iterations (the oracle's own path changes with its OpenMP thread count); the
-    # multi-iteration and whole-pipeline parity checks live in tests/test_gpu_*.py on well-conditioned sequences
-    s_g, s_o = cb.solve(pd_g, 1), orc.solve(pd_o, 1)
+    s_g, s_o = cb.solve(pd_g, 5), orc.solve(pd_o, 5)
     rel = abs(s_g.final_cost - s_o.final_cost) / s_o.final_cost
-    assert rel < 1e-6, (s_g.final_cost, s_o.final_cost)
+    assert s_g.num_iterations == s_o.num_iterations and rel < 1e-6, (s_g.final_cost, s_o.final_cost)
+    assert pipeline.quat_angle(pd_g.lidar_q, pd_o.lidar_q) < 1e-4 and np.abs(pd_g.lidar_p - pd_o.lidar_p).max() < 1e-3
     if verbose:
         print(f"smoke ok: leaves {gmap.num_leaves}, planes {gmap.num_planes}, surfel points {len(sp_g)}, "
-              f"S0 cost {s_g.final_cost:.6e}, S1(1 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
+              f"S0 cost {s_g.final_cost:.6e}, S1(5 it) cost gpu {s_g.final_cost:.6e} oracle {s_o.final_cost:.6e}, "
               f"kernel launches {cb.launches}")
     cb.close()
