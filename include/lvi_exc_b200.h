@@ -248,7 +248,8 @@ int lvi_problem_jacobian_dense(lvi_problem* p, double* J);
  * Jacobians + normal equations + damped solve + trial-step cost. Parameters are restored afterwards. */
 int lvi_problem_bench_iterations(lvi_problem* p, int iters,
                                  float* ms_per_phase /* [6] linearize, build_system, band_factor, corner+backsolve, trial cost, whole loop / iters */);
-/* linear-system layout: out[8] = band dims, border dims, half bandwidth, block columns, sub-diagonal tile rows, border tile rows, 0, 0 */
+/* linear-system layout: out[8] = band dims, border dims, half bandwidth, block columns, sub-diagonal tile rows, border tile rows,
+ * first position of the second chain of the two-sided ordering (== band dims: one chain), unused padding positions before it */
 int lvi_problem_layout(lvi_problem* p, int32_t* out);
 
 /* ---- (a-3') visual landmark -> surfel association ------------------------------------------------------- */
@@ -288,9 +289,11 @@ int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scan
 /* ---- diagnostics ---------------------------------------------------------------------------------------------- */
 /* Solves A x = rhs through the band+arrow tile Cholesky used by lvi_problem_solve (tests only). A_dense is
  * [n x n] row-major symmetric positive definite, n = nb + nbo; within the first nb rows/cols entries with
- * |i-j| > bw must be zero. Returns LVI_ERR_NUMERIC on Cholesky breakdown. */
-int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_dense, const double* rhs,
-                         double* x_out);
+ * |i-j| > bw must be zero.  Two-sided ordering: band positions [0, chain1_start) and [chain1_start, nb) are two
+ * chains that must not couple directly (chain1_start a multiple of 32, == nb for one chain); the first n_mid
+ * border dims are the separator, factored as a second-level system.  LVI_ERR_NUMERIC on Cholesky breakdown. */
+int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start, int n_mid, const double* A_dense,
+                         const double* rhs, double* x_out);
 
 #ifdef __cplusplus
 }

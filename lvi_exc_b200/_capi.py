@@ -194,7 +194,7 @@ def load() -> C.CDLL:
     for name in ("lvi_transform_scans", "lvi_transform_scans_d"):
         getattr(lib, name).argtypes = [vp, vp, C.c_int32, C.c_int64, c_double_p, vp]
     lib.lvi_trajectory_evaluate.argtypes = [vp, C.POINTER(ProblemDesc), c_double_p, C.c_int64, c_double_p, c_double_p, c_uint8_p]
-    lib.lvi_band_solve_dense.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+    lib.lvi_band_solve_dense.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     _lib = lib
     return lib
 

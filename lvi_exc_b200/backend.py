@@ -268,8 +268,8 @@ class CudaBackend:
         check(self.lib.lvi_associate_landmarks(self.ctx, smap.surfels, ptr(pts), len(pts), radius, ptr(out)))
         return out
 
-    def band_solve_dense(self, A, rhs, nb, nbo, bw):
+    def band_solve_dense(self, A, rhs, nb, nbo, bw, chain1_start=None, n_mid=0):
         A = np.ascontiguousarray(A, dtype=np.float64); rhs = np.ascontiguousarray(rhs, dtype=np.float64)
         x = np.zeros(nb + nbo)
-        check(self.lib.lvi_band_solve_dense(self.ctx, nb, nbo, bw, ptr(A), ptr(rhs), ptr(x)))
+        check(self.lib.lvi_band_solve_dense(self.ctx, nb, nbo, bw, nb if chain1_start is None else chain1_start, n_mid, ptr(A), ptr(rhs), ptr(x)))
         return x

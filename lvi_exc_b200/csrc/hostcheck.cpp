@@ -44,7 +44,7 @@ extern "C" {
 
 const char* lvi_hostcheck_last_error() { return g_err.c_str(); }
 
-// sizes: out[0]=n_res out[1]=nt out[2]=nb out[3]=nbo out[4]=bw ; pos arrays may be NULL
+// sizes: out[0]=n_res out[1]=nt out[2]=nb out[3]=nbo out[4]=bw out[5]=chain1_start out[6]=n_mid out[7]=n_pad ; pos arrays may be NULL
 int lvi_hostcheck_layout(const lvi_problem_desc* d, int* out, int* pos_r3, int* pos_so3, int* pos_sens, int* pos_rho) {
   try {
     Lowered L;
@@ -53,7 +53,7 @@ int lvi_hostcheck_layout(const lvi_problem_desc* d, int* out, int* pos_r3, int* 
     pack_sens(*d, sens);
     ProblemView P = host_view(*d, L, sens);
     compute_bandwidth(P, L);
-    out[0] = L.n_res; out[1] = L.nt(); out[2] = L.nb; out[3] = L.nbo; out[4] = L.bw;
+    out[0] = L.n_res; out[1] = L.nt(); out[2] = L.nb; out[3] = L.nbo; out[4] = L.bw; out[5] = L.chain1_start; out[6] = L.n_mid; out[7] = L.n_pad;
     if (pos_r3) std::memcpy(pos_r3, L.pos_r3.data(), sizeof(int) * d->n_knots);
     if (pos_so3) std::memcpy(pos_so3, L.pos_so3.data(), sizeof(int) * d->n_knots);
     if (pos_sens) std::memcpy(pos_sens, L.pos_sens, sizeof(int) * TB_COUNT);

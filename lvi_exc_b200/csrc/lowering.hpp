@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -47,6 +48,13 @@ struct Lowered {
   std::vector<int> pos_r3, pos_so3, pos_rho;
   int pos_sens[TB_COUNT];
   int nb = 0, nbo = 0, bw = 0;   // band dims, border dims, half bandwidth
+  // Two-sided ("burn at both ends") ordering: the band part is split into chain 0 = [0, chain1_start) holding the first half of the
+  // trajectory in time order and chain 1 = [chain1_start, nb) holding the second half in REVERSED time order; the knots in between
+  // (wide enough that no residual or Schur row couples the two chains) lead the arrow border.  Both chains are ordinary band matrices
+  // that only meet in the border, so they factor concurrently and the serial pivot chain halves.  chain1_start == nb: single chain.
+  int chain1_start = 0;          // multiple of 32
+  int n_mid = 0;                 // dims of the middle separator (= first n_mid border dims)
+  int n_pad = 0;                 // unused dims padding chain 0 up to a tile boundary (positions chain1_start - n_pad .. chain1_start - 1)
   int n_rho = 0;                 // free inverse depths; tangent positions nb+nbo .. nb+nbo+n_rho-1
   // Schur rows of the inverse depths: landmark l couples to row_pos[row_start[l] .. row_start[l+1]) (-1: constant parameter);
   // slots: [0,24) reference window (cols 0..23 of its camera residuals), [24,30) camera q,p, then 24 per observation
@@ -243,18 +251,38 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   if (border_knots.size() > 16) border_knots.clear();  // not an arrow structure: leave those knots in the band
   // ---- positions
   L.pos_r3.assign(n, -1); L.pos_so3.assign(n, -1); L.pos_rho.assign(std::max(d.n_landmarks, 1), -1);
-  int pb = 0;
-  for (int i = 0; i < n; ++i) {
-    if (knot_used[i] && !border_knots.count(i)) {
-      if (r3_free) { L.pos_r3[i] = pb; pb += 3; }
-      if (so3_free) { L.pos_so3[i] = pb; pb += 3; }
-    }
+  std::vector<int> band;  // band knots in time order
+  for (int i = 0; i < n; ++i) if (knot_used[i] && !border_knots.count(i)) band.push_back(i);
+  // longest coupling in knots among band knots: 3 inside one evaluation window, reference -> last observation for the camera
+  int kspan = 3;
+  {
+    const LoweredTable& TS = L.tab[RT_SURFEL];
+    if (border_knots.empty()) for (int i = 0; i < TS.n; ++i) kspan = std::max(kspan, TS.i0b[i] + 3 - TS.i0a[i]);
+    const LoweredTable& TC = L.tab[RT_CAM];
+    for (int i = 0; i < TC.n; ++i) kspan = std::max(kspan, std::abs(TC.i0b[i] - TC.i0a[i]) + 3);
+    std::vector<int> lo(std::max(d.n_landmarks, 1), 1 << 30), hi(std::max(d.n_landmarks, 1), -1);
+    for (int i = 0; i < TC.n; ++i) { const int l = TC.ia[i]; lo[l] = std::min(lo[l], std::min(TC.i0a[i], TC.i0b[i])); hi[l] = std::max(hi[l], std::max(TC.i0a[i], TC.i0b[i]) + 3); }
+    for (int l = 0; l < d.n_landmarks; ++l) if (hi[l] >= 0) kspan = std::max(kspan, hi[l] - lo[l]);  // Schur fill couples all windows of a landmark
+    const LoweredTable& TV = L.tab[RT_CAMSURF];
+    if (border_knots.empty()) for (int i = 0; i < TV.n; ++i) kspan = std::max(kspan, TV.i0b[i] + 3 - TV.i0a[i]);
   }
+  const int m = static_cast<int>(band.size()), wmid = kspan + 1;
+  const bool twist = traj_free && m >= 8 * wmid && !std::getenv("LVI_NO_TWIST");
+  const int mid_a = twist ? (m - wmid) / 2 : m, mid_b = twist ? mid_a + wmid : m;   // band[mid_a, mid_b) = separator
+  int pb = 0;
+  auto place = [&](int i) { if (r3_free) { L.pos_r3[i] = pb; pb += 3; } if (so3_free) { L.pos_so3[i] = pb; pb += 3; } };
+  for (int k = 0; k < mid_a; ++k) place(band[k]);
+  L.n_pad = 0;
+  if (twist) { L.n_pad = (32 - pb % 32) % 32; pb += L.n_pad; }
+  L.chain1_start = pb;
+  for (int k = m - 1; k >= mid_b; --k) place(band[k]);
   L.nb = pb;
+  if (!twist) L.chain1_start = L.nb;
+  for (int k = mid_a; k < mid_b; ++k) place(band[k]);
+  L.n_mid = pb - L.nb;
   for (int i : border_knots) {
     if (!knot_used[i]) continue;
-    if (r3_free) { L.pos_r3[i] = pb; pb += 3; }
-    if (so3_free) { L.pos_so3[i] = pb; pb += 3; }
+    place(i);
   }
   const bool sens_free[TB_COUNT] = {!d.lock_lidar_q, !d.lock_lidar_p, !d.lock_cam_q, !d.lock_cam_p, true, !d.lock_acc_bias, !d.lock_gyr_bias};
   const int sens_dim[TB_COUNT] = {3, 3, 3, 3, 2, 3, 3};
@@ -317,21 +345,33 @@ inline void pack_sens(const lvi_problem_desc& d, double* s) {
   s[SENS_G] = d.gravity ? d.gravity[0] : 0; s[SENS_G + 1] = d.gravity ? d.gravity[1] : 0;
 }
 
-template <int TYPE> inline void bw_of_type(const ProblemView& P, int nb, int& bw) {
+// half bandwidth inside each chain; a residual must never couple the two chains directly (the separator guarantees it)
+struct SpanAcc {
+  int c1, nb, bw = 0;
+  int lo[2], hi[2];
+  void begin() { lo[0] = lo[1] = 1 << 30; hi[0] = hi[1] = -1; }
+  void add(int p) { if (p >= 0 && p < nb) { const int c = p >= c1; lo[c] = std::min(lo[c], p); hi[c] = std::max(hi[c], p); } }
+  void end() {
+    if (hi[0] >= 0 && hi[1] >= 0) throw std::logic_error("lowering: a coupling crosses the separator of the two-sided ordering");
+    for (int c = 0; c < 2; ++c) if (hi[c] >= 0) bw = std::max(bw, hi[c] - lo[c]);
+  }
+};
+template <int TYPE> inline void bw_of_type(const ProblemView& P, SpanAcc& A) {
   const ResTable& T = P.tab[TYPE];
   if (!T.active) return;
   for (int i = 0; i < T.n; ++i) {
-    int lo = 1 << 30, hi = -1;
-    for (int c = 0; c < rt_cols(TYPE); ++c) { const int p = col_pos<TYPE>(P, i, c); if (p >= 0 && p < nb) { lo = std::min(lo, p); hi = std::max(hi, p); } }
-    if (hi >= 0) bw = std::max(bw, hi - lo);
+    A.begin();
+    for (int c = 0; c < rt_cols(TYPE); ++c) A.add(col_pos<TYPE>(P, i, c));
+    A.end();
   }
 }
 // second lowering pass (needs the column -> position map): positions of every Schur-row slot, and the half bandwidth of the
 // band part INCLUDING the fill the inverse-depth elimination creates between the windows of one landmark
 inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
-  int bw = 0;
-  bw_of_type<RT_GYRO>(P, L.nb, bw); bw_of_type<RT_ACCEL>(P, L.nb, bw); bw_of_type<RT_SURFEL>(P, L.nb, bw);
-  bw_of_type<RT_CAM>(P, L.nb, bw); bw_of_type<RT_CAMSURF>(P, L.nb, bw); bw_of_type<RT_ORIENT>(P, L.nb, bw);
+  SpanAcc acc;
+  acc.c1 = L.chain1_start; acc.nb = L.nb;
+  bw_of_type<RT_GYRO>(P, acc); bw_of_type<RT_ACCEL>(P, acc); bw_of_type<RT_SURFEL>(P, acc);
+  bw_of_type<RT_CAM>(P, acc); bw_of_type<RT_CAMSURF>(P, acc); bw_of_type<RT_ORIENT>(P, acc);
   const LoweredTable& T = L.tab[RT_CAM];
   for (int i = 0; i < T.n; ++i) {
     const int l = T.ia[i];
@@ -342,11 +382,11 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
     for (int c = 48; c < 54; ++c) L.row_pos[rs + 24 + (c - 48)] = col_pos<RT_CAM>(P, i, c);
   }
   for (size_t l = 0; l + 1 < L.row_start.size(); ++l) {
-    int lo = 1 << 30, hi = -1;
-    for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) { const int p = L.row_pos[k]; if (p >= 0 && p < L.nb) { lo = std::min(lo, p); hi = std::max(hi, p); } }
-    if (hi >= 0) bw = std::max(bw, hi - lo);
+    acc.begin();
+    for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) acc.add(L.row_pos[k]);
+    acc.end();
   }
-  L.bw = bw;
+  L.bw = acc.bw;
 }
 
 }  // namespace lvi

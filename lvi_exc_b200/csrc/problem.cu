@@ -248,6 +248,8 @@ void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active
 static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBuf<double>& C, double* Linv, double* x, int* fail) {
   S.nb = L.nb; S.nbo = L.nbo;
   S.NT = (L.nb + kTile - 1) / kTile;
+  S.NT0 = L.chain1_start < L.nb ? L.chain1_start / kTile : S.NT;
+  S.n_mid = L.n_mid;
   S.T = S.NT > 0 ? std::min(S.NT - 1, (L.bw + kTile - 1) / kTile) : 0;
   S.RB = (L.nbo + 1 + kTile - 1) / kTile;  // + the rhs row
   S.TPC = S.T + 1 + S.RB;
@@ -269,6 +271,16 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
   alloc_bandsys(p->A, L, p->A_tiles, p->A_C, p->A_Linv.p, p->A_x.p, p->fail.p);
   p->A_work_i.alloc(p->A.work_i_count()); p->A_work_d.alloc(std::max<size_t>(p->A.work_d_count(), 1));
   p->A.work_i = p->A_work_i.p; p->A.work_d = p->A_work_d.p;
+  p->A2 = BandSys{};
+  if (p->A.n_mid > 0) {  // second-level system: the separator block of the corner, factored with the same tile machinery
+    init_second_level(p->A, p->A2);
+    BandSys& B = p->A2;
+    p->A2_tiles.alloc(static_cast<size_t>(B.NT) * B.TPC * kTileElems); p->A2_C.alloc(static_cast<size_t>(B.ldc) * B.ldc);
+    p->A2_Linv.alloc(static_cast<size_t>(B.NT) * kTileElems); p->A2_x.alloc(static_cast<size_t>(B.NT) * kTile + B.ldc);
+    p->A2_work_i.alloc(B.work_i_count()); p->A2_work_d.alloc(B.work_d_count());
+    B.tiles = p->A2_tiles.p; B.C = p->A2_C.p; B.Linv = p->A2_Linv.p; B.x = p->A2_x.p; B.fail = p->fail.p;
+    B.work_i = p->A2_work_i.p; B.work_d = p->A2_work_d.p; B.trace = nullptr;
+  }
   LVI_REQUIRE(p->A.ldc <= 1024, LVI_ERR_INVALID, "arrow border wider than 1023 dims is not supported");
   const size_t nt = std::max(p->nt, 1);
   {  // Schur rows of the inverse depths

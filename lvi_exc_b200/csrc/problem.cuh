@@ -22,6 +22,8 @@ constexpr int kTileElems = kTile * kTile;
 struct BandSys {
   int nb, nbo;       // band dims, border dims (without the rhs row)
   int NT, T, RB;     // block columns, sub-diagonal tile rows, border tile rows
+  int NT0;           // two-sided ordering: block columns [0, NT0) are chain 0, [NT0, NT) chain 1 (NT0 == NT: one chain)
+  int n_mid;         // leading border dims that form the separator between the chains (factored as a second-level system)
   int TPC;           // tiles per block column = T + 1 + RB
   int ldc;           // RB * kTile
   double* tiles;     // [NT * TPC * kTileElems], each tile column-major
@@ -81,9 +83,9 @@ struct lvi_problem {
   lvi::DBuf<double> planes;
   lvi::ProblemView view{};   // device pointers, parameters -> X
   // normal equations
-  lvi::BandSys H{}, A{};
-  lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x, A_work_d;
-  lvi::DBuf<int> A_work_i;
+  lvi::BandSys H{}, A{}, A2{};   // A2: second-level system of the separator (two-sided ordering)
+  lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x, A_work_d, A2_tiles, A2_C, A2_Linv, A2_x, A2_work_d;
+  lvi::DBuf<int> A_work_i, A2_work_i;
   lvi::SchurView schur{};
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;
@@ -103,5 +105,6 @@ void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active
 void problem_ensure_solver_buffers(lvi_problem* p);
 void problem_download_params(lvi_problem* p);
 // solver.cu
-void band_factor_solve(lvi_ctx* ctx, BandSys& A);
+void band_factor_solve(lvi_ctx* ctx, BandSys& A, BandSys& A2);
+void init_second_level(const BandSys& A, BandSys& A2);   // sizes of the separator system (no allocation)
 }  // namespace lvi

@@ -226,9 +226,22 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(q) * 8 + (slot)] = gtime(); } while (0)
+#define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(tq) * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void spin_until_set(const int* f) {
   while (ld_acquire(f) == 0) {}
+}
+
+// issue order of the block columns: the two chains of the two-sided ordering are interleaved so that both advance together
+__device__ __forceinline__ int ordered_column(int p, int NT0, int NT) {
+  const int n0 = NT0, n1 = NT - NT0, mn = min(n0, n1);
+  if (p < 2 * mn) return (p & 1) ? NT0 + (p >> 1) : (p >> 1);
+  const int r = p - 2 * mn;
+  return n0 >= n1 ? mn + r : NT0 + mn + r;
+}
+// same for the back substitution, which walks each chain from its end
+__device__ __forceinline__ int ordered_column_desc(int p, int NT0, int NT) {
+  const int c = ordered_column(p, NT0, NT);
+  return c < NT0 ? NT0 - 1 - c : NT - 1 - (c - NT0);
 }
 
 constexpr int kFacThreads = 256;
@@ -249,16 +262,19 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     const int q = s_q;
     __syncthreads();
     if (q >= ntask) break;
-    const int j = q / S.TPC, s = q - j * S.TPC;
+    const int jo = q / S.TPC, s = q - jo * S.TPC;
+    const int j = ordered_column(jo, S.NT0, S.NT);
+    const int c_start = j < S.NT0 ? 0 : S.NT0, c_end = j < S.NT0 ? S.NT0 : S.NT;   // the chain this column belongs to
     const bool band = s <= S.T;
     const int i = j + s;
-    if (band && i >= S.NT) continue;  // tile below the end of the band: never referenced
-    double* tile = S.tiles + static_cast<size_t>(q) * kTileElems;
+    if (band && i >= c_end) continue;  // tile below the end of the chain: never referenced
+    const int tq = j * S.TPC + s;      // storage / flag index of this tile
+    double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
     LVI_TRACE(0);
     double acc[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
-    const int kmin = band ? max(0, i - S.T) : max(0, j - S.T);
+    const int kmin = max(c_start, band ? i - S.T : j - S.T);
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
       const int fj = k * S.TPC + (j - k);
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
       for (int e = tid; e < kTileElems; e += kFacThreads) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
       __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
-      if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
+      if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
       LVI_TRACE(7);
     } else {       // panel task: X = P W_j^T
       if (tid == 0) spin_until_set(flags + j * S.TPC);
@@ -319,7 +335,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
       LVI_TRACE(6);
       __syncthreads();
-      if (tid == 0) { __threadfence(); st_release(flags + q, 1); }
+      if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
       LVI_TRACE(7);
       if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
         for (int bi = 0; bi < S.RB; ++bi)
@@ -372,8 +388,9 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
     __syncthreads();
     const int q = s_q;
     if (q >= S.NT) break;
-    const int m = S.NT - 1 - q;
-    const int Tm = min(S.T, S.NT - 1 - m);
+    const int m = ordered_column_desc(q, S.NT0, S.NT);
+    const int c_start = m < S.NT0 ? 0 : S.NT0, c_end = m < S.NT0 ? S.NT0 : S.NT;
+    const int Tm = min(S.T, c_end - 1 - m);
     const double* col = S.tiles + static_cast<size_t>(m) * S.TPC * kTileElems;
     const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(m) * kTileElems);
     for (int e = tid; e < kTileElems / 2; e += 256) {
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
       const int r = (2 * e) & (kTile - 1), c = (2 * e) >> kTileLog;
       sW[r + kLD * c] = v.x; sW[r + 1 + kLD * c] = v.y;
     }
-    if (m >= 1) {
+    if (m > c_start && S.T >= 1) {
       const double2* t1 = reinterpret_cast<const double2*>(S.tiles + (static_cast<size_t>(m - 1) * S.TPC + 1) * kTileElems);
       for (int e = tid; e < kTileElems / 2; e += 256) {
         const double2 v = t1[e];
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
       x[static_cast<size_t>(m) * kTile + tid] = xk;
     }
     __syncthreads();
-    const int nd = min(S.T, m);
+    const int nd = min(S.T, m - c_start);
     for (int d = 1 + warp; d <= nd; d += 8) {
       const int k = m - d;
       const double* tl = (d == 1) ? sT : S.tiles + (static_cast<size_t>(k) * S.TPC + d) * kTileElems;
@@ -473,6 +490,51 @@ __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
   __syncthreads();
   for (int i = tid; i < ld; i += 256) x2[i] = xs[i];
   if (tid == 0 && bad) *S.fail = 1;
+}
+
+// ---- second-level system of the two-sided ordering ------------------------------------------------------------------------------
+// After both chains are factored the corner C = [separator | map-time knots + sensors | rhs]^2 holds the Schur complement of the whole
+// border.  The separator part (n_mid ~ the half bandwidth) is too large for the single-CTA dense corner solve, so it is re-packed as a
+// (dense) band system B with the remaining border as ITS border and goes through the same tile factorisation.
+__global__ void __launch_bounds__(256) corner_to_second_level_kernel(BandSys A, BandSys B) {
+  const int ntile = B.NT * B.TPC;
+  const int nm = A.n_mid;
+  if (static_cast<int>(blockIdx.x) < ntile) {
+    const int J = blockIdx.x / B.TPC, q = blockIdx.x % B.TPC;
+    if (q <= B.T && J + q >= B.NT) return;
+    double* dst = B.tiles + static_cast<size_t>(blockIdx.x) * kTileElems;
+    for (int e = threadIdx.x; e < kTileElems; e += blockDim.x) {
+      const int a = e & (kTile - 1), b = e >> kTileLog;
+      const int j = J * kTile + b;
+      double v = 0.0;
+      if (q <= B.T) {
+        const int i = (J + q) * kTile + a;
+        if (i < nm && j < nm) { if (i >= j) v = A.C[i + static_cast<size_t>(A.ldc) * j]; }
+        else if (i == j) v = 1.0;
+      } else if (j < nm) {
+        const int bi = (q - B.T - 1) * kTile + a;      // row nm + bi of the corner; bi == B.nbo is the rhs row
+        if (bi <= B.nbo) v = A.C[(nm + bi) + static_cast<size_t>(A.ldc) * j];
+      }
+      dst[e] = v;
+    }
+  } else {
+    for (int e = (blockIdx.x - ntile) * blockDim.x + threadIdx.x; e < B.ldc * B.ldc; e += (gridDim.x - ntile) * blockDim.x) {
+      const int bi = e % B.ldc, bj = e / B.ldc;
+      double v = 0.0;
+      if (bi <= B.nbo && bj < B.nbo) { if (bi >= bj) v = A.C[(nm + bi) + static_cast<size_t>(A.ldc) * (nm + bj)]; }
+      else if (bi == bj) v = 1.0;
+      B.C[e] = v;
+    }
+  }
+}
+// border solution of A = [x of the separator | border solution of B]
+__global__ void second_level_solution_kernel(BandSys A, BandSys B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.ldc) return;
+  double v = 0.0;
+  if (i < A.n_mid) v = B.x[i];
+  else if (i < A.nbo) v = B.x[static_cast<size_t>(B.NT) * kTile + (i - A.n_mid)];
+  A.x[static_cast<size_t>(A.NT) * kTile + i] = v;
 }
 
 // y (tangent order) from the solver's x, delta = S y, and the scalars of the step: [2] y.g_s  [3] sum D2 y^2  [4] #non-finite
@@ -553,9 +615,8 @@ static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads, size_t s
   LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   return std::max(1, per_sm) * ctx->sm_count;
 }
-static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
+static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) {
   cudaStream_t st = ctx->stream;
-  LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), st));
   if (A.NT == 0) return;
   LVI_REQUIRE(A.work_i && A.work_d, LVI_ERR_INVALID, "band solver workspace missing");
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
@@ -564,7 +625,7 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   static int resident = 0;
   if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
   const int grid = std::min(resident, A.NT * A.TPC);
-  const char* trace_path = std::getenv("LVI_TRACE_FACTOR");
+  const char* trace_path = allow_trace ? std::getenv("LVI_TRACE_FACTOR") : nullptr;
   if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]
     const size_t n = static_cast<size_t>(A.NT) * A.TPC * 8;
     DBuf<unsigned long long> tr(n);
@@ -580,8 +641,7 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A) {
   }
   LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, A);
 }
-static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
-  LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
+static void band_backsolve_only(lvi_ctx* ctx, BandSys& A) {
   if (A.NT == 0) return;
   constexpr size_t smem = (2 * kTile * (kTile + 1) + 1024) * sizeof(double);
   static int resident = 0;
@@ -592,9 +652,31 @@ static void band_solve_only(lvi_ctx* ctx, BandSys& A) {
   // one CTA per SM: co-resident CTAs that only spin on their arrival counters slow the working one down (measured 2x in the factorisation)
   LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(std::min(resident, ctx->sm_count), A.NT), 256, smem, A);
 }
-void band_factor_solve(lvi_ctx* ctx, BandSys& A) {
+void init_second_level(const BandSys& A, BandSys& B) {
+  B = BandSys{};
+  B.nb = A.n_mid; B.nbo = A.nbo - A.n_mid;
+  B.NT = (B.nb + kTile - 1) / kTile; B.NT0 = B.NT; B.n_mid = 0;
+  B.T = B.NT - 1;                                   // dense
+  B.RB = (B.nbo + 1 + kTile - 1) / kTile; B.TPC = B.T + 1 + B.RB; B.ldc = B.RB * kTile;
+}
+// everything after the factorisation of A: corner (directly, or through the second-level system), then the back substitution
+static void band_solve_only(lvi_ctx* ctx, BandSys& A, BandSys& A2) {
+  if (A.n_mid > 0) {
+    const int ntile = A2.NT * A2.TPC;
+    LVI_LAUNCH(ctx, corner_to_second_level_kernel, ntile + 4, 256, 0, A, A2);
+    band_factor_only(ctx, A2, false);
+    LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A2);
+    band_backsolve_only(ctx, A2);
+    LVI_LAUNCH(ctx, second_level_solution_kernel, (A.ldc + 255) / 256, 256, 0, A, A2);
+  } else {
+    LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
+  }
+  band_backsolve_only(ctx, A);
+}
+void band_factor_solve(lvi_ctx* ctx, BandSys& A, BandSys& A2) {
+  LVI_CUDA(cudaMemsetAsync(A.fail, 0, sizeof(int), ctx->stream));
   band_factor_only(ctx, A);
-  band_solve_only(ctx, A);
+  band_solve_only(ctx, A, A2);
 }
 
 struct Scalars {  // mirrors p->scal
@@ -658,7 +740,7 @@ static void compute_step(lvi_problem* p, double radius) {  // A = S H S + D^2 ; 
   const int corner_ctas = std::max(1, std::min(64, (p->A.ldc * p->A.ldc + 255) / 256));
   LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, 1.0 / radius, p->g.p);
   schur_eliminate(p, 1.0 / radius);
-  band_factor_solve(ctx, p->A);
+  band_factor_solve(ctx, p->A, p->A2);
   schur_back(p, 1.0 / radius);
   LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), ctx->stream));
   LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->schur, p->nt, p->scale.p, p->diag.p, 1.0 / radius, p->g.p,
@@ -863,9 +945,10 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
       LVI_LAUNCH(ctx, build_system_kernel, ntile + corner_ctas, 256, 0, p->H, p->A, p->scale.p, p->diag.p, inv_radius, p->g.p);
       schur_eliminate(p, inv_radius);
       LVI_CUDA(cudaEventRecord(ev[2], st));
+      LVI_CUDA(cudaMemsetAsync(p->A.fail, 0, sizeof(int), st));
       band_factor_only(ctx, p->A);
       LVI_CUDA(cudaEventRecord(ev[3], st));
-      band_solve_only(ctx, p->A);
+      band_solve_only(ctx, p->A, p->A2);
       schur_back(p, inv_radius);
       LVI_CUDA(cudaMemsetAsync(p->scal.p + 2, 0, 3 * sizeof(double), st));
       LVI_LAUNCH(ctx, finish_step_kernel, std::min(blocks_for(p->nt), ctx->sm_count * 4), 256, 0, p->A, p->schur, p->nt, p->scale.p, p->diag.p, inv_radius, p->g.p,
@@ -889,27 +972,32 @@ int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase)
   });
 }
 
-// out[8]: band dims, border dims, half bandwidth, block columns NT, sub-diagonal tile rows T, border tile rows RB, 0, 0
+// out[8]: band dims, border dims, half bandwidth, block columns NT, sub-diagonal tile rows T, border tile rows RB, chain1_start, n_pad
 int lvi_problem_layout(lvi_problem* p, int32_t* out) {
   return guarded([&] {
     LVI_REQUIRE(p && out, LVI_ERR_INVALID, "lvi_problem_layout: null argument");
     problem_ensure_solver_buffers(p);
-    out[0] = p->L.nb; out[1] = p->L.nbo; out[2] = p->L.bw; out[3] = p->A.NT; out[4] = p->A.T; out[5] = p->A.RB; out[6] = 0; out[7] = 0;
+    out[0] = p->L.nb; out[1] = p->L.nbo; out[2] = p->L.bw; out[3] = p->A.NT; out[4] = p->A.T; out[5] = p->A.RB; out[6] = p->L.chain1_start; out[7] = p->L.n_pad;
   });
 }
 
 // test hook: solve a dense SPD system given in band+border form through the tile solver.
 //   A_dense [n x n] row-major symmetric, n = nb + nbo, entries outside the band (|i-j| > bw within the first nb) must be zero.
-int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_dense, const double* rhs, double* x_out) {
+int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start, int n_mid, const double* A_dense, const double* rhs, double* x_out) {
   return guarded([&] {
     LVI_REQUIRE(ctx && A_dense && rhs && x_out && nb >= 0 && nbo >= 0 && nb + nbo > 0, LVI_ERR_INVALID, "lvi_band_solve_dense: bad argument");
+    LVI_REQUIRE(chain1_start % kTile == 0 && chain1_start >= 0 && chain1_start <= nb && n_mid >= 0 && n_mid <= nbo, LVI_ERR_INVALID,
+                "lvi_band_solve_dense: chain1_start must be a multiple of 32 in [0, nb], n_mid in [0, nbo]");
     LVI_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     BandSys S{};
     S.nb = nb; S.nbo = nbo;
     S.NT = (nb + kTile - 1) / kTile;
+    S.NT0 = chain1_start < nb ? chain1_start / kTile : S.NT;
+    S.n_mid = n_mid;
     S.T = S.NT > 0 ? std::min(S.NT - 1, (bw + kTile - 1) / kTile) : 0;
     S.RB = (nbo + 1 + kTile - 1) / kTile; S.TPC = S.T + 1 + S.RB; S.ldc = S.RB * kTile;
+    LVI_REQUIRE(S.ldc <= 1024, LVI_ERR_INVALID, "lvi_band_solve_dense: border too wide");
     const size_t ntile = static_cast<size_t>(S.NT) * S.TPC;
     std::vector<double> ht(std::max<size_t>(ntile * kTileElems, 1), 0.0), hc(static_cast<size_t>(S.ldc) * S.ldc, 0.0);
     const int n = nb + nbo;
@@ -923,7 +1011,8 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
             if (q <= S.T) {
               const int i = (J + q) * kTile + a;
               if (J + q >= S.NT) continue;
-              if (i < nb && j < nb) { if (i >= j) v = at(i, j); }
+              if (J < S.NT0 && J + q >= S.NT0) v = 0.0;  // the two chains never couple directly
+              else if (i < nb && j < nb) { if (i >= j) v = at(i, j); }
               else if (i == j) v = 1.0;
             } else if (j < nb) {
               const int bi = (q - S.T - 1) * kTile + a;
@@ -947,7 +1036,17 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, const double* A_
     DBuf<int> wi(S.work_i_count());
     DBuf<double> wd(std::max<size_t>(S.work_d_count(), 1));
     S.work_i = wi.p; S.work_d = wd.p;
-    band_factor_solve(ctx, S);
+    BandSys S2{};
+    DBuf<double> t2, c2, l2, x2v, wd2;
+    DBuf<int> wi2;
+    if (n_mid > 0) {
+      init_second_level(S, S2);
+      t2.alloc(static_cast<size_t>(S2.NT) * S2.TPC * kTileElems); c2.alloc(static_cast<size_t>(S2.ldc) * S2.ldc);
+      l2.alloc(static_cast<size_t>(S2.NT) * kTileElems); x2v.alloc(static_cast<size_t>(S2.NT) * kTile + S2.ldc);
+      wi2.alloc(S2.work_i_count()); wd2.alloc(S2.work_d_count());
+      S2.tiles = t2.p; S2.C = c2.p; S2.Linv = l2.p; S2.x = x2v.p; S2.fail = fail.p; S2.work_i = wi2.p; S2.work_d = wd2.p;
+    }
+    band_factor_solve(ctx, S, S2);
     std::vector<double> hx(x.n);
     int hf = 0;
     x.download(hx.data(), x.n, st);

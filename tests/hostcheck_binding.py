@@ -27,13 +27,13 @@ def lib():
 
 def layout(pd) -> dict:
     d = pd.desc()
-    out = np.zeros(5, np.int32)
+    out = np.zeros(8, np.int32)
     n, nl = pd.n_knots, max(len(pd.rho), 1)
     pr3, pso3, psens, prho = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(7, np.int32), np.zeros(nl, np.int32)
     rc = lib().lvi_hostcheck_layout(C.byref(d), ptr(out), ptr(pr3), ptr(pso3), ptr(psens), ptr(prho))
     if rc:
         raise (IndexError if rc == -4 else RuntimeError)(lib().lvi_hostcheck_last_error().decode())
-    return dict(n_res=int(out[0]), nt=int(out[1]), nb=int(out[2]), nbo=int(out[3]), bw=int(out[4]), pos_r3=pr3, pos_so3=pso3, pos_sens=psens,
+    return dict(n_res=int(out[0]), nt=int(out[1]), nb=int(out[2]), nbo=int(out[3]), bw=int(out[4]), chain1_start=int(out[5]), n_mid=int(out[6]), n_pad=int(out[7]), pos_r3=pr3, pos_so3=pso3, pos_sens=psens,
                 pos_rho=prho[:len(pd.rho)])
 
 
@@ -59,7 +59,7 @@ def traj_eval(pd, t: float) -> dict:
 
 
 def perm_to_oracle(pd, lay, op) -> np.ndarray:
-    """perm[library tangent position] = oracle tangent offset"""
+    """perm[library tangent position] = oracle tangent offset (-1 at the unused padding positions of the two-sided ordering)"""
     perm = np.full(lay["nt"], -1, np.int64)
     for i in range(pd.n_knots):
         if lay["pos_r3"][i] >= 0:
@@ -78,5 +78,7 @@ def perm_to_oracle(pd, lay, op) -> np.ndarray:
         assert (p < 0) == (o < 0)
         if p >= 0:
             perm[p] = o
-    assert (perm >= 0).all() and len(set(perm.tolist())) == lay["nt"]
+    pad = np.arange(lay["chain1_start"] - lay["n_pad"], lay["chain1_start"])
+    real = np.setdiff1d(np.arange(lay["nt"]), pad)
+    assert (perm[pad] < 0).all() and (perm[real] >= 0).all() and len(set(perm[real].tolist())) == len(real)
     return perm

@@ -78,10 +78,14 @@ def make_lvi_problem(stage: str, duration: float = 2.0, n_landmarks: int = 400):
 
 
 def map_tangent(backend, gp, op, pd) -> np.ndarray:
-    """perm[library tangent position] = oracle tangent offset, from the two libraries' own layout queries"""
+    """perm[library tangent position] = oracle tangent offset (-1 at the padding positions of the two-sided ordering), from the two
+    libraries' own layout queries"""
     from lvi_exc_b200._capi import load
     lib = load()
     nt = gp.num_tangent
+    lay = np.zeros(8, np.int32)
+    assert lib.lvi_problem_layout(gp.h, ptr(lay)) == 0
+    pad = np.arange(lay[6] - lay[7], lay[6])
     perm = np.full(nt, -1, dtype=np.int64)
     n = pd.n_knots
     for i in range(n):
@@ -108,5 +112,6 @@ def map_tangent(backend, gp, op, pd) -> np.ndarray:
         assert (pos < 0) == (off < 0)
         if pos >= 0:
             perm[pos] = off
-    assert (perm >= 0).all() and len(set(perm.tolist())) == nt
+    real = np.setdiff1d(np.arange(nt), pad)
+    assert (perm[pad] < 0).all() and (perm[real] >= 0).all() and len(set(perm[real].tolist())) == len(real)
     return perm

@@ -120,23 +120,27 @@ def test_product_jacobian_matches_oracle(stage):
     op = ob.OracleProblem(pd)
     eo = op.evaluate(jacobian=True)
     eh = hc.evaluate(pd)
-    assert eh["layout"]["n_res"] == op.num_residuals and eh["layout"]["nt"] == op.num_tangent
+    assert eh["layout"]["n_res"] == op.num_residuals and eh["layout"]["nt"] - eh["layout"]["n_pad"] == op.num_tangent
     assert eh["cost"] == pytest.approx(eo["cost"], rel=1e-12) and eh["fixed_cost"] == pytest.approx(eo["fixed_cost"], rel=1e-12, abs=1e-9)
     assert np.abs(eh["residuals"] - eo["residuals"]).max() <= 1e-10 * max(1.0, np.abs(eo["residuals"]).max())
     perm = hc.perm_to_oracle(pd, eh["layout"], op)
-    Jo = eo["J"][:, perm]
-    assert np.abs(eh["J"] - Jo).max() <= 1e-9 * max(1.0, np.abs(Jo).max())
+    real = perm >= 0
+    Jo = eo["J"][:, perm[real]]
+    assert np.abs(eh["J"][:, real] - Jo).max() <= 1e-9 * max(1.0, np.abs(Jo).max())
+    assert not eh["J"][:, ~real].any()                      # padding positions carry nothing
 
 
 def test_layout_is_band_plus_arrow():
     pd = make_lvi_problem("surfel", 1.0, 300)
     lay = hc.layout(pd)
-    # arrow border = 4 map-time knots x 6 + lidar q,p (6) + gravity (2) + biases (6)
-    assert lay["nbo"] == 24 + 6 + 2 + 6
+    # arrow border = separator of the two-sided ordering (4 knots x 6) + 4 map-time knots x 6 + lidar q,p (6) + gravity (2) + biases (6)
+    assert lay["n_mid"] == 24 and lay["nbo"] - lay["n_mid"] == 24 + 6 + 2 + 6
     assert lay["bw"] == 23                      # 4 consecutive knots x 6 dims
+    assert lay["chain1_start"] % 32 == 0 and 0 < lay["chain1_start"] < lay["nb"] and lay["n_pad"] < 32
     pd4 = make_lvi_problem("lvi")
     l4 = hc.layout(pd4)
-    assert l4["nbo"] == 24 + 12 + 2 + 6 and l4["bw"] > 100   # camera residuals couple reference and observation windows
+    assert l4["nbo"] - l4["n_mid"] == 24 + 12 + 2 + 6 and l4["bw"] > 100   # camera residuals couple reference and observation windows
+    assert l4["n_mid"] == 0 and l4["chain1_start"] == l4["nb"]               # too short for a separator of ~100 knots: single chain
     pd5 = make_lvi_problem("lvi_locked", 1.0, 300)
     l5 = hc.layout(pd5)
     assert (l5["pos_r3"] < 0).all() and (l5["pos_so3"] < 0).all() and l5["bw"] == 0   # Q15: only camera, biases, gravity, rho move
