@@ -291,7 +291,8 @@ int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scan
  * [n x n] row-major symmetric positive definite, n = nb + nbo; within the first nb rows/cols entries with
  * |i-j| > bw must be zero.  Two-sided ordering: band positions [0, chain1_start) and [chain1_start, nb) are two
  * chains that must not couple directly (chain1_start a multiple of 32, == nb for one chain); the first n_mid
- * border dims are the separator, factored as a second-level system.  LVI_ERR_NUMERIC on Cholesky breakdown. */
+ * border dims are the separator (they may only couple to the last bw positions of each chain), factored as a
+ * second-level system.  LVI_ERR_NUMERIC on Cholesky breakdown. */
 int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start, int n_mid, const double* A_dense,
                          const double* rhs, double* x_out);
 

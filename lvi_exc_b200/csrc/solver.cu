@@ -268,13 +268,19 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     const bool band = s <= S.T;
     const int i = j + s;
     if (band && i >= c_end) continue;  // tile below the end of the chain: never referenced
+    // separator rows of the two-sided ordering couple only to the last <= bw positions of a chain: their border tiles are
+    // structurally zero (and stay zero in the factor) before block column sep_first, so those tasks and products are skipped
+    const int RBsep = S.n_mid >> kTileLog;                       // border tile rows made of separator dims only
+    const int sep_first = max(c_start, c_end - S.T - 1);
+    const bool sep_row = !band && (s - S.T - 1) < RBsep;
+    if (sep_row && j < sep_first) continue;
     const int tq = j * S.TPC + s;      // storage / flag index of this tile
     double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
     LVI_TRACE(0);
     double acc[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
-    const int kmin = max(c_start, band ? i - S.T : j - S.T);
+    const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
       const int fj = k * S.TPC + (j - k);
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
         for (int bi = 0; bi < S.RB; ++bi)
           for (int bj = 0; bj <= bi; ++bj) {
+            if (j < sep_first && bj < RBsep) continue;   // bj <= bi: a zero separator tile makes the product vanish
             const int fa = j * S.TPC + S.T + 1 + bi, fb = j * S.TPC + S.T + 1 + bj;
             if (tid == 0) { spin_until_set(flags + fa); spin_until_set(flags + fb); }
             __syncthreads();
@@ -409,7 +416,8 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
     // right-hand side minus the border part (independent of the chain): warps 0,1 own columns c = tid (< 64)
     if (tid < kTile) {
       double bsum = 0.0;
-      for (int rb = 0; rb < S.RB; ++rb) {
+      const int RBsep = S.n_mid >> kTileLog;
+      for (int rb = (m < max(c_start, c_end - S.T - 1)) ? RBsep : 0; rb < S.RB; ++rb) {   // zero separator tiles are skipped
         const double* bt = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems + kTile * tid;
         const double* xv = x2s + kTile * rb;
 #pragma unroll 8
@@ -986,7 +994,7 @@ int lvi_problem_layout(lvi_problem* p, int32_t* out) {
 int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start, int n_mid, const double* A_dense, const double* rhs, double* x_out) {
   return guarded([&] {
     LVI_REQUIRE(ctx && A_dense && rhs && x_out && nb >= 0 && nbo >= 0 && nb + nbo > 0, LVI_ERR_INVALID, "lvi_band_solve_dense: bad argument");
-    LVI_REQUIRE(chain1_start % kTile == 0 && chain1_start >= 0 && chain1_start <= nb && n_mid >= 0 && n_mid <= nbo, LVI_ERR_INVALID,
+    LVI_REQUIRE((chain1_start == nb || chain1_start % kTile == 0) && chain1_start >= 0 && chain1_start <= nb && n_mid >= 0 && n_mid <= nbo, LVI_ERR_INVALID,
                 "lvi_band_solve_dense: chain1_start must be a multiple of 32 in [0, nb], n_mid in [0, nbo]");
     LVI_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

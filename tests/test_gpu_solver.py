@@ -44,6 +44,10 @@ def test_two_sided_band_solver_matches_numpy(cuda_backend, n0, n1, nbo, n_mid, b
     A = _spd_band(rng, nb, nbo, bw)
     A[n0:nb, :n0] = 0.0
     A[:n0, n0:nb] = 0.0
+    # separator rows couple only to the last bw positions of each chain (that is what makes them a separator)
+    far = np.ones(nb, bool); far[max(0, n0 - bw):n0] = False; far[max(n0, nb - bw):nb] = False
+    A[nb:nb + n_mid, :nb][:, far] = 0.0
+    A[:nb, nb:nb + n_mid][far, :] = 0.0
     rhs = rng.standard_normal(nb + nbo)
     x = cuda_backend.band_solve_dense(A, rhs, nb, nbo, bw, chain1_start=n0, n_mid=n_mid)
     ref = np.linalg.solve(A, rhs)
