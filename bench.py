@@ -203,12 +203,18 @@ def main():
     clocks = sampler.stop() if sampler else None
     # ---- end to end through the C-ABI with host buffers (H2D of tables/parameters and D2H of the optimum inside the timed region)
     tol0 = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+    pw = CudaProblem(backend, pd)       # untimed warm-up of the host-buffer path (first-use costs of the solve loop's small kernels)
+    pw.solve(2, **tol0)
+    pw.close()
     pd.restore_params(saved)
     barrier()
     t0 = time.perf_counter()
     p2 = CudaProblem(backend, pd)
+    t_create = time.perf_counter()
     s = p2.solve(args.steps, **tol0)
+    t_solve = time.perf_counter()
     p2.close()
+    t_close = time.perf_counter()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_iters = max(1, s.num_iterations)
@@ -247,6 +253,7 @@ def main():
            "phases_ms": phases,
            "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
                    "iterations": e2e_iters, "wall_s": e2e_s,
+                   "host_s": {"create": t_create - t0, "solve": t_solve - t_create, "destroy": t_close - t_solve},
                    "solver_ms": {"total": s.time_total_ms, "jacobian": s.time_jacobian_ms, "linear_solve": s.time_linear_solve_ms}},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
            "map_path": info}

@@ -343,28 +343,34 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       __syncthreads();
       if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
       LVI_TRACE(7);
-      if (s == S.TPC - 1) {  // last border tile of column j: Schur complement of the arrow corner, C -= Lb(:,j) Lb(:,j)^T
-        for (int bi = 0; bi < S.RB; ++bi)
-          for (int bj = 0; bj <= bi; ++bj) {
-            if (j < sep_first && bj < RBsep) continue;   // bj <= bi: a zero separator tile makes the product vanish
-            const int fa = j * S.TPC + S.T + 1 + bi, fb = j * S.TPC + S.T + 1 + bj;
-            if (tid == 0) { spin_until_set(flags + fa); spin_until_set(flags + fb); }
-            __syncthreads();
-            const double* Xa = S.tiles + static_cast<size_t>(fa) * kTileElems;
-            const double* Xb = S.tiles + static_cast<size_t>(fb) * kTileElems;
-            for (int e = tid; e < kTileElems; e += kFacThreads) { sA[e] = __ldcg(Xa + e); sB[e] = __ldcg(Xb + e); }
-            __syncthreads();
-            double pr[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int m = 0; m < 32; ++m) {
-              const double xa = sA[a + 32 * m];
+      if (!band) {  // border tile rb of column j: its share of the corner's Schur complement, C(rb, bj) -= Lb(rb,j) Lb(bj,j)^T for bj <= rb
+        const int rb = s - S.T - 1;
+        __syncthreads();
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) pr[jj] = fma(xa, sB[c0 + 8 * jj + 32 * m], pr[jj]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (pr[jj] != 0.0) atomicAdd(S.C + 32 * bi + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
+        for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = out[jj];   // own finished tile stays in shared memory
+        for (int bj = 0; bj <= rb; ++bj) {
+          if (j < sep_first && bj < RBsep) continue;   // zero separator tile: the product vanishes
+          const double* Xb_s = sA;
+          if (bj < rb) {
+            const int fb = j * S.TPC + S.T + 1 + bj;
+            if (tid == 0) spin_until_set(flags + fb);
             __syncthreads();
+            const double2* Xb = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fb) * kTileElems);
+            for (int e = tid; e < kTileElems / 2; e += kFacThreads) reinterpret_cast<double2*>(sB)[e] = __ldcg(Xb + e);
+            Xb_s = sB;
           }
+          __syncthreads();
+          double pr[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int m = 0; m < 32; ++m) {
+            const double xa = sA[a + 32 * m];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) pr[jj] = fma(xa, Xb_s[c0 + 8 * jj + 32 * m], pr[jj]);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if (pr[jj] != 0.0) atomicAdd(S.C + 32 * rb + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
+          __syncthreads();
+        }
       }
     }
   }
