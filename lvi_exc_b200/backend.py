@@ -206,16 +206,15 @@ class CudaBackend:
         torch.cuda.synchronize(self.device)
         n_out, n_all = C.c_int64(0), C.c_int64(0)
         args = (self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H, radius, k, step)
-        check(self.lib.lvi_associate_d(*args, None, 0, C.byref(n_out), C.byref(n_all)))
+        cap = (S * H * W) // step + 1      # every emitted point is a scan point: one pass with a worst-case buffer instead of a sizing pass
+        od = torch.empty(cap * 64, dtype=torch.uint8, device=m.device)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.lvi_associate_d(*args, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
         n = n_out.value
         self.last_n_all = n_all.value
         out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
-        if n == 0:
-            return out
-        od = torch.empty(n * 64, dtype=torch.uint8, device=m.device)
-        torch.cuda.synchronize(self.device)
-        check(self.lib.lvi_associate_d(*args, C.c_void_p(od.data_ptr()), n, C.byref(n_out), C.byref(n_all)))
-        out[:] = od.cpu().numpy().view(SURFEL_POINT_DTYPE)
+        if n:
+            out[:] = od[:n * 64].cpu().numpy().view(SURFEL_POINT_DTYPE)
         return out
 
     def transform(self, scans_xyzi, poses):

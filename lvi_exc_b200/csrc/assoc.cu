@@ -7,8 +7,8 @@
 // voxel lookup per point with identical results (tests/test_oracle_map.py proves the equivalence on the oracle).
 //   1. assoc_hit_kernel    : per point — voxel index (same float arithmetic as the map build) -> plane -> strict bbox test
 //                            + |n.x+d| <= radius in fp64.  Streams 12 of every 32 input bytes; HBM-bound.
-//   2. assoc_select_kernel : one CTA per (scan, ring) — bitonic sort of (plane, column) keys in shared memory, per-plane
-//                            hit lists -> picks hits[step*(s+1)-1], step = max(hits/(k+1),1), if hits >= 2k (:127-136)
+//   2. assoc_select_kernel : one warp per (scan, ring) — rank of every hit inside its plane's hit list (match_any + a per-warp hash
+//                            table of running counts) -> picks hits[step*(s+1)-1], step = max(hits/(k+1),1), if hits >= 2k (:127-136)
 //   3. exclusive scan over the reference's emission order (scan, w outer, h inner, timestamp != 0, :139-158), then every
 //      `time_step`-th emitted point is gathered into a SurfelPoint record (:240-244).
 // Compiled with -fmad=false (bit-exact index selection).
@@ -72,61 +72,89 @@ __global__ void __launch_bounds__(256) assoc_hit_kernel(const char* __restrict__
   }
 }
 
-// One CTA per (scan, ring). cand: [n_scans][H][W]; sel (emission order): [n_scans][W][H]
-template <int CAP>
-__global__ void __launch_bounds__(256) assoc_select_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw, int W, int H,
-                                                           int k_per_ring, int32_t* __restrict__ sel) {
-  __shared__ unsigned long long key[CAP];
-  __shared__ int seg_start[CAP];
-  const int scan = blockIdx.x / H, h = blockIdx.x % H;
+// One WARP per (scan, ring). cand: [n_scans][H][W]; sel (emission order): [n_scans][W][H].
+// The reference collects, per plane, the hit columns of the ring in ascending order and picks hits[step*(s+1)-1] (:127-136).  Hits
+// arrive in column order already, so a hit only needs its RANK among the hits of its plane and the plane's total: pass 1 ranks the
+// hits 32 columns at a time (__match_any_sync groups equal planes, a small per-warp hash table in shared memory carries the running
+// count per plane) and parks the rank in `sel`; pass 2 keeps the hits whose rank is one of the k selected ones.  No sort: the first
+// version bitonic-sorted 2048 (plane, column) keys per ring and was the slowest kernel of the map path (0.94 ms at 17 M points).
+constexpr int kSelHash = 256;   // distinct planes per ring are far fewer (a ring crosses a 0.5 m voxel a handful of times)
+constexpr int kSelWarps = 8;
+
+__device__ __forceinline__ int sel_hash_slot(int* hkey, int plane) {  // find-or-insert with linear probing; one lane at a time
+  unsigned h = (static_cast<unsigned>(plane) * 2654435761u) >> 24;    // 8 bits
+  for (int probe = 0; probe < kSelHash; ++probe) {
+    const int sl = (h + probe) & (kSelHash - 1);
+    const int k = hkey[sl];
+    if (k == plane) return sl;
+    if (k == -1) { hkey[sl] = plane; return sl; }
+  }
+  return -1;  // table full: cannot happen for W <= 4096 with 256 slots unless > 256 distinct planes hit one ring
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw, int n_rings,
+                                                                       int W, int H, int k_per_ring, int32_t* __restrict__ sel, int* __restrict__ overflow) {
+  __shared__ int hkey[kSelWarps][kSelHash], hcnt[kSelWarps][kSelHash];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const int ring = blockIdx.x * kSelWarps + warp;
+  if (ring >= n_rings) return;
+  const int scan = ring / H, h = ring % H;
+  int* hk = hkey[warp]; int* hc = hcnt[warp];
+  for (int i = lane; i < kSelHash; i += 32) { hk[i] = -1; hc[i] = 0; }
+  __syncwarp();
   const int32_t* row = cand + (static_cast<int64_t>(scan) * H + h) * W;
   int32_t* selrow = sel + static_cast<int64_t>(scan) * W * H + h;  // + w*H
-  for (int w = threadIdx.x; w < CAP; w += blockDim.x) {
-    unsigned long long kk = ~0ull;
-    if (w < W) {
-      const int c = row[w];
-      if (c >= 0) kk = (static_cast<unsigned long long>(static_cast<uint32_t>(c)) << 32) | static_cast<uint32_t>(w);
-      selrow[static_cast<int64_t>(w) * H] = -1;
-    }
-    key[w] = kk;
-  }
-  __syncthreads();
-  // bitonic sort ascending
-  for (int size = 2; size <= CAP; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < CAP / 2; t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const unsigned long long a = key[lo], b = key[hi];
-        if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+  // pass 1: rank of every hit among the hits of its plane
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    const int c = w < W ? row[w] : -1;
+    const unsigned hits = __ballot_sync(FULL, c >= 0);
+    int rank = -1;
+    if (c >= 0) {
+      const unsigned grp = __match_any_sync(hits, c);
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      // leaders update the table one after another (usually 1-3 distinct planes per 32 columns)
+      unsigned leaders = __ballot_sync(hits, lane == leader);
+      while (leaders) {
+        const int l = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        if (lane == l) {
+          const int sl = sel_hash_slot(hk, c);
+          if (sl < 0) { atomicExch(overflow, 1); base = 0; }
+          else { base = hc[sl]; hc[sl] = base + __popc(grp); }
+        }
+        __syncwarp(hits);
       }
-      __syncthreads();
+      base = __shfl_sync(grp, base, leader);
+      rank = base + __popc(grp & ((1u << lane) - 1));
     }
-  // segment heads
-  for (int i = threadIdx.x; i < CAP; i += blockDim.x) {
-    const unsigned long long kk = key[i];
-    int head = 0;
-    if (kk != ~0ull) head = (i == 0) || ((key[i - 1] >> 32) != (kk >> 32));
-    seg_start[i] = head ? i : -1;
+    if (w < W) selrow[static_cast<int64_t>(w) * H] = rank;
   }
-  __syncthreads();
-  // each segment head walks to its end (segments are short runs of one plane) and marks the selected hits
-  for (int i = threadIdx.x; i < CAP; i += blockDim.x) {
-    if (seg_start[i] != i) continue;
-    const unsigned long long pl = key[i] >> 32;
-    int e = i + 1;
-    while (e < CAP && key[e] != ~0ull && (key[e] >> 32) == pl) ++e;
-    const int hits = e - i;
-    if (hits < k_per_ring * 2) continue;  // :128
-    int step = hits / (k_per_ring + 1);   // :130-131
-    step = step > 1 ? step : 1;
-    for (int s = 0; s < k_per_ring; ++s) {
-      const int w = static_cast<int>(key[i + step * (s + 1) - 1] & 0xffffffffu);
-      // emission filter: timestamp == 0 points are never emitted (:141-143)
-      const double ts = raw[(static_cast<int64_t>(scan) * H + h) * W + w].timestamp;
-      selrow[static_cast<int64_t>(w) * H] = (ts == 0.0) ? -1 : static_cast<int32_t>(pl);
+  __syncwarp();
+  // pass 2: keep hits[step*(s+1)-1], s < k, of planes with >= 2k hits (:128-136); timestamp == 0 points are never emitted (:141-143)
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    if (w >= W) continue;
+    const int c = row[w];
+    int out = -1;
+    if (c >= 0) {
+      const int rank = selrow[static_cast<int64_t>(w) * H];
+      unsigned hsh = (static_cast<unsigned>(c) * 2654435761u) >> 24;
+      int total = 0;
+      for (int probe = 0; probe < kSelHash; ++probe) { const int sl = (hsh + probe) & (kSelHash - 1); if (hk[sl] == c) { total = hc[sl]; break; } if (hk[sl] == -1) break; }
+      if (total >= k_per_ring * 2) {
+        int step = total / (k_per_ring + 1);
+        step = step > 1 ? step : 1;
+        const int r1 = rank + 1;
+        if (r1 % step == 0 && r1 / step >= 1 && r1 / step <= k_per_ring) {
+          const double ts = raw[(static_cast<int64_t>(scan) * H + h) * W + w].timestamp;
+          if (ts != 0.0) out = c;
+        }
+      }
     }
+    selrow[static_cast<int64_t>(w) * H] = out;
   }
 }
 
@@ -197,18 +225,22 @@ static void associate_device(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_sur
   LVI_LAUNCH(ctx, assoc_hit_kernel, grid_for(n, 256, ctx->sm_count, 8), 256, 0, static_cast<const char*>(map_d), stride, n, m->grid_d.p,
              m->cell2leaf.n ? m->cell2leaf.p : nullptr, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p, s->p4.p, s->bmin.p, s->bmax.p,
              radius, cand.p);
-  if (W <= 2048) LVI_LAUNCH(ctx, assoc_select_kernel<2048>, n_scans * H, 256, 0, cand.p, raw_d, W, H, k, sel.p);
-  else LVI_LAUNCH(ctx, assoc_select_kernel<4096>, n_scans * H, 256, 0, cand.p, raw_d, W, H, k, sel.p);
+  DBuf<int> overflow(1);
+  overflow.zero(st);
+  const int n_rings = n_scans * H;
+  LVI_LAUNCH(ctx, assoc_select_kernel, (n_rings + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, cand.p, raw_d, n_rings, W, H, k, sel.p, overflow.p);
   LVI_LAUNCH(ctx, assoc_flag_kernel, grid_for(n, 256, ctx->sm_count, 8), 256, 0, sel.p, n, flag.p);
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, static_cast<int>(n), st);
   DBuf<char> tmp(tb + 16);
   LVI_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, rank.p, static_cast<int>(n), st));
   ctx->launches += 2;
-  int last_rank = 0, last_flag = 0;
+  int last_rank = 0, last_flag = 0, h_overflow = 0;
+  LVI_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, 4, cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaMemcpyAsync(&last_rank, rank.p + n - 1, 4, cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaMemcpyAsync(&last_flag, flag.p + n - 1, 4, cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaStreamSynchronize(st));
+  LVI_REQUIRE(h_overflow == 0, LVI_ERR_INVALID, "lvi_associate: more than 256 distinct surfels hit by one ring (not supported)");
   const int64_t total = static_cast<int64_t>(last_rank) + last_flag;
   if (n_all) *n_all = total;
   if (n_out) *n_out = (total + time_step - 1) / time_step;

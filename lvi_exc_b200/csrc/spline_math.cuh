@@ -218,6 +218,17 @@ LVI_HD void so3_spline_eval(const double* cps /*16*/, double u, double dt_inv, b
   if (want_w) { e.N[0] = -1.0 * Nj[1]; e.N[1] = Nj[1] - Nj[2]; e.N[2] = Nj[2] - Nj[3]; e.N[3] = Nj[3]; }
 }
 
+// Orientation only, with the knot-to-knot half-angle logs h_j = logq_half(q_{j-1}^-1 q_j) precomputed once per knot (they do not
+// depend on t): q(u) = q_i0 * prod_{j=1..3} expq_half(B~_j(u) h_{i0+j}).  Used by the per-point pose queries of the map path.
+LVI_HD Q4 so3_orientation_pre(const double* q_i0 /*4*/, const double* hlog /*3 x 3: h_{i0+1..i0+3}*/, double u) {
+  double B[4];
+  basis_cumul(u, B);
+  Q4 q = q4(q_i0[0], q_i0[1], q_i0[2], q_i0[3]);
+#pragma unroll
+  for (int j = 1; j < 4; ++j) q = qmul(q, expq_half(B[j] * v3(hlog[3 * (j - 1)], hlog[3 * (j - 1) + 1], hlog[3 * (j - 1) + 2])));
+  return q;
+}
+
 LVI_HD V3 r3_spline(const double* cps /*12*/, const double B[4]) {
   return v3(B[0] * cps[0] + B[1] * cps[3] + B[2] * cps[6] + B[3] * cps[9], B[0] * cps[1] + B[1] * cps[4] + B[2] * cps[7] + B[3] * cps[10],
             B[0] * cps[2] + B[1] * cps[5] + B[2] * cps[8] + B[3] * cps[11]);

@@ -3,7 +3,7 @@
 // Replaces SurfelAssociation::setSurfelMap / checkPlaneType / fitPlane (L/src/core/surfel_association.cpp:50-108,246-294)
 // which loops serially over the std::map, copies every leaf cloud twice and runs pcl::SACSegmentation per leaf.
 //   1. surfel_candidate_kernel : thread per leaf — nr_points >= 10 and planarity 2(l1-l2)/(l0+l1+l2) >= lambda (Lv et al. eq. 13)
-//   2. surfel_fit_kernel       : one warp per candidate leaf — RANSAC plane (50 iterations max, p = 0.99 adaptive stop,
+//   2. surfel_fit_kernel       : one CTA per candidate leaf — RANSAC plane (50 iterations max, p = 0.99 adaptive stop,
 //                                |n.x+d| < thr inlier test), PCA refinement over the inliers, inlier re-selection, bbox
 //   3. compaction in leaf order -> plane_id = position in ascending voxel-index order (reference: push_back order)
 // Leaf points are contiguous float4 in HBM (voxel.cu), so every RANSAC pass is a coalesced stream.
@@ -86,14 +86,50 @@ __device__ __forceinline__ bool model_from3(const float4 p0, const float4 p1, co
 
 struct FitOut { double p4[4]; double bmin[3], bmax[3]; int ninl; int ok; };
 
-// One warp per candidate leaf.
-__global__ void __launch_bounds__(128) surfel_fit_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start,
-                                                         const int32_t* __restrict__ leaf_key, const int32_t* __restrict__ cand, int n_cand,
-                                                         float thr, int min_inliers, FitOut* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const unsigned FULL = 0xffffffffu;
-  for (int ci = blockIdx.x * wpb + (threadIdx.x >> 5); ci < n_cand; ci += gridDim.x * wpb) {
+// One CTA (128 threads) per candidate leaf: a leaf of the room scene holds ~10^4 points and RANSAC makes up to 50 passes over them,
+// so one warp per leaf (the first version) left the kernel latency-bound at 5 % of the warp slots.
+constexpr int kFitThreads = 128;
+__device__ __forceinline__ int block_sum_int(int v, int* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return sh[0] + sh[1] + sh[2] + sh[3];
+}
+__device__ __forceinline__ unsigned block_min_uint(unsigned v, unsigned* sh) {
+  v = __reduce_min_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return min(min(sh[0], sh[1]), min(sh[2], sh[3]));
+}
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+__device__ __forceinline__ float block_min_float(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fminf(fminf(sh[0], sh[1]), fminf(sh[2], sh[3]));
+}
+
+__global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start,
+                                                                 const int32_t* __restrict__ leaf_key, const int32_t* __restrict__ cand, int n_cand,
+                                                                 float thr, int min_inliers, FitOut* __restrict__ out) {
+  __shared__ int shi[4];
+  __shared__ unsigned shu[4];
+  __shared__ double shd[4];
+  __shared__ float shf[4];
+  const int tid = threadIdx.x;
+  for (int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {
     const int leaf = cand[ci];
     const int beg = leaf_start[leaf];
     const uint32_t n = static_cast<uint32_t>(leaf_start[leaf + 1] - beg);
@@ -105,7 +141,7 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const float4* __restric
     bool fail = n < 3;
     float best[4] = {0, 0, 0, 0};
     int best_count = 0;
-    if (!fail) {
+    if (!fail) {  // every thread runs the same (uniform) RANSAC control flow; only the inlier counting is split
       const int max_iterations = 50;
       const double log_probability = log(1.0 - 0.99);
       const double one_over_n = 1.0 / static_cast<double>(n);
@@ -126,8 +162,8 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const float4* __restric
         float coef[4];
         if (!model_from3(__ldg(P + a), __ldg(P + b), __ldg(P + c), coef)) { ++skipped; continue; }
         int count = 0;
-        for (uint32_t i = lane; i < n; i += 32) count += plane_dist(coef, __ldg(P + i)) < thr ? 1 : 0;
-        count = __reduce_add_sync(FULL, count);
+        for (uint32_t i = tid; i < n; i += kFitThreads) count += plane_dist(coef, __ldg(P + i)) < thr ? 1 : 0;
+        count = block_sum_int(count, shi);
         if (count > best_count) {
           best_count = count;
           best[0] = coef[0]; best[1] = coef[1]; best[2] = coef[2]; best[3] = coef[3];
@@ -146,33 +182,29 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const float4* __restric
     if (!fail && best_count > 3) {
       // first inlier in leaf order defines the local origin of the PCA sums
       uint32_t first = 0xffffffffu;
-      for (uint32_t i = lane; i < n && first == 0xffffffffu; i += 32) if (plane_dist(best, __ldg(P + i)) < thr) first = i;
-      first = __reduce_min_sync(FULL, first);
+      for (uint32_t i = tid; i < n && first == 0xffffffffu; i += kFitThreads) if (plane_dist(best, __ldg(P + i)) < thr) first = i;
+      first = block_min_uint(first, shu);
       const float4 p0 = __ldg(P + first);
       const double x0 = p0.x, y0 = p0.y, z0 = p0.z;
-      double s0 = 0, s1 = 0, s2 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0;
+      double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       int cnt = 0;
-      for (uint32_t i = lane; i < n; i += 32) {
+      for (uint32_t i = tid; i < n; i += kFitThreads) {
         const float4 p = __ldg(P + i);
         if (!(plane_dist(best, p) < thr)) continue;
         const double dx = static_cast<double>(p.x) - x0, dy = static_cast<double>(p.y) - y0, dz = static_cast<double>(p.z) - z0;
-        s0 += dx; s1 += dy; s2 += dz;
-        q0 += dx * dx; q1 += dx * dy; q2 += dx * dz; q3 += dy * dy; q4 += dy * dz; q5 += dz * dz;
+        sums[0] += dx; sums[1] += dy; sums[2] += dz;
+        sums[3] += dx * dx; sums[4] += dx * dy; sums[5] += dx * dz; sums[6] += dy * dy; sums[7] += dy * dz; sums[8] += dz * dz;
         ++cnt;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(FULL, s0, o); s1 += __shfl_xor_sync(FULL, s1, o); s2 += __shfl_xor_sync(FULL, s2, o);
-        q0 += __shfl_xor_sync(FULL, q0, o); q1 += __shfl_xor_sync(FULL, q1, o); q2 += __shfl_xor_sync(FULL, q2, o);
-        q3 += __shfl_xor_sync(FULL, q3, o); q4 += __shfl_xor_sync(FULL, q4, o); q5 += __shfl_xor_sync(FULL, q5, o);
-      }
-      cnt = __reduce_add_sync(FULL, cnt);
+      for (int q = 0; q < 9; ++q) sums[q] = block_sum_double(sums[q], shd);
+      cnt = block_sum_int(cnt, shi);
       const double inv_n = 1.0 / cnt;
-      const double m0 = s0 * inv_n, m1 = s1 * inv_n, m2 = s2 * inv_n;
+      const double m0 = sums[0] * inv_n, m1 = sums[1] * inv_n, m2 = sums[2] * inv_n;
       const float cf0 = static_cast<float>(x0 + m0), cf1 = static_cast<float>(y0 + m1), cf2 = static_cast<float>(z0 + m2);
-      const float cv0 = static_cast<float>(q0 * inv_n - m0 * m0), cv1 = static_cast<float>(q1 * inv_n - m0 * m1),
-                  cv2 = static_cast<float>(q2 * inv_n - m0 * m2), cv3 = static_cast<float>(q3 * inv_n - m1 * m1),
-                  cv4 = static_cast<float>(q4 * inv_n - m1 * m2), cv5 = static_cast<float>(q5 * inv_n - m2 * m2);
+      const float cv0 = static_cast<float>(sums[3] * inv_n - m0 * m0), cv1 = static_cast<float>(sums[4] * inv_n - m0 * m1),
+                  cv2 = static_cast<float>(sums[5] * inv_n - m0 * m2), cv3 = static_cast<float>(sums[6] * inv_n - m1 * m1),
+                  cv4 = static_cast<float>(sums[7] * inv_n - m1 * m2), cv5 = static_cast<float>(sums[8] * inv_n - m2 * m2);
       const double A[9] = {cv0, cv1, cv2, cv1, cv3, cv4, cv2, cv4, cv5};
       double ev[3], V[9];
       jacobi3_lower(A, ev, V);
@@ -186,24 +218,22 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const float4* __restric
     if (!fail) {
       int cnt2 = 0;
       float mn0 = 3.402823466e38f, mn1 = mn0, mn2 = mn0, mx0 = -mn0, mx1 = -mn0, mx2 = -mn0;
-      for (uint32_t i = lane; i < n; i += 32) {
+      for (uint32_t i = tid; i < n; i += kFitThreads) {
         const float4 p = __ldg(P + i);
         cnt2 += plane_dist(fin, p) < thr ? 1 : 0;
         mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
         mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
       }
-      cnt2 = __reduce_add_sync(FULL, cnt2);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn0 = fminf(mn0, __shfl_xor_sync(FULL, mn0, o)); mn1 = fminf(mn1, __shfl_xor_sync(FULL, mn1, o)); mn2 = fminf(mn2, __shfl_xor_sync(FULL, mn2, o));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(FULL, mx0, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL, mx1, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(FULL, mx2, o));
-      }
+      cnt2 = block_sum_int(cnt2, shi);
+      mn0 = block_min_float(mn0, shf); mn1 = block_min_float(mn1, shf); mn2 = block_min_float(mn2, shf);
+      mx0 = -block_min_float(-mx0, shf); mx1 = -block_min_float(-mx1, shf); mx2 = -block_min_float(-mx2, shf);
       fo.ninl = cnt2;
       fo.ok = cnt2 >= min_inliers;  // surfel_association.cpp:284
       for (int k = 0; k < 4; ++k) fo.p4[k] = fin[k];
       fo.bmin[0] = mn0; fo.bmin[1] = mn1; fo.bmin[2] = mn2; fo.bmax[0] = mx0; fo.bmax[1] = mx1; fo.bmax[2] = mx2;  // getMinMax3D :82
     }
-    if (lane == 0) out[ci] = fo;
+    if (tid == 0) out[ci] = fo;
+    __syncthreads();
   }
 }
 
@@ -268,7 +298,7 @@ int lvi_surfel_extract(lvi_ctx* ctx, const lvi_voxel_map* m, double lambda, int 
     DBuf<int32_t> cand(n_cand);
     LVI_LAUNCH(ctx, surfel_scatter_ids_kernel, (L + 255) / 256, 256, 0, flag.p, pos.p, L, cand.p);
     DBuf<FitOut> fit(n_cand);
-    LVI_LAUNCH(ctx, surfel_fit_kernel, grid_for(static_cast<int64_t>(n_cand) * 32, 128, ctx->sm_count, 16), 128, 0, m->pts_sorted.p, m->leaf_start.p,
+    LVI_LAUNCH(ctx, surfel_fit_kernel, std::min(n_cand, ctx->sm_count * 16), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
                m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, fit.p);
     DBuf<int32_t> okf(n_cand), okpos(n_cand);
     LVI_LAUNCH(ctx, surfel_flag_ok_kernel, (n_cand + 255) / 256, 256, 0, fit.p, n_cand, okf.p);

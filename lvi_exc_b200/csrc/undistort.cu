@@ -19,8 +19,21 @@ struct TrajView {
   int n_knots;
   const double* r3;   // [n*3]
   const double* so3;  // [n*4]
+  const double* hlog; // [n*3] half-angle log of q_{i-1}^-1 q_i per knot (so3_log_kernel), row 0 unused
   Q4 qL; V3 pL;
 };
+
+// knot-to-knot logs once per trajectory instead of three atan2/sqrt chains per point
+__global__ void so3_log_kernel(const double* __restrict__ so3, int n, double* __restrict__ hlog) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V3 h = v3(0, 0, 0);
+  if (i >= 1) {
+    const Q4 a = q4(so3[4 * i - 4], so3[4 * i - 3], so3[4 * i - 2], so3[4 * i - 1]), b = q4(so3[4 * i], so3[4 * i + 1], so3[4 * i + 2], so3[4 * i + 3]);
+    h = logq_half(qmul(qconj(a), b));
+  }
+  hlog[3 * i] = h.x; hlog[3 * i + 1] = h.y; hlog[3 * i + 2] = h.z;
+}
 
 __device__ __forceinline__ bool lidar_pose(const TrajView& T, double t, Q4& q, V3& p) {
   const double tt = t + T.toff;
@@ -29,13 +42,12 @@ __device__ __forceinline__ bool lidar_pose(const TrajView& T, double t, Q4& q, V
   int i0 = static_cast<int>(floor(s));
   if (i0 < 0 || i0 > T.n_knots - 4) return false;
   const double u = s - i0;
-  So3Eval e;
-  so3_spline_eval(T.so3 + 4 * i0, u, T.dt_inv, false, false, e);
+  const Q4 qI = so3_orientation_pre(T.so3 + 4 * i0, T.hlog + 3 * (i0 + 1), u);
   double B[4];
   basis_pos(u, B);
   const V3 pI = r3_spline(T.r3 + 3 * i0, B);
-  q = qmul(e.q, T.qL);                 // q_LtoG = q_ItoG * q_LtoI
-  p = qrot(e.q, T.pL) + pI;            // p_LinG = q_ItoG * p_LinI + p_IinG
+  q = qmul(qI, T.qL);                  // q_LtoG = q_ItoG * q_LtoI
+  p = qrot(qI, T.pL) + pI;             // p_LinG = q_ItoG * p_LinI + p_IinG
   return true;
 }
 
@@ -120,7 +132,9 @@ static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_
   r3.upload(d->r3_knots, r3.n, st); so3.upload(d->so3_knots, so3.n, st); tt.upload(target_time_h, n_scans, st);
   TrajView T;
   T.t0 = d->t0; T.dt = d->dt; T.dt_inv = 1.0 / d->dt; T.t_max = d->t0 + (n - 3) * d->dt; T.toff = d->lidar_toff; T.n_knots = n;
-  T.r3 = r3.p; T.so3 = so3.p;
+  DBuf<double> hlog(3 * static_cast<size_t>(n));
+  LVI_LAUNCH(ctx, so3_log_kernel, (n + 127) / 128, 128, 0, so3.p, n, hlog.p);
+  T.r3 = r3.p; T.so3 = so3.p; T.hlog = hlog.p;
   static const double ident[4] = {0, 0, 0, 1}, zero[3] = {0, 0, 0};
   const double* lq = d->lidar_q ? d->lidar_q : ident; const double* lp = d->lidar_p ? d->lidar_p : zero;
   T.qL = q4(lq[0], lq[1], lq[2], lq[3]); T.pL = v3(lp[0], lp[1], lp[2]);
@@ -192,7 +206,9 @@ int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const doubl
     r3.upload(d->r3_knots, r3.n, st); so3.upload(d->so3_knots, so3.n, st); td.upload(t, n, st);
     TrajView T;
     T.t0 = d->t0; T.dt = d->dt; T.dt_inv = 1.0 / d->dt; T.t_max = d->t0 + (nk - 3) * d->dt; T.toff = 0.0; T.n_knots = nk;
-    T.r3 = r3.p; T.so3 = so3.p; T.qL = q4(0, 0, 0, 1); T.pL = v3(0, 0, 0);
+    DBuf<double> hlog(3 * static_cast<size_t>(nk));
+    LVI_LAUNCH(ctx, so3_log_kernel, (nk + 127) / 128, 128, 0, so3.p, nk, hlog.p);
+    T.r3 = r3.p; T.so3 = so3.p; T.hlog = hlog.p; T.qL = q4(0, 0, 0, 1); T.pL = v3(0, 0, 0);
     LVI_LAUNCH(ctx, traj_eval_kernel, static_cast<int>((n + 127) / 128), 128, 0, T, td.p, n, pd.p, qd.p, vd.p);
     pd.download(pos, pd.n, st); qd.download(quat, qd.n, st); vd.download(valid, n, st);
     LVI_CUDA(cudaStreamSynchronize(st));
