@@ -25,6 +25,22 @@ template <int TYPE> struct RTr {
 
 constexpr int kLinWarps = 2;
 
+// (c1, c2), c1 >= c2, of the p-th column pair in row-major triangular order, packed c1 << 8 | c2.  One table serves every residual type:
+// the pairs of an n-column block are the first n(n+1)/2 entries.  (Decoding p with sqrtf + fix-up loops cost ~25 of the ~60 instructions
+// per accumulated pair.)
+constexpr int kMaxPairs = LVI_MAX_COLS * (LVI_MAX_COLS + 1) / 2;
+__device__ unsigned short g_pair_table[kMaxPairs];
+static void ensure_pair_table() {
+  static bool done = false;
+  if (done) return;
+  std::vector<unsigned short> h(kMaxPairs);
+  int p = 0;
+  for (int c1 = 0; c1 < LVI_MAX_COLS; ++c1)
+    for (int c2 = 0; c2 <= c1; ++c2) h[p++] = static_cast<unsigned short>(c1 << 8 | c2);
+  LVI_CUDA(cudaMemcpyToSymbol(g_pair_table, h.data(), sizeof(unsigned short) * kMaxPairs));
+  done = true;
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P, BandSys H, SchurView SV, double* __restrict__ g, double* __restrict__ cost) {
   constexpr int ROWS = RTr<TYPE>::rows, COLS = RTr<TYPE>::cols, RC = ROWS * COLS, SC = RTr<TYPE>::shared_cols;
@@ -74,10 +90,8 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
       __syncwarp();
       constexpr int NP = SC * (SC + 1) / 2;
       for (int p = lane; p < NP; p += 32) {
-        int c1 = static_cast<int>((sqrtf(8.f * p + 1.f) - 1.f) * 0.5f);
-        while (c1 * (c1 + 1) / 2 > p) --c1;
-        while ((c1 + 1) * (c1 + 2) / 2 <= p) ++c1;
-        const int c2 = p - c1 * (c1 + 1) / 2;
+        const int pc = g_pair_table[p];
+        const int c1 = pc >> 8, c2 = pc & 255;
         const int p1 = posw[c1], p2 = posw[c2];
         if (p1 < 0 || p2 < 0) continue;
         double acc = 0.0;
@@ -187,6 +201,7 @@ template <int TYPE>
 static void launch_linearize(lvi_problem* p) {
   const ResTable& T = p->view.tab[TYPE];
   if (T.n == 0 || !T.active) return;
+  ensure_pair_table();
   static bool attr_set = false;
   const size_t smem = static_cast<size_t>(kLinWarps) * RTr<TYPE>::warp_doubles * sizeof(double);
   if (!attr_set) {

@@ -124,18 +124,23 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(BandSys A, SchurVi
   const int rhs_row = A.nb + A.nbo;
   for (int i = threadIdx.x; i < len; i += blockDim.x)
     if (hp[i] >= 0 && hv[i] != 0.0) atomicAdd(band_addr(A, rhs_row, hp[i]), -hv[i] * br * dinv);
-  const int np = len * (len + 1) / 2;
-  for (int q = threadIdx.x; q < np; q += blockDim.x) {
-    int i = static_cast<int>((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
-    while (i * (i + 1) / 2 > q) --i;
-    while ((i + 1) * (i + 2) / 2 <= q) ++i;
-    const int j = q - i * (i + 1) / 2;
-    const int pi = hp[i], pj = hp[j];
-    if (pi < 0 || pj < 0) continue;
-    double v = hv[i] * hv[j] * dinv;
-    if (v == 0.0) continue;
-    if (i != j && pi == pj) v += v;
-    atomicAdd(band_addr(A, max(pi, pj), min(pi, pj)), -v);
+  // rows i and len-1-i together hold len+1 pairs: every thread gets the same amount of work and no index decoding is needed
+  for (int r = threadIdx.x; 2 * r < len; r += blockDim.x) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int i = half == 0 ? r : len - 1 - r;
+      if (half == 1 && i == r) break;
+      const int pi = hp[i];
+      const double hi = hv[i] * dinv;
+      if (pi < 0 || hi == 0.0) continue;
+      for (int j = 0; j <= i; ++j) {
+        const int pj = hp[j];
+        double v = hi * hv[j];
+        if (pj < 0 || v == 0.0) continue;
+        if (i != j && pi == pj) v += v;
+        atomicAdd(band_addr(A, max(pi, pj), min(pi, pj)), -v);
+      }
+    }
   }
 }
 
@@ -176,18 +181,25 @@ __device__ __noinline__ bool warp_potrf_inv(const double* tile, int ld, double* 
   for (int c = 0; c < 32; ++c) A[c] = tile[a + ld * c];
   bool bad = false;
   double rinv = 0.0;
+  double d = __shfl_sync(FULL, A[0], 0);
+  if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+  double ri = rsqrt(d);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    double d = __shfl_sync(FULL, A[j], j);
-    if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-    const double ri = rsqrt(d);
     const double l = A[j] * ri;  // row j: d / sqrt(d) = sqrt(d)
     A[j] = l;
     if (a == j) rinv = ri;
     sCol[a] = l;
+    if (j < 31) {  // software pipeline: the next pivot only needs column j+1, so its rsqrt overlaps the rest of this rank-1 update
+      const double lc1 = __shfl_sync(FULL, l, j + 1);
+      A[j + 1] = fma(-l, lc1, A[j + 1]);
+      d = __shfl_sync(FULL, A[j + 1], j + 1);
+      if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+      ri = rsqrt(d);
+    }
     __syncwarp();
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) A[c] = fma(-l, sCol[c], A[c]);
+    for (int c = j + 2; c < 32; ++c) A[c] = fma(-l, sCol[c], A[c]);
     __syncwarp();
   }
 #pragma unroll
