@@ -239,8 +239,11 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(tq) * 8 + (slot)] = gtime(); } while (0)
-__device__ __forceinline__ void spin_until_set(const int* f) {
-  while (ld_acquire(f) == 0) {}
+// Tasks on the pivot chain (diagonal tile and first sub-diagonal tile) poll tightly; every other task backs off between polls so that the
+// CTAs that merely wait do not steal issue slots and L2 bandwidth from the ones that work (two CTAs share an SM).
+__device__ __forceinline__ void spin_until_set(const int* f, bool critical = true) {
+  if (critical) { while (ld_acquire(f) == 0) {} }
+  else { while (ld_acquire(f) == 0) __nanosleep(400); }
 }
 
 // issue order of the block columns: the two chains of the two-sided ordering are interleaved so that both advance together
@@ -259,7 +262,7 @@ __device__ __forceinline__ int ordered_column_desc(int p, int NT0, int NT) {
 constexpr int kFacThreads = 256;
 static_assert(kTile == 32, "band_factor_ll_kernel is written for 32x32 tiles (4 outputs per thread)");
 
-__global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys S) {
+__global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys S) {
   __shared__ __align__(16) double sA[kTileElems], sB[kTileElems];
   __shared__ double sM[32 * kLP], sW[32 * kLP], sR[32];
   __shared__ int s_q;
@@ -296,8 +299,8 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
       const int fj = k * S.TPC + (j - k);
-      if (tid == 0) spin_until_set(flags + fi);
-      if (tid == 32 && fj != fi) spin_until_set(flags + fj);
+      if (tid == 0) spin_until_set(flags + fi, s <= 1);
+      if (tid == 32 && fj != fi) spin_until_set(flags + fj, s <= 1);
       __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
       if (k == j - 1) LVI_TRACE(1);
       const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
       if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
       LVI_TRACE(7);
     } else {       // panel task: X = P W_j^T
-      if (tid == 0) spin_until_set(flags + j * S.TPC);
+      if (tid == 0) spin_until_set(flags + j * S.TPC, s <= 1);
       __syncthreads();
       LVI_TRACE(4);
       const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kFacThreads, 1) band_factor_ll_kernel(BandSys 
           const double* Xb_s = sA;
           if (bj < rb) {
             const int fb = j * S.TPC + S.T + 1 + bj;
-            if (tid == 0) spin_until_set(flags + fb);
+            if (tid == 0) spin_until_set(flags + fb, false);
             __syncthreads();
             const double2* Xb = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fb) * kTileElems);
             for (int e = tid; e < kTileElems / 2; e += kFacThreads) reinterpret_cast<double2*>(sB)[e] = __ldcg(Xb + e);
