@@ -33,9 +33,9 @@ struct BandSys {
   int* fail;         // != 0: Cholesky breakdown
   int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters] (zeroed per solve)
   unsigned long long* trace;  // optional [NT*TPC*8] per-task timestamps (LVI_TRACE_FACTOR=file), else nullptr
-  double* work_d;    // [NT*kTile] partial sums of the back substitution
+  double* work_d;    // [NT*kTile] partial sums of the back substitution, then [NT*2*kTile] 8-byte mailbox words (value half | flag)
   size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
-  size_t work_d_count() const { return static_cast<size_t>(NT) * kTile; }
+  size_t work_d_count() const { return static_cast<size_t>(NT) * kTile + static_cast<size_t>(NT) * 2 * kTile; }   // + LL mailbox words
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row

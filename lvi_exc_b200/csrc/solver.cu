@@ -395,6 +395,22 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 // One task per block column, fetched in descending order.  A task stages W_m and its first sub-diagonal tile in shared memory while it
 // waits for the contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of
 // k = m-1 (first: it is the dependency chain), m-2, ... m-T with one warp per tile.
+// The contribution of column m to column m-1 is the serial chain of the substitution.  It travels through a flagged mailbox (each 8-byte
+// word = 32 bits of the value | a flag, in the style of NCCL's LL protocol): the consumer sees data and readiness in ONE L2 round trip
+// instead of the three of "atomicAdd partial sum, fence, bump arrival counter / poll counter, load partial sum".
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long w0 = (b << 32) | 1ull, w1 = (b & 0xffffffff00000000ull) | 1ull;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* slot) {
+  unsigned long long w0, w1;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  } while ((w0 & 1ull) == 0 || (w1 & 1ull) == 0);   // each 8-byte half carries its own flag: no reliance on 16-byte atomicity
+  return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
+}
+
 __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
   extern __shared__ double smem[];
   constexpr int kLD = kTile + 1;      // padded: thread c walks column c, so consecutive threads must hit different banks
@@ -406,6 +422,7 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
   int* arrivals = S.work_i + static_cast<size_t>(S.NT) * S.TPC;
   int* counter = arrivals + S.NT + 1;
   double* vsum = S.work_d;
+  unsigned long long* mailbox = reinterpret_cast<unsigned long long*>(S.work_d + static_cast<size_t>(S.NT) * kTile);   // [NT][32][2]
   double* x = S.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < S.ldc; i += 256) x2s[i] = x[static_cast<size_t>(S.NT) * kTile + i];
@@ -445,15 +462,21 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
         for (int r = 0; r < kTile; ++r) bsum = fma(bt[r], xv[r], bsum);
       }
       bsum = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + kTile * tid] - bsum;  // z_m - Lb^T x2
-      if (tid == 0) while (ld_acquire(arrivals + m) < Tm) {}
+      if (tid == 0) while (ld_acquire(arrivals + m) < Tm - 1) {}   // contributions of columns m+2.. (m+1 comes through the mailbox)
       sv[tid] = bsum;
     }
     __syncthreads();
-    if (tid < kTile) sv[tid] -= __ldcg(vsum + static_cast<size_t>(m) * kTile + tid);
+    if (tid < kTile) {
+      double v = sv[tid] - __ldcg(vsum + static_cast<size_t>(m) * kTile + tid);
+      if (Tm >= 1) v -= ll_load(mailbox + (static_cast<size_t>(m) * kTile + tid) * 2);
+      sv[tid] = v;
+    }
     __syncthreads();
     if (tid < kTile) {
-      double xk = 0.0;
-      for (int r = tid; r < kTile; ++r) xk = fma(sW[r + kLD * tid], sv[r], xk);  // column tid of W (lower triangular): (W^T v)_tid
+      double x0 = 0.0, x1 = 0.0;   // column tid of W (zero above the diagonal): (W^T v)_tid, two independent accumulation chains
+#pragma unroll
+      for (int r = 0; r < kTile; r += 2) { x0 = fma(sW[r + kLD * tid], sv[r], x0); x1 = fma(sW[r + 1 + kLD * tid], sv[r + 1], x1); }
+      const double xk = x0 + x1;
       sx[tid] = xk;
       x[static_cast<size_t>(m) * kTile + tid] = xk;
     }
@@ -467,11 +490,17 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
       for (int h = 0; h < kTile / 32; ++h) {
         const int c = lane + 32 * h;
         const double* tc = tl + ldt * c;
-        double u = 0.0;
-#pragma unroll 8
-        for (int r = 0; r < kTile; ++r) u = fma(tc[r], sx[r], u);
-        atomicAdd(vsum + static_cast<size_t>(k) * kTile + c, u);
+        double tv[kTile];
+#pragma unroll
+        for (int r = 0; r < kTile; ++r) tv[r] = tc[r];   // all loads in flight at once: one L2 round trip per tile, not four
+        double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kTile; r += 2) { u0 = fma(tv[r], sx[r], u0); u1 = fma(tv[r + 1], sx[r + 1], u1); }
+        const double u = u0 + u1;
+        if (d == 1) ll_store(mailbox + (static_cast<size_t>(k) * kTile + c) * 2, u);
+        else atomicAdd(vsum + static_cast<size_t>(k) * kTile + c, u);
       }
+      if (d == 1) continue;
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(arrivals + k, 1);
