@@ -35,7 +35,8 @@ struct BandSys {
   unsigned long long* trace;  // optional [NT*TPC*8] per-task timestamps (LVI_TRACE_FACTOR=file), else nullptr
   double* work_d;    // [NT*kTile] partial sums of the back substitution, then [NT*2*kTile] 8-byte mailbox words (value half | flag)
   size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
-  size_t work_d_count() const { return static_cast<size_t>(NT) * kTile + static_cast<size_t>(NT) * 2 * kTile; }   // + LL mailbox words
+  // vsum [NT*32] | back-substitution mailbox [NT*64 words] | flagged copies of W_j and of the first sub-diagonal tile [2 * NT*2048 words]
+  size_t work_d_count() const { return static_cast<size_t>(NT) * (3 * kTile + 4 * kTileElems); }
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row

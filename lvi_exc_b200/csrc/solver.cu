@@ -259,6 +259,23 @@ __device__ __forceinline__ int ordered_column_desc(int p, int NT0, int NT) {
   return c < NT0 ? NT0 - 1 - c : NT - 1 - (c - NT0);
 }
 
+// ---- flagged ("LL") transfers for the hand-offs on the serial chains
+// The contribution of column m to column m-1 is the serial chain of the substitution.  It travels through a flagged mailbox (each 8-byte
+// word = 32 bits of the value | a flag, in the style of NCCL's LL protocol): the consumer sees data and readiness in ONE L2 round trip
+// instead of the three of "atomicAdd partial sum, fence, bump arrival counter / poll counter, load partial sum".
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long w0 = (b << 32) | 1ull, w1 = (b & 0xffffffff00000000ull) | 1ull;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* slot) {
+  unsigned long long w0, w1;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  } while ((w0 & 1ull) == 0 || (w1 & 1ull) == 0);   // each 8-byte half carries its own flag: no reliance on 16-byte atomicity
+  return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
+}
+
 constexpr int kFacThreads = 256;
 static_assert(kTile == 32, "band_factor_ll_kernel is written for 32x32 tiles (4 outputs per thread)");
 
@@ -268,6 +285,10 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   __shared__ int s_q;
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
+  // flagged copies of the two tiles that travel along the pivot chain (W_j: diagonal task -> first panel task; L(j+1,j): first panel task
+  // -> next diagonal task): the consumer polls the data itself, one L2 round trip instead of "store, fence, flag / poll flag, load"
+  unsigned long long* WLL = reinterpret_cast<unsigned long long*>(S.work_d + static_cast<size_t>(S.NT) * 3 * kTile);
+  unsigned long long* SubLL = WLL + static_cast<size_t>(S.NT) * 2 * kTileElems;
   const int ntask = S.NT * S.TPC;
   const int tid = threadIdx.x;
   const int a = tid & 31, c0 = tid >> 5;
@@ -299,16 +320,24 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     for (int k = kmin; k < j; ++k) {
       const int fi = k * S.TPC + (band ? (i - k) : s);
       const int fj = k * S.TPC + (j - k);
-      if (tid == 0) spin_until_set(flags + fi, s <= 1);
-      if (tid == 32 && fj != fi) spin_until_set(flags + fj, s <= 1);
-      __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
-      if (k == j - 1) LVI_TRACE(1);
-      const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
-      const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
+      if (s == 0 && k == j - 1) {  // pivot chain: L(j,j-1) arrives through its flagged copy
+        __syncthreads();
+        const unsigned long long* src = SubLL + static_cast<size_t>(k) * 2 * kTileElems;
 #pragma unroll
-      for (int e = tid; e < kTileElems / 2; e += kFacThreads) {
-        reinterpret_cast<double2*>(sA)[e] = __ldcg(Li + e);
-        reinterpret_cast<double2*>(sB)[e] = __ldcg(Lj + e);
+        for (int e = tid; e < kTileElems; e += kFacThreads) { const double v = ll_load(src + 2 * e); sA[e] = v; sB[e] = v; }
+        LVI_TRACE(1);
+      } else {
+        if (tid == 0) spin_until_set(flags + fi, s <= 1);
+        if (tid == 32 && fj != fi) spin_until_set(flags + fj, s <= 1);
+        __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
+        if (k == j - 1) LVI_TRACE(1);
+        const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
+        const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
+#pragma unroll
+        for (int e = tid; e < kTileElems / 2; e += kFacThreads) {
+          reinterpret_cast<double2*>(sA)[e] = __ldcg(Li + e);
+          reinterpret_cast<double2*>(sB)[e] = __ldcg(Lj + e);
+        }
       }
       __syncthreads();
       if (k == j - 1) LVI_TRACE(2);
@@ -332,16 +361,25 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       __syncthreads();
       LVI_TRACE(4);
       double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      unsigned long long* wll = WLL + static_cast<size_t>(j) * 2 * kTileElems;
+      for (int e = tid; e < kTileElems; e += kFacThreads) ll_store(wll + 2 * e, sW[(e & 31) * kLP + (e >> 5)]);   // the chain's copy first
       for (int e = tid; e < kTileElems; e += kFacThreads) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
       __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
       if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
       LVI_TRACE(7);
     } else {       // panel task: X = P W_j^T
-      if (tid == 0) spin_until_set(flags + j * S.TPC, s <= 1);
-      __syncthreads();
-      LVI_TRACE(4);
-      const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
-      for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
+      const bool chain_tile = band && s == 1;   // the first sub-diagonal tile is on the pivot chain
+      if (chain_tile) {
+        const unsigned long long* wll = WLL + static_cast<size_t>(j) * 2 * kTileElems;
+        for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = ll_load(wll + 2 * e);
+        LVI_TRACE(4);
+      } else {
+        if (tid == 0) spin_until_set(flags + j * S.TPC, false);
+        __syncthreads();
+        LVI_TRACE(4);
+        const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+        for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
+      }
       __syncthreads();
       LVI_TRACE(5);
       double out[4];
@@ -351,6 +389,11 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
         double v = 0.0;
         for (int m = 0; m <= c; ++m) v = fma(sA[a + 32 * m], sW[c * kLP + m], v);
         out[jj] = v;
+      }
+      if (chain_tile) {
+        unsigned long long* sll = SubLL + static_cast<size_t>(j) * 2 * kTileElems;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) ll_store(sll + 2 * (a + 32 * (c0 + 8 * jj)), out[jj]);
       }
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
@@ -395,22 +438,6 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 // One task per block column, fetched in descending order.  A task stages W_m and its first sub-diagonal tile in shared memory while it
 // waits for the contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of
 // k = m-1 (first: it is the dependency chain), m-2, ... m-T with one warp per tile.
-// The contribution of column m to column m-1 is the serial chain of the substitution.  It travels through a flagged mailbox (each 8-byte
-// word = 32 bits of the value | a flag, in the style of NCCL's LL protocol): the consumer sees data and readiness in ONE L2 round trip
-// instead of the three of "atomicAdd partial sum, fence, bump arrival counter / poll counter, load partial sum".
-__device__ __forceinline__ void ll_store(unsigned long long* slot, double v) {
-  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-  const unsigned long long w0 = (b << 32) | 1ull, w1 = (b & 0xffffffff00000000ull) | 1ull;
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
-}
-__device__ __forceinline__ double ll_load(const unsigned long long* slot) {
-  unsigned long long w0, w1;
-  do {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-  } while ((w0 & 1ull) == 0 || (w1 & 1ull) == 0);   // each 8-byte half carries its own flag: no reliance on 16-byte atomicity
-  return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
-}
-
 __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
   extern __shared__ double smem[];
   constexpr int kLD = kTile + 1;      // padded: thread c walks column c, so consecutive threads must hit different banks
