@@ -22,11 +22,12 @@
 
 #include "nccl_dyn.hpp"
 #include "problem.cuh"
+#include "tile_chol.cuh"
 
 namespace lvi {
 
-constexpr unsigned FULL = 0xffffffffu;
-constexpr int kLP = 33;  // padded leading dimension of the 32x32 shared-memory tiles
+constexpr unsigned FULL = kFullWarp;
+constexpr int kLP = kCholLd;  // padded leading dimension of the 32x32 shared-memory tiles
 
 // ---- small elementwise kernels -------------------------------------------------------------------------------------
 __global__ void diag_kernel(BandSys H, SchurView SV, int nt, double* __restrict__ d) {
@@ -166,60 +167,6 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
   if (lane == 0) SV.yrho[k] = (-g[t] * sr - acc) / d;
 }
 
-// ---- 32x32 Cholesky + inverse in one warp ------------------------------------------------------------------------------
-// The diagonal block is the serial pivot chain of the whole factorisation, so this routine is latency-critical.  Measured on B200
-// inside the factor kernel (tools/analyze_factor_trace.py): a CTA-wide shared-memory version with one barrier per pivot costs 10.5 us,
-// a one-warp shared-memory loop 30+ us (a ~7k-instruction dependent chain); this one-warp REGISTER version is the fastest (~6 us):
-// lane a owns row a in registers (fully unrolled, constant indices; __noinline__ so the unroller does not give up inside the big
-// kernel), column j is broadcast through shared memory (one LDS per update instead of two shuffles, no predicates: entries above the
-// diagonal hold garbage that is never read), then W = L^-1 is built column-parallel, right-looking, so a lane's FMAs are independent.
-// Writes L (lower, zero upper) to sL[r*33+c] and W to sW[r*33+m].  Call with one full warp.
-__device__ __noinline__ bool warp_potrf_inv(const double* tile, int ld, double* sL, double* sW, double* sCol /*[32]*/) {
-  const int a = threadIdx.x & 31;
-  double A[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) A[c] = tile[a + ld * c];
-  bool bad = false;
-  double rinv = 0.0;
-  double d = __shfl_sync(FULL, A[0], 0);
-  if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-  double ri = rsqrt(d);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const double l = A[j] * ri;  // row j: d / sqrt(d) = sqrt(d)
-    A[j] = l;
-    if (a == j) rinv = ri;
-    sCol[a] = l;
-    if (j < 31) {  // software pipeline: the next pivot only needs column j+1, so its rsqrt overlaps the rest of this rank-1 update
-      const double lc1 = __shfl_sync(FULL, l, j + 1);
-      A[j + 1] = fma(-l, lc1, A[j + 1]);
-      d = __shfl_sync(FULL, A[j + 1], j + 1);
-      if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-      ri = rsqrt(d);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = j + 2; c < 32; ++c) A[c] = fma(-l, sCol[c], A[c]);
-    __syncwarp();
-  }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) sL[a * kLP + c] = (c <= a) ? A[c] : 0.0;
-  __syncwarp();
-  double w[32];
-#pragma unroll
-  for (int r = 0; r < 32; ++r) w[r] = (r == a) ? 1.0 : 0.0;
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    w[t] *= __shfl_sync(FULL, rinv, t);
-#pragma unroll
-    for (int r = t + 1; r < 32; ++r) w[r] = fma(-sL[r * kLP + t], w[t], w[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < 32; ++r) sW[r * kLP + a] = w[r];
-  __syncwarp();
-  return !bad;
-}
-
 // ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
 // Every 32x32 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a global counter, keeps the tile's
 // accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are published (per-tile ready
@@ -283,6 +230,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   __shared__ __align__(16) double sA[kTileElems], sB[kTileElems];
   __shared__ double sM[32 * kLP], sW[32 * kLP], sR[32];
   __shared__ int s_q;
+  __shared__ volatile int s_progress;
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
   // flagged copies of the two tiles that travel along the pivot chain (W_j: diagonal task -> first panel task; L(j+1,j): first panel task
@@ -354,9 +302,13 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = acc[jj];
     __syncthreads();
     if (s == 0) {  // diagonal task: L_jj and W_j = L_jj^-1 (only W is kept: panel solves and the back substitution multiply by it)
+      if (tid == 64) s_progress = 0;
+      __syncthreads();
       if (tid < 32) {
-        const bool ok = warp_potrf_inv(sA, 32, sM, sW, sR);
+        const bool ok = warp_potrf_cols(sA, 32, sM, sR, &s_progress);
         if (!ok && tid == 0) *S.fail = 1;
+      } else if (tid < 64) {
+        warp_inverse_cols(sM, sR, &s_progress, sW);
       }
       __syncthreads();
       LVI_TRACE(4);
