@@ -261,7 +261,7 @@ int lvi_associate_d(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* 
                     lvi_surfel_point* out_d, int64_t cap, int64_t* n_out, int64_t* n_all) {
   return guarded([&] {
     LVI_REQUIRE(ctx && m && s && scans_in_map_d && scans_raw_d, LVI_ERR_INVALID, "lvi_associate_d: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     associate_device(ctx, m, s, scans_in_map_d, map_stride_bytes, scans_raw_d, n_scans, W, H, radius, k_per_ring, time_step, out_d, cap, n_out, n_all);
   });
 }
@@ -271,7 +271,7 @@ int lvi_associate(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s,
                   lvi_surfel_point* out, int64_t cap, int64_t* n_out, int64_t* n_all) {
   return guarded([&] {
     LVI_REQUIRE(ctx && m && s && scans_in_map && scans_raw, LVI_ERR_INVALID, "lvi_associate: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     const int64_t n = static_cast<int64_t>(n_scans) * W * H;
     DBuf<char> map_d(static_cast<size_t>(n) * map_stride_bytes);
     DBuf<lvi_point_xyzit> raw_d(n);
@@ -293,7 +293,7 @@ int lvi_associate_landmarks(lvi_ctx* ctx, const lvi_surfel_set* s, const double*
   return guarded([&] {
     LVI_REQUIRE(ctx && s && plane_out && (pts || n == 0), LVI_ERR_INVALID, "lvi_associate_landmarks: null argument");
     if (n == 0) return;
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     DBuf<double> pd(3 * static_cast<size_t>(n));
     DBuf<int32_t> od(n);
     pd.upload(pts, 3 * static_cast<size_t>(n), ctx->stream);

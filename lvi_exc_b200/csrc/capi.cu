@@ -42,6 +42,12 @@ static void ctx_init(lvi_ctx* c, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   LVI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // device buffers come from the stream-ordered pool (common.cuh, DBuf): keep freed blocks cached instead of returning them to the driver
+  cudaMemPool_t pool;
+  LVI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;
+  LVI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  tl_stream = c->stream;
 }
 
 int lvi_ctx_create(int device, void* nccl_comm, int rank, int world, lvi_ctx** out) {
@@ -88,7 +94,14 @@ int lvi_ctx_destroy(lvi_ctx* ctx) {
   if (!ctx) return LVI_OK;
   cudaSetDevice(ctx->device);
   if (ctx->owns_nccl && ctx->nccl) nccl().CommDestroy(static_cast<ncclComm_t>(ctx->nccl));
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // hand cached blocks back to the driver
+    cudaStreamDestroy(ctx->stream);
+    if (tl_stream == ctx->stream) tl_stream = nullptr;
+  }
+  (void)cudaGetLastError();
   delete ctx;
   return LVI_OK;
 }
@@ -96,7 +109,7 @@ int lvi_ctx_destroy(lvi_ctx* ctx) {
 int lvi_ctx_synchronize(lvi_ctx* ctx) {
   return guarded([&] {
     LVI_REQUIRE(ctx, LVI_ERR_INVALID, "null ctx");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     LVI_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }

@@ -62,24 +62,45 @@ struct lvi_ctx {
 
 namespace lvi {
 
+// The stream the calling thread's current entry point works on.  Device buffers are taken from and returned to the device's
+// stream-ordered memory pool on it (cudaMallocAsync / cudaFreeAsync; the pool keeps freed blocks, release threshold = never), so
+// creating and destroying a problem or a map costs microseconds per buffer instead of a device-synchronising cudaMalloc / cudaFree.
+inline thread_local cudaStream_t tl_stream = nullptr;
+inline void activate(lvi_ctx* c) {
+  LVI_CUDA(cudaSetDevice(c->device));
+  tl_stream = c->stream;
+}
+
 // RAII device buffer on a context's stream-ordered pool
 template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t pool_stream = nullptr;   // stream the block was taken on (nullptr: plain cudaMalloc)
   DBuf() = default;
   explicit DBuf(size_t count) { alloc(count); }
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; pool_stream = o.pool_stream; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
   ~DBuf() { release(); }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) LVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    if (!count) return;
+    pool_stream = tl_stream;
+    if (pool_stream) LVI_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), pool_stream));
+    else LVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) {  // a destroyed context's stream is no longer valid: fall back to the synchronising free
+      if (!pool_stream || cudaFreeAsync(p, pool_stream) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+    }
+    p = nullptr; n = 0;
+  }
   void zero(cudaStream_t s) { if (n) LVI_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t count, cudaStream_t s) { if (count) LVI_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
   void download(T* h, size_t count, cudaStream_t s) const { if (count) LVI_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }

@@ -9,6 +9,7 @@
 // consecutive residuals that share a knot span (same column -> position map; residual tables are chronological) into ONE
 // J_run^T J_run contribution, so HBM sees one fp64 atomic per (run, column pair) instead of one per (residual, pair).
 // The Huber corrector (ceres Corrector, rho'' <= 0 branch) and the EigenQuaternionParameterization tangent are folded in.
+#include <chrono>
 #include <cstring>
 
 #include "problem.cuh"
@@ -337,6 +338,14 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
   auto p = std::unique_ptr<lvi_problem>(new lvi_problem());
   p->ctx = ctx; p->desc = *d;
   Lowered& L = p->L;
+  const bool timing = std::getenv("LVI_TIME_CREATE") != nullptr;   // diagnostics: host phases of problem creation on stderr
+  auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto T1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lvi] create: %-22s %.3f ms\n", what, std::chrono::duration<double, std::milli>(T1 - T0).count());
+    T0 = T1;
+  };
   try {
     lower_problem(*d, L);
   } catch (const RangeError& e) {
@@ -350,12 +359,14 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
     const double nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     if (std::fabs(nrm - 1.0) > 1e-5) throw Error(LVI_ERR_DOMAIN, "SO3 control point is not a unit quaternion");
   }
+  lap("lower_problem");
   double sens[SENS_N];
   pack_sens(*d, sens);
   {
     ProblemView hv = host_view(*d, L, sens);
     compute_bandwidth(hv, L);
   }
+  lap("compute_bandwidth");
   cudaStream_t st = ctx->stream;
   const int n = d->n_knots, nl = d->n_landmarks;
   p->off_r3 = 0; p->off_so3 = 3 * n; p->off_sens = 7 * n; p->off_rho = 7 * n + SENS_N; p->nx = 7 * n + SENS_N + std::max(nl, 1);
@@ -382,6 +393,7 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
     R.ua = up_d(p->tab_d[t][0], T.ua); R.ub = up_d(p->tab_d[t][1], T.ub); R.v = up_d(p->tab_d[t][2], T.v);
     R.weight = up_d(p->tab_d[t][3], T.weight); R.huber = up_d(p->tab_d[t][4], T.huber);
   }
+  lap("tables alloc+upload");
   V.pos_r3 = up_i(p->pos_r3, L.pos_r3); V.pos_so3 = up_i(p->pos_so3, L.pos_so3); V.pos_rho = up_i(p->pos_rho, L.pos_rho);
   for (int b = 0; b < TB_COUNT; ++b) V.pos_sens[b] = L.pos_sens[b];
   if (d->n_planes > 0) {
@@ -411,6 +423,7 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
   p->scal.alloc(64);
   LVI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_scal), 64 * sizeof(double)));
   LVI_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  lap("rest + sync");
   return p.release();
 }
 
@@ -432,13 +445,13 @@ void lvi_solve_options_default(lvi_solve_options* o) {
 int lvi_problem_create(lvi_ctx* ctx, const lvi_problem_desc* desc, lvi_problem** out) {
   return guarded([&] {
     LVI_REQUIRE(ctx && desc && out, LVI_ERR_INVALID, "lvi_problem_create: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     *out = create_problem(ctx, desc);
   });
 }
 
 int lvi_problem_destroy(lvi_problem* p) {
-  if (p) { cudaSetDevice(p->ctx->device); delete p; }
+  if (p) { cudaSetDevice(p->ctx->device); tl_stream = p->ctx->stream; delete p; }
   return LVI_OK;
 }
 
@@ -458,7 +471,7 @@ int lvi_problem_tangent_offset_block(const lvi_problem* p, int which) {
 int lvi_problem_evaluate(lvi_problem* p, double* cost, double* residuals, double* gradient) {
   return guarded([&] {
     LVI_REQUIRE(p, LVI_ERR_INVALID, "lvi_problem_evaluate: null problem");
-    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    activate(p->ctx);
     cudaStream_t st = p->ctx->stream;
     if (gradient) {
       problem_linearize(p, nullptr);
@@ -482,7 +495,7 @@ int lvi_problem_evaluate(lvi_problem* p, double* cost, double* residuals, double
 int lvi_problem_jacobian_dense(lvi_problem* p, double* J) {
   return guarded([&] {
     LVI_REQUIRE(p && J, LVI_ERR_INVALID, "lvi_problem_jacobian_dense: null argument");
-    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    activate(p->ctx);
     const size_t n = static_cast<size_t>(p->L.n_res) * p->nt;
     LVI_REQUIRE(n < (1ull << 28), LVI_ERR_INVALID, "lvi_problem_jacobian_dense: problem too large for a dense Jacobian");
     cudaStream_t st = p->ctx->stream;

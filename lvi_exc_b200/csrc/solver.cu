@@ -223,6 +223,23 @@ __device__ __forceinline__ double ll_load(const unsigned long long* slot) {
   return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
 }
 
+// N flagged words with all loads in flight at once (a late word costs ONE more round trip, not one per word)
+template <int N>
+__device__ __forceinline__ void ll_load_n(const unsigned long long* slot, int stride_words, double (&v)[N]) {
+  unsigned long long w0[N], w1[N];
+  bool ok;
+  do {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[i]), "=l"(w1[i]) : "l"(slot + static_cast<size_t>(i) * stride_words) : "memory");
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && ((w0[i] & w1[i] & 1ull) != 0);
+  } while (!ok);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __longlong_as_double(static_cast<long long>((w0[i] >> 32) | (w1[i] & 0xffffffff00000000ull)));
+}
+
 constexpr int kFacThreads = 256;
 static_assert(kTile == 32, "band_factor_ll_kernel is written for 32x32 tiles (4 outputs per thread)");
 
@@ -271,8 +288,10 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       if (s == 0 && k == j - 1) {  // pivot chain: L(j,j-1) arrives through its flagged copy
         __syncthreads();
         const unsigned long long* src = SubLL + static_cast<size_t>(k) * 2 * kTileElems;
+        double v[4];
+        ll_load_n<4>(src + 2 * tid, 2 * kFacThreads, v);
 #pragma unroll
-        for (int e = tid; e < kTileElems; e += kFacThreads) { const double v = ll_load(src + 2 * e); sA[e] = v; sB[e] = v; }
+        for (int q4 = 0; q4 < 4; ++q4) { sA[tid + kFacThreads * q4] = v[q4]; sB[tid + kFacThreads * q4] = v[q4]; }
         LVI_TRACE(1);
       } else {
         if (tid == 0) spin_until_set(flags + fi, s <= 1);
@@ -323,7 +342,10 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       const bool chain_tile = band && s == 1;   // the first sub-diagonal tile is on the pivot chain
       if (chain_tile) {
         const unsigned long long* wll = WLL + static_cast<size_t>(j) * 2 * kTileElems;
-        for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = ll_load(wll + 2 * e);
+        double v[4];
+        ll_load_n<4>(wll + 2 * tid, 2 * kFacThreads, v);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) sW[a * kLP + c0 + 8 * q4] = v[q4];   // element e = tid + 256 q4: row e & 31 = a, column e >> 5
         LVI_TRACE(4);
       } else {
         if (tid == 0) spin_until_set(flags + j * S.TPC, false);
@@ -334,13 +356,17 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       }
       __syncthreads();
       LVI_TRACE(5);
-      double out[4];
+      double out[4] = {0.0, 0.0, 0.0, 0.0};   // X(a, c) = sum_{m <= c} P(a, m) W(c, m), c = c0 + 8 jj: four chains, warp-uniform bounds
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int c = c0 + 8 * jj;
-        double v = 0.0;
-        for (int m = 0; m <= c; ++m) v = fma(sA[a + 32 * m], sW[c * kLP + m], v);
-        out[jj] = v;
+      for (int seg = 0; seg < 4; ++seg) {
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          const int m = seg * 8 + mm;
+          const double xa = sA[a + 32 * m];
+#pragma unroll
+          for (int jj = seg + 1; jj < 4; ++jj) out[jj] = fma(xa, sW[(c0 + 8 * jj) * kLP + m], out[jj]);
+          if (mm <= c0) out[seg] = fma(xa, sW[(c0 + 8 * seg) * kLP + m], out[seg]);
+        }
       }
       if (chain_tile) {
         unsigned long long* sll = SubLL + static_cast<size_t>(j) * 2 * kTileElems;
@@ -716,8 +742,9 @@ void band_factor_solve(lvi_ctx* ctx, BandSys& A, BandSys& A2) {
   band_solve_only(ctx, A, A2);
 }
 
-struct Scalars {  // mirrors p->scal
+struct Scalars {  // mirrors p->scal (+ the factorisation failure flag)
   double cost, cand_cost, yg, d2y2, nonfinite, diff_ss, diff_max, xnorm_ss, gd;
+  int failed;
 };
 
 static void allreduce_sum(lvi_ctx* ctx, double* buf, size_t count) {
@@ -728,9 +755,11 @@ static void allreduce_sum(lvi_ctx* ctx, double* buf, size_t count) {
 
 static void read_scalars(lvi_problem* p, Scalars& s) {
   cudaStream_t st = p->ctx->stream;
-  LVI_CUDA(cudaMemcpyAsync(p->h_scal, p->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  LVI_CUDA(cudaStreamSynchronize(st));
+  LVI_CUDA(cudaMemcpyAsync(p->h_scal, p->scal.p, 15 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LVI_CUDA(cudaMemcpyAsync(p->h_scal + 15, p->fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LVI_CUDA(cudaStreamSynchronize(st));   // the ONLY host wait of the LM loop: twice per iteration
   const double* h = p->h_scal;
+  std::memcpy(&s.failed, p->h_scal + 15, sizeof(int));
   s.cost = h[0]; s.cand_cost = h[1]; s.yg = h[2]; s.d2y2 = h[3]; s.nonfinite = h[4]; s.diff_ss = h[5]; s.diff_max = h[6]; s.xnorm_ss = h[7]; s.gd = h[8];
 }
 
@@ -808,17 +837,23 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   const int nt = p->nt;
   DBuf<double> dH(std::max(nt, 1));
   Scalars sc{};
-  cudaEvent_t e0, e1;
-  LVI_CUDA(cudaEventCreate(&e0)); LVI_CUDA(cudaEventCreate(&e1));
-  float tj = 0, tl = 0, ms = 0;
-  auto tic = [&] { LVI_CUDA(cudaEventRecord(e0, st)); };
-  auto toc = [&](float& accu) { LVI_CUDA(cudaEventRecord(e1, st)); LVI_CUDA(cudaEventSynchronize(e1)); LVI_CUDA(cudaEventElapsedTime(&ms, e0, e1)); accu += ms; };
+  // phase timing with CUDA events that are only read back after the loop: the loop itself never waits for them
+  struct Span { cudaEvent_t a, b; float* accu; };
+  std::vector<Span> spans;
+  float tj = 0, tl = 0;
+  auto tic = [&](float& accu) {
+    Span sp{nullptr, nullptr, &accu};
+    LVI_CUDA(cudaEventCreate(&sp.a)); LVI_CUDA(cudaEventCreate(&sp.b));
+    LVI_CUDA(cudaEventRecord(sp.a, st));
+    spans.push_back(sp);
+  };
+  auto toc = [&] { LVI_CUDA(cudaEventRecord(spans.back().b, st)); };
 
   // fixed cost of the residual blocks whose parameter blocks are all constant (dropped from the reduced program)
   trial_cost(p, p->X.p, p->scal.p + 1, false, true);
   read_scalars(p, sc);
   const double fixed_cost = sc.cand_cost;
-  tic(); linearize(p); toc(tj);
+  tic(tj); linearize(p); toc();
   read_scalars(p, sc);
   double x_cost = sc.cost;
   S.initial_cost = x_cost + fixed_cost; S.fixed_cost = fixed_cost;
@@ -853,18 +888,26 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
     if (it >= o.max_num_iterations) break;
     ++it;
     if (!reuse_diagonal) refresh_diag(p, dH, o);
-    tic();
+    // the whole trial is queued before the host looks at anything: step, candidate point, its cost, the Armijo slope, step norms
+    tic(tl);
     compute_step(p, radius);
-    toc(tl);
+    toc();
+    apply_plus(p, p->delta.p, 1.0, 1.0);
+    tic(tj);
+    trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
+    toc();
+    if (p->L.constrained) {
+      LVI_CUDA(cudaMemsetAsync(p->scal.p + 8, 0, sizeof(double), st));
+      LVI_LAUNCH(ctx, dot_kernel, std::min(blocks_for(nt), ctx->sm_count * 4), 256, 0, p->g.p, p->delta.p, nt, p->scal.p + 8);
+    }
+    diff_norms(p);
     read_scalars(p, sc);
-    int failed = 0;
-    LVI_CUDA(cudaMemcpy(&failed, p->fail.p, sizeof(int), cudaMemcpyDeviceToHost));
     reuse_diagonal = true;
-    bool step_valid = !failed && sc.nonfinite == 0.0;
+    bool step_valid = !sc.failed && sc.nonfinite == 0.0;
     // model_cost_change = -(J y).(r + J y / 2) = -y.g_s - y^T H_s y / 2, with H_s y = -g_s - D^2 y
     const double model_cost_change = -0.5 * sc.yg + 0.5 * sc.d2y2;
     if (step_valid && !(model_cost_change > 0.0)) step_valid = false;
-    if (!step_valid) {  // HandleInvalidStep
+    if (!step_valid) {  // HandleInvalidStep (the candidate evaluated above is simply discarded)
       ++invalid;
       if (invalid >= o.max_num_consecutive_invalid_steps) { S.termination_type = LVI_FAILURE; break; }
       radius *= 0.5;
@@ -873,16 +916,8 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
       continue;
     }
     invalid = 0;
-    apply_plus(p, p->delta.p, 1.0, 1.0);
-    tic();
-    trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
-    toc(tj);
-    read_scalars(p, sc);
     double cand_cost = sc.cand_cost;
     if (p->L.constrained) {  // projected step: Armijo check along delta (ceres DoLineSearch)
-      LVI_CUDA(cudaMemsetAsync(p->scal.p + 8, 0, sizeof(double), st));
-      LVI_LAUNCH(ctx, dot_kernel, std::min(blocks_for(nt), ctx->sm_count * 4), 256, 0, p->g.p, p->delta.p, nt, p->scal.p + 8);
-      read_scalars(p, sc);
       const double gd = sc.gd;
       double step = 1.0;
       int ls = 0;
@@ -892,12 +927,11 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
         step = ns; ++ls;
         apply_plus(p, p->delta.p, step, 1.0);
         trial_cost(p, p->XC.p, p->scal.p + 1, true, false);
+        diff_norms(p);
         read_scalars(p, sc);
         cand_cost = sc.cand_cost;
       }
     }
-    diff_norms(p);
-    read_scalars(p, sc);
     const double step_norm = std::sqrt(sc.diff_ss);
     const double cost_change = x_cost - cand_cost;
     if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
@@ -910,7 +944,7 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
     if (rel > o.min_relative_decrease) {  // HandleSuccessfulStep
       LVI_CUDA(cudaMemcpyAsync(p->X.p, p->XC.p, sizeof(double) * p->nx, cudaMemcpyDeviceToDevice, st));
       x_cost = cand_cost;
-      tic(); linearize(p); toc(tj);
+      tic(tj); linearize(p); toc();
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(o.max_trust_region_radius, radius);
       decrease_factor = 2.0; reuse_diagonal = false;
@@ -928,8 +962,14 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
     }
     if (radius <= o.min_trust_region_radius) { S.termination_type = LVI_CONVERGENCE; break; }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   problem_download_params(p);
+  LVI_CUDA(cudaStreamSynchronize(st));
+  for (Span& sp : spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.accu += ms;
+    cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+  }
+  (void)cudaGetLastError();
   S.num_iterations = it;
   S.final_cost = x_cost + fixed_cost;
   S.time_jacobian_ms = tj; S.time_linear_solve_ms = tl;
@@ -945,7 +985,7 @@ extern "C" {
 int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary) {
   return guarded([&] {
     LVI_REQUIRE(p && opt && summary, LVI_ERR_INVALID, "lvi_problem_solve: null argument");
-    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    activate(p->ctx);
     solve_lm(p, *opt, *summary);
   });
 }
@@ -955,7 +995,7 @@ int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_su
 int lvi_problem_bench_iterations(lvi_problem* p, int iters, float* ms_per_phase) {
   return guarded([&] {
     LVI_REQUIRE(p && iters > 0, LVI_ERR_INVALID, "lvi_problem_bench_iterations: bad argument");
-    LVI_CUDA(cudaSetDevice(p->ctx->device));
+    activate(p->ctx);
     lvi_ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
     problem_ensure_solver_buffers(p);
@@ -1025,7 +1065,7 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start
     LVI_REQUIRE(ctx && A_dense && rhs && x_out && nb >= 0 && nbo >= 0 && nb + nbo > 0, LVI_ERR_INVALID, "lvi_band_solve_dense: bad argument");
     LVI_REQUIRE((chain1_start == nb || chain1_start % kTile == 0) && chain1_start >= 0 && chain1_start <= nb && n_mid >= 0 && n_mid <= nbo, LVI_ERR_INVALID,
                 "lvi_band_solve_dense: chain1_start must be a multiple of 32 in [0, nb], n_mid in [0, nbo]");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     cudaStream_t st = ctx->stream;
     BandSys S{};
     S.nb = nb; S.nbo = nbo;

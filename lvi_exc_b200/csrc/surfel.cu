@@ -284,7 +284,7 @@ int lvi_surfel_extract(lvi_ctx* ctx, const lvi_voxel_map* m, double lambda, int 
                        lvi_surfel_set** out) {
   return guarded([&] {
     LVI_REQUIRE(ctx && m && out, LVI_ERR_INVALID, "lvi_surfel_extract: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     auto s = std::unique_ptr<lvi_surfel_set>(new lvi_surfel_set());
     s->ctx = ctx;
     const int L = static_cast<int>(m->n_leaves);
@@ -323,7 +323,7 @@ int lvi_surfel_export(lvi_ctx* ctx, const lvi_surfel_set* s, double* p4, double*
                       int32_t* n_inliers) {
   return guarded([&] {
     LVI_REQUIRE(ctx && s, LVI_ERR_INVALID, "lvi_surfel_export: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     const size_t P = static_cast<size_t>(s->n_planes);
     cudaStream_t st = ctx->stream;
     if (p4) s->p4.download(p4, 4 * P, st);

@@ -174,7 +174,7 @@ int lvi_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_
                     const double* target_time, int correct_position, void* out_xyzi_d, int32_t* n_bad_targets) {
   return guarded([&] {
     LVI_REQUIRE(ctx && traj && scans_raw_d && target_time && out_xyzi_d, LVI_ERR_INVALID, "lvi_undistort_d: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     undistort_device(ctx, traj, scans_raw_d, n_scans, pts_per_scan, target_time, correct_position, out_xyzi_d, n_bad_targets);
   });
 }
@@ -183,7 +183,7 @@ int lvi_undistort(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xy
                   const double* target_time, int correct_position, void* out_xyzi, int32_t* n_bad_targets) {
   return guarded([&] {
     LVI_REQUIRE(ctx && traj && scans_raw && target_time && out_xyzi, LVI_ERR_INVALID, "lvi_undistort: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     const size_t np = static_cast<size_t>(n_scans) * pts_per_scan;
     DBuf<lvi_point_xyzit> raw_d(np);
     DBuf<char> out_d(np * 32);
@@ -198,7 +198,7 @@ int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const doubl
   return guarded([&] {
     LVI_REQUIRE(ctx && d && t && pos && quat && valid && n > 0, LVI_ERR_INVALID, "lvi_trajectory_evaluate: bad argument");
     LVI_REQUIRE(d->r3_knots && d->so3_knots && d->n_knots >= 4, LVI_ERR_INVALID, "lvi_trajectory_evaluate: trajectory needs both splines and >= 4 knots");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     cudaStream_t st = ctx->stream;
     const int nk = d->n_knots;
     DBuf<double> r3(3 * static_cast<size_t>(nk)), so3(4 * static_cast<size_t>(nk)), td(n), pd(3 * static_cast<size_t>(n)), qd(4 * static_cast<size_t>(n));
@@ -218,7 +218,7 @@ int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const doubl
 int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scans, int64_t pts_per_scan, const double* poses, void* out_xyzi_d) {
   return guarded([&] {
     LVI_REQUIRE(ctx && scans_xyzi_d && poses && out_xyzi_d, LVI_ERR_INVALID, "lvi_transform_scans_d: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     transform_device(ctx, scans_xyzi_d, n_scans, pts_per_scan, poses, out_xyzi_d);
   });
 }
@@ -226,7 +226,7 @@ int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scan
 int lvi_transform_scans(lvi_ctx* ctx, const void* scans_xyzi, int32_t n_scans, int64_t pts_per_scan, const double* poses, void* out_xyzi) {
   return guarded([&] {
     LVI_REQUIRE(ctx && scans_xyzi && poses && out_xyzi, LVI_ERR_INVALID, "lvi_transform_scans: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     const size_t bytes = static_cast<size_t>(n_scans) * pts_per_scan * 32;
     DBuf<char> in_d(bytes), out_d(bytes);
     LVI_CUDA(cudaMemcpyAsync(in_d.p, scans_xyzi, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -270,7 +270,7 @@ int lvi_voxel_build_d(lvi_ctx* ctx, const void* xyz_d, size_t stride_bytes, int6
                       lvi_voxel_map** out) {
   return guarded([&] {
     LVI_REQUIRE(ctx && xyz_d && out, LVI_ERR_INVALID, "lvi_voxel_build_d: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     *out = build_from_device(ctx, xyz_d, stride_bytes, n_points, leaf_size, min_points, eig_mult);
   });
 }
@@ -280,7 +280,7 @@ int lvi_voxel_build(lvi_ctx* ctx, const void* xyz, size_t stride_bytes, int64_t 
   return guarded([&] {
     LVI_REQUIRE(ctx && xyz && out, LVI_ERR_INVALID, "lvi_voxel_build: null argument");
     LVI_REQUIRE(n_points > 0, LVI_ERR_INVALID, "lvi_voxel_build: empty cloud");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     DBuf<char> in(static_cast<size_t>(n_points) * stride_bytes);
     LVI_CUDA(cudaMemcpyAsync(in.p, xyz, in.n, cudaMemcpyHostToDevice, ctx->stream));
     *out = build_from_device(ctx, in.p, stride_bytes, n_points, leaf_size, min_points, eig_mult);
@@ -303,7 +303,7 @@ int lvi_voxel_export(lvi_ctx* ctx, const lvi_voxel_map* m, int64_t* keys, int32_
                      double* evecs, double* icov, int64_t* leaf_start, int32_t* point_index) {
   return guarded([&] {
     LVI_REQUIRE(ctx && m, LVI_ERR_INVALID, "lvi_voxel_export: null argument");
-    LVI_CUDA(cudaSetDevice(ctx->device));
+    activate(ctx);
     cudaStream_t st = ctx->stream;
     const size_t L = static_cast<size_t>(m->n_leaves);
     std::vector<int32_t> k32, ls32;

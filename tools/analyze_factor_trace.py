@@ -19,6 +19,13 @@ if p is not None:
     print("panel task (j+1,j), mean us between marks:")
     for a in range(1, 8):
         print(f"  {names_p[a-1]:>18} -> {names_p[a]:<18} {np.nanmean(p[sl, a] - p[sl, a-1]):8.2f}")
-    print("chain: diag publish(j) -> panel W seen(j)      %.2f" % np.nanmean(p[sl, 4] - d[sl, 7]))
-    print("chain: panel publish(j) -> diag(j+1) dep seen   %.2f" % np.nanmean(d[21:NT-19, 1] - p[sl, 7]))
-    print("column period (diag publish j+1 - j)            %.2f" % np.nanmean(np.diff(d[sl, 7])))
+    sl1 = slice(21, NT // 2 - 39)
+    sl0 = slice(20, NT // 2 - 40)
+    m = np.nanmean
+    print("pivot chain of the first chain, mean us per column:")
+    print("  potrf + inverse (accum done -> W ready)        %.2f" % m(d[sl0, 4] - d[sl0, 3]))
+    print("  W hand-off (W ready -> panel has W)            %.2f" % m(p[sl0, 5] - d[sl0, 4]))
+    print("  panel solve X = P W^T                          %.2f" % m(p[sl0, 6] - p[sl0, 5]))
+    print("  L(j+1,j) hand-off (X done -> next diag has it) %.2f" % m(d[sl1, 2] - p[sl0, 6]))
+    print("  last rank-32 update of the next diagonal       %.2f" % m(d[sl1, 3] - d[sl1, 2]))
+    print("  column period                                  %.2f" % m(d[sl1, 3] - d[sl0, 3]))
