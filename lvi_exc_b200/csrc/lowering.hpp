@@ -176,7 +176,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     }
   }
   // ---- surfel (map time first: spans must be ordered, Q12)
-  std::set<int> border_knots;
+  std::vector<char> border_flag(n + 4, 0);   // knots of the map-time windows (they go to the arrow border)
   {
     LoweredTable& T = L.tab[RT_SURFEL];
     need(d.surfel_t, d.n_surfel, "surfel_t"); need(d.surfel_point, d.n_surfel, "surfel_point"); need(d.surfel_plane, d.n_surfel, "surfel_plane");
@@ -190,7 +190,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
       if (d.surfel_t[i] < d.surfel_tmap[i]) throw RangeError("Time spans are not ordered");
       if (T.ia[i] < 0 || T.ia[i] >= d.n_planes) throw std::invalid_argument("surfel plane id out of range");
       locate2(d, d.surfel_tmap[i], d.surfel_t[i], d.surfel_tmap[i] + d.lidar_toff, d.surfel_t[i] + d.lidar_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
-      if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) border_knots.insert(T.i0a[i] + k); }
+      if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) border_flag[T.i0a[i] + k] = 1; }
     }
     if (T.n && T.active) sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
@@ -242,12 +242,14 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
       if (T.ia[i] < 0 || T.ia[i] >= d.n_planes || T.ib[i] < 0 || T.ib[i] >= d.n_landmarks) throw std::invalid_argument("camera-surfel id out of range");
       locate2(d, d.cs_tmap[i], d.cs_t[i], d.cs_tmap[i] + d.cam_toff, d.cs_t[i] + d.cam_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
       use_window(T.i0a[i]); use_window(T.i0b[i]);
-      for (int k = 0; k < 4; ++k) border_knots.insert(T.i0a[i] + k);
+      for (int k = 0; k < 4; ++k) border_flag[T.i0a[i] + k] = 1;
       rho_used[T.ib[i]] = 1;
       rho_anchor[T.ib[i]] = std::max(rho_anchor[T.ib[i]], T.i0b[i] + 3);
     }
     if (T.n) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
+  std::set<int> border_knots;
+  for (int i = 0; i < n; ++i) if (border_flag[i]) border_knots.insert(i);
   if (border_knots.size() > 16) border_knots.clear();  // not an arrow structure: leave those knots in the band
   // ---- positions
   L.pos_r3.assign(n, -1); L.pos_so3.assign(n, -1); L.pos_rho.assign(std::max(d.n_landmarks, 1), -1);
@@ -359,7 +361,13 @@ struct SpanAcc {
 template <int TYPE> inline void bw_of_type(const ProblemView& P, SpanAcc& A) {
   const ResTable& T = P.tab[TYPE];
   if (!T.active) return;
+  // the band positions a residual touches depend only on its two spline windows (everything else it touches lives in the border or is
+  // an eliminated inverse depth), and consecutive residuals are time-ordered: evaluate each distinct window pair once
+  int last_a = -1, last_b = -1;
   for (int i = 0; i < T.n; ++i) {
+    const int wa = T.i0a ? T.i0a[i] : 0, wb = T.i0b ? T.i0b[i] : 0;
+    if (i > 0 && wa == last_a && wb == last_b) continue;
+    last_a = wa; last_b = wb;
     A.begin();
     for (int c = 0; c < rt_cols(TYPE); ++c) A.add(col_pos<TYPE>(P, i, c));
     A.end();

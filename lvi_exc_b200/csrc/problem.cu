@@ -272,7 +272,7 @@ static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBu
   S.ldc = S.RB * kTile;
   tiles.alloc(std::max<size_t>(static_cast<size_t>(S.NT) * S.TPC * kTileElems, 1));
   C.alloc(static_cast<size_t>(S.ldc) * S.ldc);
-  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail; S.work_i = nullptr; S.work_d = nullptr; S.trace = nullptr;
+  S.tiles = tiles.p; S.C = C.p; S.Linv = Linv; S.x = x; S.fail = fail; S.work_i = nullptr; S.work_d = nullptr; S.trace = nullptr; S.ll = nullptr; S.epoch = 0;
 }
 
 void problem_ensure_solver_buffers(lvi_problem* p) {
@@ -287,6 +287,7 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
   alloc_bandsys(p->A, L, p->A_tiles, p->A_C, p->A_Linv.p, p->A_x.p, p->fail.p);
   p->A_work_i.alloc(p->A.work_i_count()); p->A_work_d.alloc(std::max<size_t>(p->A.work_d_count(), 1));
   p->A.work_i = p->A_work_i.p; p->A.work_d = p->A_work_d.p;
+  p->A_ll.alloc(std::max<size_t>(p->A.ll_count(), 1)); p->A_ll.zero(p->ctx->stream); p->A.ll = p->A_ll.p;
   p->A2 = BandSys{};
   if (p->A.n_mid > 0) {  // second-level system: the separator block of the corner, factored with the same tile machinery
     init_second_level(p->A, p->A2);
@@ -296,6 +297,7 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
     p->A2_work_i.alloc(B.work_i_count()); p->A2_work_d.alloc(B.work_d_count());
     B.tiles = p->A2_tiles.p; B.C = p->A2_C.p; B.Linv = p->A2_Linv.p; B.x = p->A2_x.p; B.fail = p->fail.p;
     B.work_i = p->A2_work_i.p; B.work_d = p->A2_work_d.p; B.trace = nullptr;
+    p->A2_ll.alloc(B.ll_count()); p->A2_ll.zero(p->ctx->stream); B.ll = p->A2_ll.p; B.epoch = 0;
   }
   LVI_REQUIRE(p->A.ldc <= 1024, LVI_ERR_INVALID, "arrow border wider than 1023 dims is not supported");
   const size_t nt = std::max(p->nt, 1);

@@ -31,12 +31,17 @@ struct BandSys {
   double* Linv;      // [NT * kTileElems] inverse of each diagonal Cholesky block (filled by the factorisation)
   double* x;         // [NT*kTile + ldc] solution (band part then border part)
   int* fail;         // != 0: Cholesky breakdown
-  int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters] (zeroed per solve)
+  int* work_i;       // [NT*TPC tile-ready flags | NT back-substitution arrival counters | 2 task counters | 2 chain SM ids] (zeroed per solve)
   unsigned long long* trace;  // optional [NT*TPC*8] per-task timestamps (LVI_TRACE_FACTOR=file), else nullptr
   double* work_d;    // [NT*kTile] partial sums of the back substitution, then [NT*2*kTile] 8-byte mailbox words (value half | flag)
-  size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2; }
-  // vsum [NT*32] | back-substitution mailbox [NT*64 words] | flagged copies of W_j and of the first sub-diagonal tile [2 * NT*2048 words]
-  size_t work_d_count() const { return static_cast<size_t>(NT) * (3 * kTile + 4 * kTileElems); }
+  size_t work_i_count() const { return static_cast<size_t>(NT) * TPC + NT + 2 + 2; }   // + SM ids of the chain CTAs
+  // vsum [NT*32] | back-substitution mailbox [NT*64 words]
+  size_t work_d_count() const { return static_cast<size_t>(NT) * 3 * kTile; }
+  // flagged ("LL") copies: one per tile, W_j and the pre-accumulated first sub-diagonal tile per column; 16 B per value; zeroed ONCE at
+  // allocation, valid words carry the epoch of the factorisation that wrote them
+  unsigned long long* ll;
+  unsigned epoch;
+  size_t ll_count() const { return (static_cast<size_t>(NT) * TPC + 2 * static_cast<size_t>(NT)) * 2 * kTileElems; }
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row
@@ -87,6 +92,7 @@ struct lvi_problem {
   lvi::BandSys H{}, A{}, A2{};   // A2: second-level system of the separator (two-sided ordering)
   lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x, A_work_d, A2_tiles, A2_C, A2_Linv, A2_x, A2_work_d;
   lvi::DBuf<int> A_work_i, A2_work_i;
+  lvi::DBuf<unsigned long long> A_ll, A2_ll;
   lvi::SchurView schur{};
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;

@@ -14,6 +14,7 @@
 //   corner_solve_kernel       dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
 //   band_backsolve_ll_kernel  flag-driven backward substitution, one task per block column.
 // All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -167,13 +168,7 @@ __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV
   if (lane == 0) SV.yrho[k] = (-g[t] * sr - acc) / d;
 }
 
-// ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
-// Every 32x32 tile of the factor is ONE task: a CTA fetches tasks in column-major order from a global counter, keeps the tile's
-// accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are published (per-tile ready
-// flags, ld.acquire / st.release), then finishes it and publishes it.  Each tile is written once by one CTA (no read-modify-write on
-// HBM, no grid-wide barrier); only the chain potrf(j) -> panel(j+1,j) -> potrf(j+1) is serial and everything off the chain overlaps it.
-// Tasks are fetched in dependency order, so a fetched task only ever waits on tasks already held by running CTAs: no deadlock for any
-// grid size.
+// ---- primitives of the flag-driven tile kernels
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -186,6 +181,7 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(tq) * 8 + (slot)] = gtime(); } while (0)
+#define LVI_TRACE_AT(row, slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(row) * 8 + (slot)] = gtime(); } while (0)
 // Tasks on the pivot chain (diagonal tile and first sub-diagonal tile) poll tightly; every other task backs off between polls so that the
 // CTAs that merely wait do not steal issue slots and L2 bandwidth from the ones that work (two CTAs share an SM).
 __device__ __forceinline__ void spin_until_set(const int* f, bool critical = true) {
@@ -210,22 +206,27 @@ __device__ __forceinline__ int ordered_column_desc(int p, int NT0, int NT) {
 // The contribution of column m to column m-1 is the serial chain of the substitution.  It travels through a flagged mailbox (each 8-byte
 // word = 32 bits of the value | a flag, in the style of NCCL's LL protocol): the consumer sees data and readiness in ONE L2 round trip
 // instead of the three of "atomicAdd partial sum, fence, bump arrival counter / poll counter, load partial sum".
-__device__ __forceinline__ void ll_store(unsigned long long* slot, double v) {
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned flag = 1u) {
   const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-  const unsigned long long w0 = (b << 32) | 1ull, w1 = (b & 0xffffffff00000000ull) | 1ull;
+  const unsigned long long w0 = (b << 32) | flag, w1 = (b & 0xffffffff00000000ull) | flag;
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ double ll_load(const unsigned long long* slot) {
+__device__ __forceinline__ bool ll_valid(unsigned long long w0, unsigned long long w1, unsigned flag) {
+  return static_cast<unsigned>(w0) == flag && static_cast<unsigned>(w1) == flag;   // each 8-byte half carries its own flag: no reliance on 16-byte atomicity
+}
+__device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long long w1) {
+  return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* slot, unsigned flag = 1u) {
   unsigned long long w0, w1;
   do {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-  } while ((w0 & 1ull) == 0 || (w1 & 1ull) == 0);   // each 8-byte half carries its own flag: no reliance on 16-byte atomicity
-  return __longlong_as_double(static_cast<long long>((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
+  } while (!ll_valid(w0, w1, flag));
+  return ll_value(w0, w1);
 }
-
 // N flagged words with all loads in flight at once (a late word costs ONE more round trip, not one per word)
 template <int N>
-__device__ __forceinline__ void ll_load_n(const unsigned long long* slot, int stride_words, double (&v)[N]) {
+__device__ __forceinline__ void ll_load_n(const unsigned long long* slot, int stride_words, double (&v)[N], unsigned flag) {
   unsigned long long w0[N], w1[N];
   bool ok;
   do {
@@ -234,33 +235,273 @@ __device__ __forceinline__ void ll_load_n(const unsigned long long* slot, int st
       asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[i]), "=l"(w1[i]) : "l"(slot + static_cast<size_t>(i) * stride_words) : "memory");
     ok = true;
 #pragma unroll
-    for (int i = 0; i < N; ++i) ok = ok && ((w0[i] & w1[i] & 1ull) != 0);
+    for (int i = 0; i < N; ++i) ok = ok && ll_valid(w0[i], w1[i], flag);
   } while (!ok);
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = __longlong_as_double(static_cast<long long>((w0[i] >> 32) | (w1[i] & 0xffffffff00000000ull)));
+  for (int i = 0; i < N; ++i) v[i] = ll_value(w0[i], w1[i]);
 }
 
 constexpr int kFacThreads = 256;
 static_assert(kTile == 32, "band_factor_ll_kernel is written for 32x32 tiles (4 outputs per thread)");
 
+// Flagged copies ("LL": every 8-byte word = half of a value | a 32-bit flag) of every tile, of W_j and of the pre-accumulated first
+// sub-diagonal tile.  A consumer that needs a tile the moment it is made polls the data itself: one L2 round trip instead of "store,
+// fence, flag / poll flag, load" (measured, tools/bench_handoff.cu: 0.76 us same die / 1.19 us across dies against 1.9 - 2.3 us for a
+// 32x32 tile).  The flag is a per-factorisation epoch, so the copies never need clearing.
+__device__ __forceinline__ unsigned long long* ll_tile(const BandSys& S, int tq) { return S.ll + static_cast<size_t>(tq) * 2 * kTileElems; }
+__device__ __forceinline__ unsigned long long* ll_W(const BandSys& S, int j) { return ll_tile(S, S.NT * S.TPC + j); }
+__device__ __forceinline__ unsigned long long* ll_P(const BandSys& S, int j) { return ll_tile(S, S.NT * S.TPC + S.NT + j); }
+
+// CTA-wide fetch of one flagged tile into shared memory (element e of the tile -> dst[e], optionally a second copy).  `eager` consumers
+// sit next to the pivot chain and poll the whole tile; the others first wait, with back-off, for one word, so that two dozen waiting CTAs
+// per chain do not spend L2 bandwidth on polling.
+__device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, unsigned flag, bool eager, double* dst, double* dst2) {
+  const int tid = threadIdx.x;
+  if (!eager) {
+    if (tid == 0) {
+      unsigned long long w0, w1;
+      while (true) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if (ll_valid(w0, w1, flag)) break;
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  double v[4];
+  ll_load_n<4>(src + 2 * tid, 2 * kFacThreads, v, flag);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) dst[tid + kFacThreads * q4] = v[q4];
+  if (dst2) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) dst2[tid + kFacThreads * q4] = v[q4];
+  }
+}
+
+// the warps that idle during the diagonal block's Cholesky fetch flagged tiles into shared memory, all their loads in flight at once;
+// the non-blocking form gives up as soon as the Cholesky has finished (its barrier must not wait for a tile that is still being made)
+template <bool BLOCKING>
+__device__ __forceinline__ bool helper_fetch_tile(const unsigned long long* src, unsigned flag, double* dst, int ht, volatile int* progress) {
+  constexpr int kHelpers = 160, kPer = 7;   // 7 * 160 >= 1024
+  unsigned long long w0[kPer], w1[kPer];
+  while (true) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int e = ht + kHelpers * q;
+      w0[q] = w1[q] = flag;
+      if (e < kTileElems) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(src + 2 * e) : "memory");
+    }
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) ok = ok && ll_valid(w0[q], w1[q], flag);
+    if (ok) break;
+    if (!BLOCKING && *progress >= 32) return false;
+  }
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int e = ht + kHelpers * q;
+    if (e < kTileElems) dst[e] = ll_value(w0[q], w1[q]);
+  }
+  return true;
+}
+
+struct FacShared {
+  double sA[kTileElems], sB[kTileElems], sD[kTileElems];
+  double sM[32 * kLP], sW[32 * kLP], sR[32];
+  int q;
+  volatile int progress;
+  int leave;
+  int nready;
+};
+
+// acc(2x2 block of rows 2rp.., columns 2cp..) -= A(rows, :) B(cols, :)^T over one 32-wide k-step, A in sA[r + 32 m], B in sB[c + 32 m].
+// 2x2 register blocking with 16-byte shared-memory loads: 3 shared-memory wavefronts per 4 DFMA instead of the 6 of a 1x4 blocking -- the
+// shared-memory pipe, not the FP64 pipe, bounds this loop (measured: 0.75 us -> per 32^3 step and SM with 1x4).
+__device__ __forceinline__ void rank32_update_2x2(const double* sA, const double* sB, int rp, int cp, double (&acc)[4]) {
+#pragma unroll 8
+  for (int m = 0; m < 32; ++m) {
+    const double2 xa = *reinterpret_cast<const double2*>(sA + 2 * rp + 32 * m);
+    const double2 xb = *reinterpret_cast<const double2*>(sB + 2 * cp + 32 * m);
+    acc[0] = fma(-xa.x, xb.x, acc[0]);
+    acc[1] = fma(-xa.y, xb.x, acc[1]);
+    acc[2] = fma(-xa.x, xb.y, acc[2]);
+    acc[3] = fma(-xa.y, xb.y, acc[3]);
+  }
+}
+// element index of accumulator q of thread (rp, cp) in a column-major 32x32 tile
+__device__ __forceinline__ int acc_elem(int rp, int cp, int q) { return 2 * rp + (q & 1) + 32 * (2 * cp + (q >> 1)); }
+
+// X(a, c) = sum_{m <= c} P(a, m) W(c, m) for c = c0 + 8 jj: four accumulation chains per thread with warp-uniform bounds (W is lower
+// triangular).  P in sP[a + 32 m], W in sW[c * kLP + m].
+__device__ __forceinline__ void panel_times_winv_t(const double* sP, const double* sW, int a, int c0, double (&out)[4]) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) out[jj] = 0.0;
+#pragma unroll
+  for (int seg = 0; seg < 4; ++seg) {
+#pragma unroll
+    for (int mm = 0; mm < 8; ++mm) {
+      const int m = seg * 8 + mm;
+      const double xa = sP[a + 32 * m];
+#pragma unroll
+      for (int jj = seg + 1; jj < 4; ++jj) out[jj] = fma(xa, sW[(c0 + 8 * jj) * kLP + m], out[jj]);
+      if (mm <= c0) out[seg] = fma(xa, sW[(c0 + 8 * seg) * kLP + m], out[seg]);
+    }
+  }
+}
+
+// ---- the pivot chain: one CTA per chain walks its block columns ---------------------------------------------------------------
+//   D_j = Dpre_j - X_{j-1} X_{j-1}^T ; L_jj L_jj^T = D_j, W_j = L_jj^-1 ; X_j = L(j+1,j) = Ppre_j W_j^T
+// Dpre_j (all contributions of columns <= j-2 to the diagonal tile) and Ppre_j (all contributions of columns <= j-1 to tile (j+1,j)) are
+// pre-accumulated by worker CTAs and arrive as flagged copies; X_{j-1} and W_j never leave this CTA's shared memory on their way to the
+// next step, so the serial chain itself has no global-memory hand-off.  While warps 0 and 1 factor and invert the diagonal block, warps
+// 2..6 fetch Ppre_j and (if it is there in time) Dpre_{j+1}, and warp 7 releases the ready flags of the previous column (the fence in
+// front of a release waits for 24 KB of stores to be acknowledged, ~1.5 us: kept off the chain).
+__device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
+  const int tid = threadIdx.x, a = tid & 31, c0 = tid >> 5;
+  const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
+  int* flags = S.work_i;
+  const unsigned ep = S.epoch;
+  const int c_start = chain == 0 ? 0 : S.NT0, c_end = chain == 0 ? S.NT0 : S.NT;
+  const bool coupled = S.T >= 1;
+  double* sA = sh.sA; double* sB = sh.sB; double* sW = sh.sW;
+  bool have_next = false;   // Dpre_j already in sh.sD (fetched under the previous column's Cholesky)
+  int pending = -1;         // column whose ready flags still have to be released
+  bool pending_panel = false;
+  for (int j = c_start; j < c_end; ++j) {
+    const int tq = j * S.TPC;
+    LVI_TRACE(0);
+    double acc[4];
+    if (j == c_start || !coupled) {   // nothing precedes this column: the tile is already final
+      const double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
+      LVI_TRACE(1);
+    } else {
+      if (!have_next) {
+        double v[4];
+        ll_load_n<4>(ll_tile(S, tq) + 2 * tid, 2 * kFacThreads, v, ep);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) sh.sD[tid + kFacThreads * q4] = v[q4];
+        __syncthreads();
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sh.sD[acc_elem(rp, cp, q4)];
+      LVI_TRACE(1);
+      rank32_update_2x2(sA, sA, rp, cp, acc);   // X_{j-1} is still in sA
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) sA[acc_elem(rp, cp, q4)] = acc[q4];
+    if (tid == 64) sh.progress = 0;
+    __syncthreads();
+    LVI_TRACE(2);
+    const bool has_panel = coupled && j + 1 < c_end;
+    int got_next = 1;
+    if (tid < 32) {
+      const bool ok = warp_potrf_cols(sA, 32, sh.sM, sh.sR, &sh.progress);
+      if (!ok && tid == 0) *S.fail = 1;
+    } else if (tid < 64) {
+      warp_inverse_cols(sh.sM, sh.sR, &sh.progress, sW);
+    } else if (tid < 224) {
+      if (has_panel) {
+        if (j == c_start) {
+          const double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
+          for (int e = tid - 64; e < kTileElems; e += 160) sB[e] = tile[e];
+        } else {
+          helper_fetch_tile<true>(ll_P(S, j), ep, sB, tid - 64, &sh.progress);
+        }
+        got_next = helper_fetch_tile<false>(ll_tile(S, tq + S.TPC), ep, sh.sD, tid - 64, &sh.progress) ? 1 : 0;
+      }
+    } else if (tid == 224 && pending >= 0) {
+      __threadfence();
+      st_release(flags + pending * S.TPC, 1);
+      if (pending_panel) st_release(flags + pending * S.TPC + 1, 1);
+    }
+    have_next = __syncthreads_and(got_next) != 0 && has_panel;
+    LVI_TRACE(3);
+    {  // publish W_j: flagged copy for the tasks waiting on it, plain copy for the back substitution
+      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      unsigned long long* wll = ll_W(S, j);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int e = tid + kFacThreads * q4;
+        const double w = sW[(e & 31) * kLP + (e >> 5)];
+        ll_store(wll + 2 * e, w, ep);
+        Wg[e] = w;
+      }
+    }
+    LVI_TRACE(4);
+    if (has_panel) {
+      double out[4];
+      panel_times_winv_t(sB, sW, a, c0, out);
+      LVI_TRACE(5);
+      unsigned long long* sll = ll_tile(S, tq + 1);
+      double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int e = a + 32 * (c0 + 8 * jj);
+        ll_store(sll + 2 * e, out[jj], ep);
+        tile[e] = out[jj];
+        sA[e] = out[jj];     // stays here for the next diagonal tile
+      }
+      LVI_TRACE(6);
+    }
+    __syncthreads();  // every thread's stores are issued (and ordered before warp 7's fence + release under the next Cholesky); X_j is in sA
+    pending = j; pending_panel = has_panel;
+    LVI_TRACE(7);
+  }
+  if (tid == 0 && pending >= 0) {
+    __threadfence();
+    st_release(flags + pending * S.TPC, 1);
+    if (pending_panel) st_release(flags + pending * S.TPC + 1, 1);
+  }
+}
+
+// ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
+// Every 32x32 tile of the factor off the pivot chain is ONE task: a worker CTA fetches tasks in column-major order from a global
+// counter, keeps the tile's accumulator in registers and subtracts L(i,k) L(j,k)^T for k ascending AS SOON AS the two source tiles are
+// published, then multiplies by W_j^T and publishes the tile.  Each tile is written once by one CTA (no read-modify-write on HBM, no
+// grid-wide barrier).  Older source tiles are read plainly behind their ready flag (ld.acquire / st.release); the LAST update of a task
+// -- from the column that has only just been finished -- and W_j come through the flagged copies, because every tile follows the
+// recurrence  W_j -> L(i,j) -> update of L(i,j+1) -> W_{j+1} -> ...  and that loop has to close within one column period of the chain.
+// The tasks of the diagonal tile and of the first sub-diagonal tile only PRE-ACCUMULATE (they hand Dpre / Ppre to the chain CTA, see
+// factor_chain).  Tasks are fetched in dependency order and the chain CTAs are resident from the start, so a fetched task only ever
+// waits on work that is already running: no deadlock for any grid size.
 __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys S) {
-  __shared__ __align__(16) double sA[kTileElems], sB[kTileElems];
-  __shared__ double sM[32 * kLP], sW[32 * kLP], sR[32];
-  __shared__ int s_q;
-  __shared__ volatile int s_progress;
+  __shared__ __align__(16) FacShared sh;
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
-  // flagged copies of the two tiles that travel along the pivot chain (W_j: diagonal task -> first panel task; L(j+1,j): first panel task
-  // -> next diagonal task): the consumer polls the data itself, one L2 round trip instead of "store, fence, flag / poll flag, load"
-  unsigned long long* WLL = reinterpret_cast<unsigned long long*>(S.work_d + static_cast<size_t>(S.NT) * 3 * kTile);
-  unsigned long long* SubLL = WLL + static_cast<size_t>(S.NT) * 2 * kTileElems;
+  int* chain_sm = counter + 2;   // [2] SM id + 1 of the chain CTAs
+  const unsigned ep = S.epoch;
+  const int n_chains = (S.NT0 > 0 && S.NT0 < S.NT) ? 2 : 1;
   const int ntask = S.NT * S.TPC;
   const int tid = threadIdx.x;
   const int a = tid & 31, c0 = tid >> 5;
+  const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (static_cast<int>(blockIdx.x) < n_chains) {
+    if (tid == 0) st_release(chain_sm + blockIdx.x, static_cast<int>(smid) + 1);
+    factor_chain(S, blockIdx.x, sh);
+    return;
+  }
+  // a worker that shares its SM with a chain CTA steps aside: the chain is the critical path and runs ~1.5x faster alone on the SM
+  if (tid == 0) {
+    int leave = 0;
+    for (int c = 0; c < n_chains; ++c) {
+      int v;
+      while ((v = ld_acquire(chain_sm + c)) == 0) {}
+      leave |= (v == static_cast<int>(smid) + 1);
+    }
+    sh.leave = leave && gridDim.x > static_cast<unsigned>(n_chains + 2);
+  }
+  __syncthreads();
+  if (sh.leave) return;
+  double* sA = sh.sA; double* sB = sh.sB; double* sW = sh.sW;
   while (true) {
-    if (tid == 0) s_q = atomicAdd(counter, 1);
+    if (tid == 0) sh.q = atomicAdd(counter, 1);
     __syncthreads();
-    const int q = s_q;
+    const int q = sh.q;
     __syncthreads();
     if (q >= ntask) break;
     const int jo = q / S.TPC, s = q - jo * S.TPC;
@@ -269,6 +510,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     const bool band = s <= S.T;
     const int i = j + s;
     if (band && i >= c_end) continue;  // tile below the end of the chain: never referenced
+    if (band && s <= 1 && (j == c_start || S.T == 0)) continue;   // first column of a chain: the chain CTA reads those tiles directly
     // separator rows of the two-sided ordering couple only to the last <= bw positions of a chain: their border tiles are
     // structurally zero (and stay zero in the factor) before block column sep_first, so those tasks and products are skipped
     const int RBsep = S.n_mid >> kTileLog;                       // border tile rows made of separator dims only
@@ -276,137 +518,140 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     const bool sep_row = !band && (s - S.T - 1) < RBsep;
     if (sep_row && j < sep_first) continue;
     const int tq = j * S.TPC + s;      // storage / flag index of this tile
+    const bool eager = band && s <= 3; // next to the pivot chain
+    const bool stamp = band;                                 // diagnostics (LVI_TRACE_FACTOR)
+    const int trow = j * S.TPC + (s == 0 ? S.TPC - 1 : s);   // the diagonal task stamps into the (unused) last row of its column
     double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
-    LVI_TRACE(0);
+    if (stamp) LVI_TRACE_AT(trow, 0);
     double acc[4];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[jj] = tile[a + 32 * (c0 + 8 * jj)];
+    for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
     const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
-    for (int k = kmin; k < j; ++k) {
-      const int fi = k * S.TPC + (band ? (i - k) : s);
-      const int fj = k * S.TPC + (j - k);
-      if (s == 0 && k == j - 1) {  // pivot chain: L(j,j-1) arrives through its flagged copy
-        __syncthreads();
-        const unsigned long long* src = SubLL + static_cast<size_t>(k) * 2 * kTileElems;
-        double v[4];
-        ll_load_n<4>(src + 2 * tid, 2 * kFacThreads, v);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) { sA[tid + kFacThreads * q4] = v[q4]; sB[tid + kFacThreads * q4] = v[q4]; }
-        LVI_TRACE(1);
-      } else {
-        if (tid == 0) spin_until_set(flags + fi, s <= 1);
-        if (tid == 32 && fj != fi) spin_until_set(flags + fj, s <= 1);
-        __syncthreads();  // sources published; the previous k-step's reads of sA/sB are complete
-        if (k == j - 1) LVI_TRACE(1);
-        const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
-        const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
-#pragma unroll
-        for (int e = tid; e < kTileElems / 2; e += kFacThreads) {
-          reinterpret_cast<double2*>(sA)[e] = __ldcg(Li + e);
-          reinterpret_cast<double2*>(sB)[e] = __ldcg(Lj + e);
+    const int kend = (band && s == 0) ? j - 1 : j;   // the diagonal task leaves the last contribution (X_{j-1}) to the chain CTA
+    // Updates from the older columns: the two source tiles of step k+1 travel from L2 into registers while step k is multiplied (their
+    // ready flags are checked inside the barrier that step k needs anyway); the LAST update takes the flagged copies.
+    double2 ra[2], rb[2];
+    bool staged = false;   // ra / rb hold the tiles of the step about to run
+    auto tile_of = [&](int k, int& fi, int& fj) { fi = k * S.TPC + (band ? i - k : s); fj = k * S.TPC + (j - k); };
+    auto issue = [&](int fi, int fj) {
+      const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
+      const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
+      ra[0] = __ldcg(Li + tid); ra[1] = __ldcg(Li + tid + kFacThreads);
+      rb[0] = __ldcg(Lj + tid); rb[1] = __ldcg(Lj + tid + kFacThreads);
+    };
+    int ready_end = kmin;  // the source tiles of steps [k, ready_end) are known to be published
+    for (int k = kmin; k < kend - 1;) {
+      if (k >= ready_end) {  // one warp looks at the ready flags of the next (up to 32) steps at once: one L2 round trip per batch, not per step
+        if (tid < 32) {
+          const int kk = k + tid;
+          bool ok = false;
+          if (kk < kend - 1) { int fi, fj; tile_of(kk, fi, fj); ok = ld_acquire(flags + fi) != 0 && ld_acquire(flags + fj) != 0; }
+          const unsigned mask = __ballot_sync(FULL, ok);
+          if (tid == 0) sh.nready = mask == FULL ? 32 : __ffs(~mask) - 1;
         }
+        __syncthreads();
+        const int n = sh.nready;
+        if (n == 0) { __nanosleep(200); __syncthreads(); continue; }
+        ready_end = k + n;
+        staged = false;
       }
+      int fi, fj;
+      tile_of(k, fi, fj);
+      if (!staged) issue(fi, fj);
+      __syncthreads();    // the previous k-step's reads of sA/sB are complete (and sh.nready has been read by everybody)
+      reinterpret_cast<double2*>(sA)[tid] = ra[0]; reinterpret_cast<double2*>(sA)[tid + kFacThreads] = ra[1];
+      reinterpret_cast<double2*>(sB)[tid] = rb[0]; reinterpret_cast<double2*>(sB)[tid + kFacThreads] = rb[1];
       __syncthreads();
-      if (k == j - 1) LVI_TRACE(2);
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) {
-        const double xa = sA[a + 32 * m];
+      if (stamp && k == kend - 2) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
+      staged = k + 1 < ready_end;
+      if (staged) { int nfi, nfj; tile_of(k + 1, nfi, nfj); issue(nfi, nfj); }
+      rank32_update_2x2(sA, sB, rp, cp, acc);
+      ++k;
+    }
+    if (kend - 1 >= kmin) {  // the freshest inputs -- the column that has only just been finished -- come as flagged copies
+      int fi, fj;
+      tile_of(kend - 1, fi, fj);
+      __syncthreads();    // the previous k-step's reads of sA/sB are complete
+      if (stamp) LVI_TRACE_AT(trow, 2);
+      fetch_ll_tile(ll_tile(S, fi), ep, eager, sA, fj == fi ? sB : nullptr);
+      if (fj != fi) fetch_ll_tile(ll_tile(S, fj), ep, eager, sB, nullptr);
+      __syncthreads();
+      if (stamp) LVI_TRACE_AT(trow, 3);
+      rank32_update_2x2(sA, sB, rp, cp, acc);
+    }
+    if (stamp) LVI_TRACE_AT(trow, 4);
+    if (band && s <= 1) {  // pre-accumulated diagonal / first sub-diagonal tile: hand it to the chain CTA
+      unsigned long long* dst = s == 0 ? ll_tile(S, tq) : ll_P(S, j);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[jj] = fma(-xa, sB[c0 + 8 * jj + 32 * m], acc[jj]);
-      }
+      for (int q4 = 0; q4 < 4; ++q4) ll_store(dst + 2 * acc_elem(rp, cp, q4), acc[q4], ep);
+      if (stamp) LVI_TRACE_AT(trow, 7);
+      continue;
     }
     __syncthreads();
-    LVI_TRACE(3);
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = acc[jj];
-    __syncthreads();
-    if (s == 0) {  // diagonal task: L_jj and W_j = L_jj^-1 (only W is kept: panel solves and the back substitution multiply by it)
-      if (tid == 64) s_progress = 0;
-      __syncthreads();
-      if (tid < 32) {
-        const bool ok = warp_potrf_cols(sA, 32, sM, sR, &s_progress);
-        if (!ok && tid == 0) *S.fail = 1;
-      } else if (tid < 64) {
-        warp_inverse_cols(sM, sR, &s_progress, sW);
-      }
-      __syncthreads();
-      LVI_TRACE(4);
-      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
-      unsigned long long* wll = WLL + static_cast<size_t>(j) * 2 * kTileElems;
-      for (int e = tid; e < kTileElems; e += kFacThreads) ll_store(wll + 2 * e, sW[(e & 31) * kLP + (e >> 5)]);   // the chain's copy first
-      for (int e = tid; e < kTileElems; e += kFacThreads) Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
-      __syncthreads();  // bar.sync orders every thread's stores before thread 0's (cumulative) release
-      if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
-      LVI_TRACE(7);
-    } else {       // panel task: X = P W_j^T
-      const bool chain_tile = band && s == 1;   // the first sub-diagonal tile is on the pivot chain
-      if (chain_tile) {
-        const unsigned long long* wll = WLL + static_cast<size_t>(j) * 2 * kTileElems;
-        double v[4];
-        ll_load_n<4>(wll + 2 * tid, 2 * kFacThreads, v);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) sW[a * kLP + c0 + 8 * q4] = v[q4];   // element e = tid + 256 q4: row e & 31 = a, column e >> 5
-        LVI_TRACE(4);
-      } else {
-        if (tid == 0) spin_until_set(flags + j * S.TPC, false);
+    for (int q4 = 0; q4 < 4; ++q4) sA[acc_elem(rp, cp, q4)] = acc[q4];
+    {  // W_j, transposed into sW[c * kLP + m]
+      const unsigned long long* wll = ll_W(S, j);
+      if (!eager) {
+        if (tid == 0) {
+          unsigned long long w0, w1;
+          while (true) {
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(wll) : "memory");
+            if (ll_valid(w0, w1, ep)) break;
+            __nanosleep(200);
+          }
+        }
         __syncthreads();
-        LVI_TRACE(4);
-        const double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
-        for (int e = tid; e < kTileElems; e += kFacThreads) sW[(e & 31) * kLP + (e >> 5)] = __ldcg(Wg + e);
       }
+      double v[4];
+      ll_load_n<4>(wll + 2 * tid, 2 * kFacThreads, v, ep);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) sW[a * kLP + c0 + 8 * q4] = v[q4];   // element e = tid + 256 q4: row e & 31 = a, column e >> 5
+    }
+    if (stamp) LVI_TRACE_AT(trow, 5);
+    __syncthreads();
+    double out[4];
+    panel_times_winv_t(sA, sW, a, c0, out);
+    {
+      unsigned long long* sll = ll_tile(S, tq);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int e = a + 32 * (c0 + 8 * jj);
+        ll_store(sll + 2 * e, out[jj], ep);
+        tile[e] = out[jj];
+      }
+    }
+    if (stamp) LVI_TRACE_AT(trow, 7);
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
+    if (stamp) LVI_TRACE_AT(trow, 1);   // ready flag released
+    if (!band) {  // border tile rb of column j: its share of the corner's Schur complement, C(rb, bj) -= Lb(rb,j) Lb(bj,j)^T for bj <= rb
+      const int rb = s - S.T - 1;
       __syncthreads();
-      LVI_TRACE(5);
-      double out[4] = {0.0, 0.0, 0.0, 0.0};   // X(a, c) = sum_{m <= c} P(a, m) W(c, m), c = c0 + 8 jj: four chains, warp-uniform bounds
 #pragma unroll
-      for (int seg = 0; seg < 4; ++seg) {
-#pragma unroll
-        for (int mm = 0; mm < 8; ++mm) {
-          const int m = seg * 8 + mm;
+      for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = out[jj];   // own finished tile stays in shared memory
+      for (int bj = 0; bj <= rb; ++bj) {
+        if (j < sep_first && bj < RBsep) continue;   // zero separator tile: the product vanishes
+        const double* Xb_s = sA;
+        if (bj < rb) {
+          const int fb = j * S.TPC + S.T + 1 + bj;
+          if (tid == 0) spin_until_set(flags + fb, false);
+          __syncthreads();
+          const double2* Xb = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fb) * kTileElems);
+          for (int e = tid; e < kTileElems / 2; e += kFacThreads) reinterpret_cast<double2*>(sB)[e] = __ldcg(Xb + e);
+          Xb_s = sB;
+        }
+        __syncthreads();
+        double pr[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int m = 0; m < 32; ++m) {
           const double xa = sA[a + 32 * m];
 #pragma unroll
-          for (int jj = seg + 1; jj < 4; ++jj) out[jj] = fma(xa, sW[(c0 + 8 * jj) * kLP + m], out[jj]);
-          if (mm <= c0) out[seg] = fma(xa, sW[(c0 + 8 * seg) * kLP + m], out[seg]);
+          for (int jj = 0; jj < 4; ++jj) pr[jj] = fma(xa, Xb_s[c0 + 8 * jj + 32 * m], pr[jj]);
         }
-      }
-      if (chain_tile) {
-        unsigned long long* sll = SubLL + static_cast<size_t>(j) * 2 * kTileElems;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) ll_store(sll + 2 * (a + 32 * (c0 + 8 * jj)), out[jj]);
-      }
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) tile[a + 32 * (c0 + 8 * jj)] = out[jj];
-      LVI_TRACE(6);
-      __syncthreads();
-      if (tid == 0) { __threadfence(); st_release(flags + tq, 1); }
-      LVI_TRACE(7);
-      if (!band) {  // border tile rb of column j: its share of the corner's Schur complement, C(rb, bj) -= Lb(rb,j) Lb(bj,j)^T for bj <= rb
-        const int rb = s - S.T - 1;
+        for (int jj = 0; jj < 4; ++jj)
+          if (pr[jj] != 0.0) atomicAdd(S.C + 32 * rb + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
         __syncthreads();
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) sA[a + 32 * (c0 + 8 * jj)] = out[jj];   // own finished tile stays in shared memory
-        for (int bj = 0; bj <= rb; ++bj) {
-          if (j < sep_first && bj < RBsep) continue;   // zero separator tile: the product vanishes
-          const double* Xb_s = sA;
-          if (bj < rb) {
-            const int fb = j * S.TPC + S.T + 1 + bj;
-            if (tid == 0) spin_until_set(flags + fb, false);
-            __syncthreads();
-            const double2* Xb = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fb) * kTileElems);
-            for (int e = tid; e < kTileElems / 2; e += kFacThreads) reinterpret_cast<double2*>(sB)[e] = __ldcg(Xb + e);
-            Xb_s = sB;
-          }
-          __syncthreads();
-          double pr[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int m = 0; m < 32; ++m) {
-            const double xa = sA[a + 32 * m];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) pr[jj] = fma(xa, Xb_s[c0 + 8 * jj + 32 * m], pr[jj]);
-          }
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            if (pr[jj] != 0.0) atomicAdd(S.C + 32 * rb + a + static_cast<size_t>(S.ldc) * (32 * bj + c0 + 8 * jj), -pr[jj]);
-          __syncthreads();
-        }
       }
     }
   }
@@ -681,13 +926,16 @@ static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads, size_t s
 static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) {
   cudaStream_t st = ctx->stream;
   if (A.NT == 0) return;
-  LVI_REQUIRE(A.work_i && A.work_d, LVI_ERR_INVALID, "band solver workspace missing");
+  LVI_REQUIRE(A.work_i && A.work_d && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
+  static std::atomic<unsigned> epoch_counter{0};
+  do { A.epoch = ++epoch_counter; } while (A.epoch == 0);   // flag value of this factorisation's flagged tile copies (never cleared)
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
   constexpr size_t smem = 0;
   static int resident = 0;
   if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
-  const int grid = std::min(resident, A.NT * A.TPC);
+  const int n_chains = (A.NT0 > 0 && A.NT0 < A.NT) ? 2 : 1;
+  const int grid = std::max(n_chains + 1, std::min(resident, A.NT * A.TPC + n_chains));   // chain CTAs (always resident) + workers
   const char* trace_path = allow_trace ? std::getenv("LVI_TRACE_FACTOR") : nullptr;
   if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]
     const size_t n = static_cast<size_t>(A.NT) * A.TPC * 8;
@@ -698,8 +946,11 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
     LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, At);
     std::vector<unsigned long long> h(n);
     tr.download(h.data(), n, st);
+    int chain_sm[2] = {0, 0};
+    LVI_CUDA(cudaMemcpyAsync(chain_sm, A.work_i + static_cast<size_t>(A.NT) * A.TPC + A.NT + 2, sizeof(chain_sm), cudaMemcpyDeviceToHost, st));
     LVI_CUDA(cudaStreamSynchronize(st));
     if (FILE* f = std::fopen(trace_path, "wb")) { const int hdr[4] = {A.NT, A.TPC, A.T, A.RB}; std::fwrite(hdr, sizeof(int), 4, f); std::fwrite(h.data(), 8, n, f); std::fclose(f); }
+    std::fprintf(stderr, "[lvi] factor trace: chain CTAs on SM %d and %d, grid %d\n", chain_sm[0] - 1, chain_sm[1] - 1, grid);
     return;
   }
   LVI_LAUNCH(ctx, band_factor_ll_kernel, grid, kFacThreads, smem, A);
@@ -1113,6 +1364,9 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start
     DBuf<int> wi(S.work_i_count());
     DBuf<double> wd(std::max<size_t>(S.work_d_count(), 1));
     S.work_i = wi.p; S.work_d = wd.p;
+    DBuf<unsigned long long> ll1(std::max<size_t>(S.ll_count(), 1)), ll2;
+    ll1.zero(ctx->stream);
+    S.ll = ll1.p; S.epoch = 0;
     BandSys S2{};
     DBuf<double> t2, c2, l2, x2v, wd2;
     DBuf<int> wi2;
@@ -1122,6 +1376,8 @@ int lvi_band_solve_dense(lvi_ctx* ctx, int nb, int nbo, int bw, int chain1_start
       l2.alloc(static_cast<size_t>(S2.NT) * kTileElems); x2v.alloc(static_cast<size_t>(S2.NT) * kTile + S2.ldc);
       wi2.alloc(S2.work_i_count()); wd2.alloc(S2.work_d_count());
       S2.tiles = t2.p; S2.C = c2.p; S2.Linv = l2.p; S2.x = x2v.p; S2.fail = fail.p; S2.work_i = wi2.p; S2.work_d = wd2.p;
+      ll2.alloc(std::max<size_t>(S2.ll_count(), 1)); ll2.zero(ctx->stream);
+      S2.ll = ll2.p; S2.epoch = 0;
     }
     band_factor_solve(ctx, S, S2);
     std::vector<double> hx(x.n);
