@@ -305,14 +305,44 @@ __device__ __forceinline__ bool helper_fetch_tile(const unsigned long long* src,
   return true;
 }
 
+constexpr int kBufLd = 32 * kLP;   // one staging buffer: a 32x32 tile (8 KB, TMA destination) or a padded 32x33 tile
+constexpr int kStages = 3;
 struct FacShared {
-  double sA[kTileElems], sB[kTileElems], sD[kTileElems];
-  double sM[32 * kLP], sW[32 * kLP], sR[32];
+  double buf[2 * kStages][kBufLd];   // workers: kStages x (A tile, B tile) filled by bulk async copies; chain CTA: sA, sB, sD, sM
+  double sW[32 * kLP], sR[32];
+  unsigned long long full[kStages];  // mbarriers: "stage filled"
   int q;
   volatile int progress;
   int leave;
   int nready;
 };
+
+// ---- bulk async copies (TMA, 1-D) global -> shared with mbarrier completion
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
 
 // acc(2x2 block of rows 2rp.., columns 2cp..) -= A(rows, :) B(cols, :)^T over one 32-wide k-step, A in sA[r + 32 m], B in sB[c + 32 m].
 // 2x2 register blocking with 16-byte shared-memory loads: 3 shared-memory wavefronts per 4 DFMA instead of the 6 of a 1x4 blocking -- the
@@ -363,7 +393,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
   const unsigned ep = S.epoch;
   const int c_start = chain == 0 ? 0 : S.NT0, c_end = chain == 0 ? S.NT0 : S.NT;
   const bool coupled = S.T >= 1;
-  double* sA = sh.sA; double* sB = sh.sB; double* sW = sh.sW;
+  double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sD = sh.buf[2]; double* sM = sh.buf[3]; double* sW = sh.sW;
   bool have_next = false;   // Dpre_j already in sh.sD (fetched under the previous column's Cholesky)
   int pending = -1;         // column whose ready flags still have to be released
   bool pending_panel = false;
@@ -381,11 +411,11 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
         double v[4];
         ll_load_n<4>(ll_tile(S, tq) + 2 * tid, 2 * kFacThreads, v, ep);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) sh.sD[tid + kFacThreads * q4] = v[q4];
+        for (int q4 = 0; q4 < 4; ++q4) sD[tid + kFacThreads * q4] = v[q4];
         __syncthreads();
       }
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sh.sD[acc_elem(rp, cp, q4)];
+      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sD[acc_elem(rp, cp, q4)];
       LVI_TRACE(1);
       rank32_update_2x2(sA, sA, rp, cp, acc);   // X_{j-1} is still in sA
       __syncthreads();
@@ -398,10 +428,10 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
     const bool has_panel = coupled && j + 1 < c_end;
     int got_next = 1;
     if (tid < 32) {
-      const bool ok = warp_potrf_cols(sA, 32, sh.sM, sh.sR, &sh.progress);
+      const bool ok = warp_potrf_cols(sA, 32, sM, sh.sR, &sh.progress);
       if (!ok && tid == 0) *S.fail = 1;
     } else if (tid < 64) {
-      warp_inverse_cols(sh.sM, sh.sR, &sh.progress, sW);
+      warp_inverse_cols(sM, sh.sR, &sh.progress, sW);
     } else if (tid < 224) {
       if (has_panel) {
         if (j == c_start) {
@@ -410,7 +440,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
         } else {
           helper_fetch_tile<true>(ll_P(S, j), ep, sB, tid - 64, &sh.progress);
         }
-        got_next = helper_fetch_tile<false>(ll_tile(S, tq + S.TPC), ep, sh.sD, tid - 64, &sh.progress) ? 1 : 0;
+        got_next = helper_fetch_tile<false>(ll_tile(S, tq + S.TPC), ep, sD, tid - 64, &sh.progress) ? 1 : 0;
       }
     } else if (tid == 224 && pending >= 0) {
       __threadfence();
@@ -468,7 +498,8 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
 // factor_chain).  Tasks are fetched in dependency order and the chain CTAs are resident from the start, so a fetched task only ever
 // waits on work that is already running: no deadlock for any grid size.
 __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys S) {
-  __shared__ __align__(16) FacShared sh;
+  extern __shared__ __align__(128) unsigned char fac_smem[];
+  FacShared& sh = *reinterpret_cast<FacShared*>(fac_smem);
   int* flags = S.work_i;
   int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT;
   int* chain_sm = counter + 2;   // [2] SM id + 1 of the chain CTAs
@@ -497,7 +528,13 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   }
   __syncthreads();
   if (sh.leave) return;
-  double* sA = sh.sA; double* sB = sh.sB; double* sW = sh.sW;
+  double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sW = sh.sW;
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) mbar_init(&sh.full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned g = 0;   // pipelined update steps this CTA has run so far: step n uses stage n % kStages, mbarrier phase (n / kStages) & 1
   while (true) {
     if (tid == 0) sh.q = atomicAdd(counter, 1);
     __syncthreads();
@@ -528,46 +565,49 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
     const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
     const int kend = (band && s == 0) ? j - 1 : j;   // the diagonal task leaves the last contribution (X_{j-1}) to the chain CTA
-    // Updates from the older columns: the two source tiles of step k+1 travel from L2 into registers while step k is multiplied (their
-    // ready flags are checked inside the barrier that step k needs anyway); the LAST update takes the flagged copies.
-    double2 ra[2], rb[2];
-    bool staged = false;   // ra / rb hold the tiles of the step about to run
+    // Updates from the older columns: their source tiles are staged into shared memory by bulk async copies (TMA) running two steps
+    // ahead of the arithmetic, one elected thread issuing them as soon as the ready flags allow (one warp looks at the flags of up to 32
+    // steps at once: one L2 round trip per batch, not per step).  The LAST update takes the flagged copies (below).
     auto tile_of = [&](int k, int& fi, int& fj) { fi = k * S.TPC + (band ? i - k : s); fj = k * S.TPC + (j - k); };
-    auto issue = [&](int fi, int fj) {
-      const double2* Li = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fi) * kTileElems);
-      const double2* Lj = reinterpret_cast<const double2*>(S.tiles + static_cast<size_t>(fj) * kTileElems);
-      ra[0] = __ldcg(Li + tid); ra[1] = __ldcg(Li + tid + kFacThreads);
-      rb[0] = __ldcg(Lj + tid); rb[1] = __ldcg(Lj + tid + kFacThreads);
-    };
-    int ready_end = kmin;  // the source tiles of steps [k, ready_end) are known to be published
-    for (int k = kmin; k < kend - 1;) {
-      if (k >= ready_end) {  // one warp looks at the ready flags of the next (up to 32) steps at once: one L2 round trip per batch, not per step
-        if (tid < 32) {
-          const int kk = k + tid;
+    const int n_old = max(kend - 1 - kmin, 0);
+    int issued = 0, ready_n = 0;   // warp 0: steps issued / steps known to be published
+    auto try_issue = [&](int upto) {   // warp 0 only
+      upto = min(upto, n_old);
+      while (issued < upto) {
+        if (issued >= ready_n) {
+          const int kk = kmin + issued + a;
           bool ok = false;
           if (kk < kend - 1) { int fi, fj; tile_of(kk, fi, fj); ok = ld_acquire(flags + fi) != 0 && ld_acquire(flags + fj) != 0; }
           const unsigned mask = __ballot_sync(FULL, ok);
-          if (tid == 0) sh.nready = mask == FULL ? 32 : __ffs(~mask) - 1;
+          const int n = mask == FULL ? 32 : __ffs(~mask) - 1;
+          if (n == 0) return;
+          ready_n = issued + n;
         }
-        __syncthreads();
-        const int n = sh.nready;
-        if (n == 0) { __nanosleep(200); __syncthreads(); continue; }
-        ready_end = k + n;
-        staged = false;
+        if (a == 0) {
+          int fi, fj;
+          tile_of(kmin + issued, fi, fj);
+          const unsigned st = (g + issued) % kStages;
+          asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above orders the generic proxy; the copy reads through the async proxy
+          mbar_expect_tx(&sh.full[st], fi == fj ? 8192u : 16384u);
+          tma_load_1d(sh.buf[2 * st], S.tiles + static_cast<size_t>(fi) * kTileElems, 8192u, &sh.full[st]);
+          if (fi != fj) tma_load_1d(sh.buf[2 * st + 1], S.tiles + static_cast<size_t>(fj) * kTileElems, 8192u, &sh.full[st]);
+        }
+        ++issued;
       }
-      int fi, fj;
-      tile_of(k, fi, fj);
-      if (!staged) issue(fi, fj);
-      __syncthreads();    // the previous k-step's reads of sA/sB are complete (and sh.nready has been read by everybody)
-      reinterpret_cast<double2*>(sA)[tid] = ra[0]; reinterpret_cast<double2*>(sA)[tid + kFacThreads] = ra[1];
-      reinterpret_cast<double2*>(sB)[tid] = rb[0]; reinterpret_cast<double2*>(sB)[tid + kFacThreads] = rb[1];
-      __syncthreads();
-      if (stamp && k == kend - 2) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
-      staged = k + 1 < ready_end;
-      if (staged) { int nfi, nfj; tile_of(k + 1, nfi, nfj); issue(nfi, nfj); }
-      rank32_update_2x2(sA, sB, rp, cp, acc);
-      ++k;
+    };
+    if (tid < 32) try_issue(2);
+    for (int t = 0; t < n_old; ++t) {
+      if (tid < 32) {   // stage (t + 2) % kStages was released by the barrier that ended step t - 1
+        try_issue(t + 3);
+        while (issued <= t) { __nanosleep(200); try_issue(t + 3); }
+      }
+      const unsigned st = (g + t) % kStages;
+      mbar_wait(&sh.full[st], ((g + t) / kStages) & 1u);
+      if (stamp && t == n_old - 1) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
+      rank32_update_2x2(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rp, cp, acc);
+      __syncthreads();   // everybody is done with this stage
     }
+    g += n_old;
     if (kend - 1 >= kmin) {  // the freshest inputs -- the column that has only just been finished -- come as flagged copies
       int fi, fj;
       tile_of(kend - 1, fi, fj);
@@ -931,9 +971,12 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
   do { A.epoch = ++epoch_counter; } while (A.epoch == 0);   // flag value of this factorisation's flagged tile copies (never cleared)
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
-  constexpr size_t smem = 0;
+  constexpr size_t smem = sizeof(FacShared);
   static int resident = 0;
-  if (!resident) resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
+  if (!resident) {
+    LVI_CUDA(cudaFuncSetAttribute(band_factor_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
+  }
   const int n_chains = (A.NT0 > 0 && A.NT0 < A.NT) ? 2 : 1;
   const int grid = std::max(n_chains + 1, std::min(resident, A.NT * A.TPC + n_chains));   // chain CTAs (always resident) + workers
   const char* trace_path = allow_trace ? std::getenv("LVI_TRACE_FACTOR") : nullptr;
