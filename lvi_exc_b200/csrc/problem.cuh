@@ -41,6 +41,7 @@ struct BandSys {
   // allocation, valid words carry the epoch of the factorisation that wrote them
   unsigned long long* ll;
   unsigned epoch;
+  int pre_shift;     // column slots by which the pre-accumulation tasks are queued ahead of their column (set per launch)
   size_t ll_count() const { return (static_cast<size_t>(NT) * TPC + 2 * static_cast<size_t>(NT)) * 2 * kTileElems; }
 };
 

@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   int* chain_sm = counter + 2;   // [2] SM id + 1 of the chain CTAs
   const unsigned ep = S.epoch;
   const int n_chains = (S.NT0 > 0 && S.NT0 < S.NT) ? 2 : 1;
-  const int ntask = S.NT * S.TPC;
+  const int ntask = (S.NT + S.pre_shift) * S.TPC;
   const int tid = threadIdx.x;
   const int a = tid & 31, c0 = tid >> 5;
   const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
@@ -541,7 +541,13 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     const int q = sh.q;
     __syncthreads();
     if (q >= ntask) break;
-    const int jo = q / S.TPC, s = q - jo * S.TPC;
+    // The two pre-accumulation tasks of a column are what the chain waits for, and like every task they run ~T sequential updates: they
+    // are queued pre_shift column slots EARLIER than the other tiles of their column, so that only their last update is left when the
+    // chain arrives.  (Their inputs from the last two columns are then produced by tasks LATER in the queue; the host picks pre_shift so
+    // that the resident workers always cover that span, which keeps the no-deadlock argument intact.)
+    const int slot = q / S.TPC, s = q - slot * S.TPC;
+    const int jo = (s <= 1 && s <= S.T) ? slot : slot - S.pre_shift;
+    if (jo < 0 || jo >= S.NT) continue;
     const int j = ordered_column(jo, S.NT0, S.NT);
     const int c_start = j < S.NT0 ? 0 : S.NT0, c_end = j < S.NT0 ? S.NT0 : S.NT;   // the chain this column belongs to
     const bool band = s <= S.T;
@@ -978,7 +984,11 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
   }
   const int n_chains = (A.NT0 > 0 && A.NT0 < A.NT) ? 2 : 1;
-  const int grid = std::max(n_chains + 1, std::min(resident, A.NT * A.TPC + n_chains));   // chain CTAs (always resident) + workers
+  // column slots by which the pre-accumulation tasks run ahead: at most 3, and the workers must cover that many slots twice over
+  const int live_per_slot = n_chains * (A.T + 1 + std::max(1, A.RB - (A.n_mid >> kTileLog)));
+  A.pre_shift = std::max(0, std::min(3, (resident - n_chains) / live_per_slot - 2));
+  if (std::getenv("LVI_PRE_SHIFT")) A.pre_shift = std::atoi(std::getenv("LVI_PRE_SHIFT"));   // diagnostics
+  const int grid = std::max(n_chains + 1, std::min(resident, (A.NT + A.pre_shift) * A.TPC + n_chains));   // chain CTAs (always resident) + workers
   const char* trace_path = allow_trace ? std::getenv("LVI_TRACE_FACTOR") : nullptr;
   if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]
     const size_t n = static_cast<size_t>(A.NT) * A.TPC * 8;
