@@ -42,7 +42,8 @@ struct BandSys {
   unsigned long long* ll;
   unsigned epoch;
   int pre_shift;     // column slots by which the pre-accumulation tasks are queued ahead of their column (set per launch)
-  size_t ll_count() const { return (static_cast<size_t>(NT) * TPC + 2 * static_cast<size_t>(NT)) * 2 * kTileElems; }
+  // ... followed by the flagged vectors of the back substitution (x_m and u_m, 32 values = 64 words each per column)
+  size_t ll_count() const { return (static_cast<size_t>(NT) * TPC + 2 * static_cast<size_t>(NT)) * 2 * kTileElems + static_cast<size_t>(NT) * 4 * kTile; }
 };
 
 // address of H(i,j), i >= j, positions in [0, nb+nbo]; position nb+nbo is the rhs row

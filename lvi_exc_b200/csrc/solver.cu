@@ -703,103 +703,162 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   }
 }
 
-// ---- flag-driven backward substitution: x_m = W_m^T (z_m - Lb(:,m)^T x2 - sum_d L(m+d,m)^T x_{m+d}) ------------------------------------
-// One task per block column, fetched in descending order.  A task stages W_m and its first sub-diagonal tile in shared memory while it
-// waits for the contributions of columns m+1..m+T (arrival counter), computes x_m, then pushes L(m,k)^T x_m into the partial sums of
-// k = m-1 (first: it is the dependency chain), m-2, ... m-T with one warp per tile.
-__global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
-  extern __shared__ double smem[];
-  constexpr int kLD = kTile + 1;      // padded: thread c walks column c, so consecutive threads must hit different banks
-  double* sW = smem;                  // W_m, column-major 64 x 64 (ld 65)
-  double* sT = sW + kTile * kLD;      // tile (m, m-1) (ld 65)
-  double* x2s = sT + kTile * kLD;     // border solution [ldc <= 1024]
-  __shared__ double sx[kTile], sv[kTile];
-  __shared__ int s_q;
-  int* arrivals = S.work_i + static_cast<size_t>(S.NT) * S.TPC;
-  int* counter = arrivals + S.NT + 1;
-  double* vsum = S.work_d;
-  unsigned long long* mailbox = reinterpret_cast<unsigned long long*>(S.work_d + static_cast<size_t>(S.NT) * kTile);   // [NT][32][2]
-  double* x = S.x;
+// ---- backward substitution: x_m = W_m^T (z_m - Lb(:,m)^T x2 - sum_{d=1..T} L(m+d,m)^T x_{m+d}),  m descending along each chain ------
+// The recurrence is serial in m, so its cost is (number of block columns) x (latency of one step).  One CTA per chain walks its columns
+// and does only what depends on the LATEST solutions: the products with the kBsLocal nearest sub-diagonal tiles and with W_m, on tiles
+// that bulk async copies (TMA) stage into shared memory two columns ahead -- x_{m+1} never leaves the CTA on its way to x_m.  Everything
+// else of a column (the border part, the rhs, and the products with the tiles further down, whose x are at least kBsLocal + 1 steps
+// old) is one task of a worker CTA, which hands u_m = z_m - Lb^T x2 - sum_{d > kBsLocal} ... to the chain as a flagged vector; workers
+// pick up each x_m as a flagged vector as well.  (The previous version passed x_m from CTA to CTA through a flagged mailbox: ~1 us of
+// hand-off plus a one-warp product per column, 4.4 us per column; this one is bound by the chain SM's copy bandwidth, ~0.5 us per column.)
+constexpr int kBsLocal = 6;
+constexpr int kBsStages = 3;
+struct BsShared {
+  double tiles[kBsStages][kBsLocal + 1][kTileElems];   // [stage][0] = W_m, [stage][d] = L(m+d, m)
+  double x2s[1024];                                      // border solution (workers)
+  double xring[kBsLocal + 1][kTile];                     // chain: the last kBsLocal + 1 solutions, slot = column % (kBsLocal + 1)
+  double su[kTile], sl[kTile];
+  double sred[8][kTile], xv[8][kTile];                   // workers: per-warp partial sums / per-warp copy of one x_{m+d}
+  unsigned long long full[kBsStages];
+  int q;
+};
+__device__ __forceinline__ unsigned long long* bs_xll(const BandSys& S) { return S.ll + (static_cast<size_t>(S.NT) * S.TPC + 2 * static_cast<size_t>(S.NT)) * 2 * kTileElems; }
+__device__ __forceinline__ unsigned long long* bs_ull(const BandSys& S) { return bs_xll(S) + static_cast<size_t>(S.NT) * 2 * kTile; }
+
+__device__ void backsolve_chain(const BandSys& S, const int chain, BsShared& sh) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < S.ldc; i += 256) x2s[i] = x[static_cast<size_t>(S.NT) * kTile + i];
+  const unsigned ep = S.epoch;
+  const int c_start = chain == 0 ? 0 : S.NT0, c_end = chain == 0 ? S.NT0 : S.NT;
+  const int n_cols = c_end - c_start;
+  unsigned long long* xll = bs_xll(S);
+  const unsigned long long* ull = bs_ull(S);
+  auto issue = [&](int t) {   // one thread: stage W_m and the nearest sub-diagonal tiles of step t
+    const int m = c_end - 1 - t;
+    const int Dm = min(kBsLocal, min(S.T, t));
+    const int st = t % kBsStages;
+    mbar_expect_tx(&sh.full[st], static_cast<unsigned>(1 + Dm) * 8192u);
+    tma_load_1d(sh.tiles[st][0], S.Linv + static_cast<size_t>(m) * kTileElems, 8192u, &sh.full[st]);
+    if (Dm > 0) tma_load_1d(sh.tiles[st][1], S.tiles + (static_cast<size_t>(m) * S.TPC + 1) * kTileElems, static_cast<unsigned>(Dm) * 8192u, &sh.full[st]);
+  };
+  if (tid == 0) {
+    for (int st = 0; st < kBsStages; ++st) mbar_init(&sh.full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int t = 0; t < min(2, n_cols); ++t) issue(t);
+  }
+  // u_m arrives as a flagged vector: warp 0 keeps the loads of the next two steps in flight
+  unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  auto u_issue = [&](int t, unsigned long long& w0, unsigned long long& w1) {
+    w0 = w1 = 0;
+    if (t < n_cols) {
+      const unsigned long long* src = ull + (static_cast<size_t>(c_end - 1 - t) * kTile + lane) * 2;
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    }
+  };
+  if (warp == 0) { u_issue(0, a0, a1); u_issue(1, b0, b1); }
+  __syncthreads();
+  for (int t = 0; t < n_cols; ++t) {
+    const int m = c_end - 1 - t;
+    const int Dm = min(kBsLocal, min(S.T, t));
+    const int st = t % kBsStages;
+    if (tid == 0 && t + 2 < n_cols) issue(t + 2);   // its stage was released by the barrier that ended step t - 1
+    if (warp == 0) {
+      unsigned long long w0 = a0, w1 = a1;
+      a0 = b0; a1 = b1;
+      u_issue(t + 2, b0, b1);
+      const unsigned long long* src = ull + (static_cast<size_t>(m) * kTile + lane) * 2;
+      while (!ll_valid(w0, w1, ep)) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+      sh.su[lane] = ll_value(w0, w1);
+    }
+    mbar_wait(&sh.full[st], (t / kBsStages) & 1u);
+    double part[4] = {0.0, 0.0, 0.0, 0.0};   // lane = row r of the tiles, this warp's 4 columns; summed over the lanes afterwards
+    for (int d = 1; d <= Dm; ++d) {
+      const double* tl = sh.tiles[st][d];
+      const double xr = sh.xring[(m + d) % (kBsLocal + 1)][lane];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) part[cc] = fma(tl[lane + 32 * (4 * warp + cc)], xr, part[cc]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[cc] += __shfl_xor_sync(FULL, part[cc], o);
+    }
+    if (lane < 4) sh.sl[4 * warp + lane] = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+    __syncthreads();
+    const double vr = sh.su[lane] - sh.sl[lane];
+    const double* W = sh.tiles[st][0];
+    double xs[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      xs[cc] = W[lane + 32 * (4 * warp + cc)] * vr;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) xs[cc] += __shfl_xor_sync(FULL, xs[cc], o);
+    }
+    if (lane < 4) {
+      const int c = 4 * warp + lane;
+      const double xc = lane == 0 ? xs[0] : lane == 1 ? xs[1] : lane == 2 ? xs[2] : xs[3];
+      sh.xring[m % (kBsLocal + 1)][c] = xc;
+      ll_store(xll + (static_cast<size_t>(m) * kTile + c) * 2, xc, ep);
+      S.x[static_cast<size_t>(m) * kTile + c] = xc;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
+  extern __shared__ __align__(128) unsigned char bs_smem[];
+  BsShared& sh = *reinterpret_cast<BsShared*>(bs_smem);
+  const int n_chains = (S.NT0 > 0 && S.NT0 < S.NT) ? 2 : 1;
+  if (static_cast<int>(blockIdx.x) < n_chains) { backsolve_chain(S, blockIdx.x, sh); return; }
+  int* counter = S.work_i + static_cast<size_t>(S.NT) * S.TPC + S.NT + 1;
+  const unsigned ep = S.epoch;
+  const unsigned long long* xll = bs_xll(S);
+  unsigned long long* ull = bs_ull(S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < S.ldc; i += 256) sh.x2s[i] = S.x[static_cast<size_t>(S.NT) * kTile + i];
   const int zrb = S.nbo >> kTileLog, zrow = S.nbo & (kTile - 1);
+  const int RBsep = S.n_mid >> kTileLog;
   while (true) {
     __syncthreads();
-    if (tid == 0) s_q = atomicAdd(counter, 1);
+    if (tid == 0) sh.q = atomicAdd(counter, 1);
     __syncthreads();
-    const int q = s_q;
+    const int q = sh.q;
     if (q >= S.NT) break;
     const int m = ordered_column_desc(q, S.NT0, S.NT);
     const int c_start = m < S.NT0 ? 0 : S.NT0, c_end = m < S.NT0 ? S.NT0 : S.NT;
     const int Tm = min(S.T, c_end - 1 - m);
     const double* col = S.tiles + static_cast<size_t>(m) * S.TPC * kTileElems;
-    const double2* Wg = reinterpret_cast<const double2*>(S.Linv + static_cast<size_t>(m) * kTileElems);
-    for (int e = tid; e < kTileElems / 2; e += 256) {
-      const double2 v = Wg[e];
-      const int r = (2 * e) & (kTile - 1), c = (2 * e) >> kTileLog;
-      sW[r + kLD * c] = v.x; sW[r + 1 + kLD * c] = v.y;
-    }
-    if (m > c_start && S.T >= 1) {
-      const double2* t1 = reinterpret_cast<const double2*>(S.tiles + (static_cast<size_t>(m - 1) * S.TPC + 1) * kTileElems);
-      for (int e = tid; e < kTileElems / 2; e += 256) {
-        const double2 v = t1[e];
-        const int r = (2 * e) & (kTile - 1), c = (2 * e) >> kTileLog;
-        sT[r + kLD * c] = v.x; sT[r + 1 + kLD * c] = v.y;
+    const int rb0 = (m < max(c_start, c_end - S.T - 1)) ? RBsep : 0;   // zero separator tiles are skipped
+    const int n_border = S.RB - rb0, n_far = max(Tm - kBsLocal, 0);
+    double acc = 0.0;   // lane c: column c of this warp's share of the products
+    for (int it = warp; it < n_border + n_far; it += 8) {
+      const bool border = it < n_border;
+      const int d = border ? 0 : Tm - (it - n_border);   // far tiles from the oldest x to the newest
+      const double* tc = col + static_cast<size_t>(border ? S.T + 1 + rb0 + it : d) * kTileElems + kTile * lane;
+      double tv[kTile];
+#pragma unroll
+      for (int r = 0; r < kTile; ++r) tv[r] = tc[r];   // all loads in flight at once: one memory round trip per tile
+      const double* vec;
+      if (border) {
+        vec = sh.x2s + kTile * (rb0 + it);
+      } else {
+        sh.xv[warp][lane] = ll_load(xll + (static_cast<size_t>(m + d) * kTile + lane) * 2, ep);
+        __syncwarp();
+        vec = sh.xv[warp];
       }
-    }
-    // right-hand side minus the border part (independent of the chain): warps 0,1 own columns c = tid (< 64)
-    if (tid < kTile) {
-      double bsum = 0.0;
-      const int RBsep = S.n_mid >> kTileLog;
-      for (int rb = (m < max(c_start, c_end - S.T - 1)) ? RBsep : 0; rb < S.RB; ++rb) {   // zero separator tiles are skipped
-        const double* bt = col + static_cast<size_t>(S.T + 1 + rb) * kTileElems + kTile * tid;
-        const double* xv = x2s + kTile * rb;
-#pragma unroll 8
-        for (int r = 0; r < kTile; ++r) bsum = fma(bt[r], xv[r], bsum);
-      }
-      bsum = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + kTile * tid] - bsum;  // z_m - Lb^T x2
-      if (tid == 0) while (ld_acquire(arrivals + m) < Tm - 1) {}   // contributions of columns m+2.. (m+1 comes through the mailbox)
-      sv[tid] = bsum;
-    }
-    __syncthreads();
-    if (tid < kTile) {
-      double v = sv[tid] - __ldcg(vsum + static_cast<size_t>(m) * kTile + tid);
-      if (Tm >= 1) v -= ll_load(mailbox + (static_cast<size_t>(m) * kTile + tid) * 2);
-      sv[tid] = v;
-    }
-    __syncthreads();
-    if (tid < kTile) {
-      double x0 = 0.0, x1 = 0.0;   // column tid of W (zero above the diagonal): (W^T v)_tid, two independent accumulation chains
+      double u0 = 0.0, u1 = 0.0;
 #pragma unroll
-      for (int r = 0; r < kTile; r += 2) { x0 = fma(sW[r + kLD * tid], sv[r], x0); x1 = fma(sW[r + 1 + kLD * tid], sv[r + 1], x1); }
-      const double xk = x0 + x1;
-      sx[tid] = xk;
-      x[static_cast<size_t>(m) * kTile + tid] = xk;
-    }
-    __syncthreads();
-    const int nd = min(S.T, m - c_start);
-    for (int d = 1 + warp; d <= nd; d += 8) {
-      const int k = m - d;
-      const double* tl = (d == 1) ? sT : S.tiles + (static_cast<size_t>(k) * S.TPC + d) * kTileElems;
-      const int ldt = (d == 1) ? kLD : kTile;
-#pragma unroll
-      for (int h = 0; h < kTile / 32; ++h) {
-        const int c = lane + 32 * h;
-        const double* tc = tl + ldt * c;
-        double tv[kTile];
-#pragma unroll
-        for (int r = 0; r < kTile; ++r) tv[r] = tc[r];   // all loads in flight at once: one L2 round trip per tile, not four
-        double u0 = 0.0, u1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < kTile; r += 2) { u0 = fma(tv[r], sx[r], u0); u1 = fma(tv[r + 1], sx[r + 1], u1); }
-        const double u = u0 + u1;
-        if (d == 1) ll_store(mailbox + (static_cast<size_t>(k) * kTile + c) * 2, u);
-        else atomicAdd(vsum + static_cast<size_t>(k) * kTile + c, u);
-      }
-      if (d == 1) continue;
-      __threadfence();
+      for (int r = 0; r < kTile; r += 2) { u0 = fma(tv[r], vec[r], u0); u1 = fma(tv[r + 1], vec[r + 1], u1); }
+      acc += u0 + u1;
       __syncwarp();
-      if (lane == 0) atomicAdd(arrivals + k, 1);
+    }
+    sh.sred[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += sh.sred[w][lane];
+      const double z = col[static_cast<size_t>(S.T + 1 + zrb) * kTileElems + zrow + kTile * lane];
+      ll_store(ull + (static_cast<size_t>(m) * kTile + lane) * 2, z - tot, ep);
     }
   }
 }
@@ -969,12 +1028,17 @@ static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads, size_t s
   LVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   return std::max(1, per_sm) * ctx->sm_count;
 }
+static unsigned next_epoch() {
+  static std::atomic<unsigned> epoch_counter{0};
+  unsigned e;
+  do { e = ++epoch_counter; } while (e == 0);
+  return e;
+}
 static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) {
   cudaStream_t st = ctx->stream;
   if (A.NT == 0) return;
   LVI_REQUIRE(A.work_i && A.work_d && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
-  static std::atomic<unsigned> epoch_counter{0};
-  do { A.epoch = ++epoch_counter; } while (A.epoch == 0);   // flag value of this factorisation's flagged tile copies (never cleared)
+  A.epoch = next_epoch();   // flag value of this factorisation's flagged tile copies (never cleared)
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
   constexpr size_t smem = sizeof(FacShared);
@@ -1010,14 +1074,16 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
 }
 static void band_backsolve_only(lvi_ctx* ctx, BandSys& A) {
   if (A.NT == 0) return;
-  constexpr size_t smem = (2 * kTile * (kTile + 1) + 1024) * sizeof(double);
+  LVI_REQUIRE(A.work_i && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
+  constexpr size_t smem = sizeof(BsShared);
   static int resident = 0;
   if (!resident) {
     LVI_CUDA(cudaFuncSetAttribute(band_backsolve_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256, smem);
   }
-  // one CTA per SM: co-resident CTAs that only spin on their arrival counters slow the working one down (measured 2x in the factorisation)
-  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::min(std::min(resident, ctx->sm_count), A.NT), 256, smem, A);
+  A.epoch = next_epoch();   // flag value of this substitution's flagged vectors
+  const int n_chains = (A.NT0 > 0 && A.NT0 < A.NT) ? 2 : 1;
+  LVI_LAUNCH(ctx, band_backsolve_ll_kernel, std::max(n_chains + 1, std::min(resident, A.NT + n_chains)), 256, smem, A);
 }
 void init_second_level(const BandSys& A, BandSys& B) {
   B = BandSys{};
