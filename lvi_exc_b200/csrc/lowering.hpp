@@ -39,6 +39,7 @@ struct LoweredTable {
   int n = 0, active = 1;
   std::vector<int> i0a, i0b, ia, ib;
   std::vector<double> ua, ub, v, weight, huber;
+  std::vector<int> perm;   // optional evaluation order of the normal-equation kernel (residuals with equal spline windows next to each other)
 };
 
 struct Lowered {
@@ -314,6 +315,14 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     for (int l = 0; l < nl; ++l) L.row_start[l + 1] = L.row_start[l] + ((T.active && l < d.n_landmarks && L.pos_rho[l] >= 0 && cnt[l] > 0) ? 30 + 24 * cnt[l] : 0);
     L.row_pos.assign(std::max(L.row_start[nl], 1), -1);
   }
+  // Camera residuals arrive landmark by landmark, so neighbours almost never share both spline windows and the normal-equation kernel
+  // cannot merge their J^T J before its atomics.  Its evaluation order is therefore sorted by window pair (the tables keep their order).
+  {
+    LoweredTable& T = L.tab[RT_CAM];
+    T.perm.resize(T.n);
+    for (int i = 0; i < T.n; ++i) T.perm[i] = i;
+    std::stable_sort(T.perm.begin(), T.perm.end(), [&](int x, int y) { return T.i0a[x] != T.i0a[y] ? T.i0a[x] < T.i0a[y] : T.i0b[x] < T.i0b[y]; });
+  }
   // ---- residual vector layout + bandwidth
   int ro = 0, nblk = 0;
   for (int t = 0; t < RT_COUNT; ++t) { L.res_offset[t] = ro; ro += L.tab[t].n * rt_rows(t); nblk += L.tab[t].n; }
@@ -331,7 +340,7 @@ inline ProblemView host_view(const lvi_problem_desc& d, const Lowered& L, const 
     const LoweredTable& T = L.tab[t];
     ResTable& R = P.tab[t];
     R.n = T.n; R.lo = 0; R.hi = T.n; R.active = T.active; R.i0a = T.i0a.data(); R.ua = T.ua.data(); R.i0b = T.i0b.data(); R.ub = T.ub.data(); R.v = T.v.data();
-    R.ia = T.ia.data(); R.ib = T.ib.data(); R.weight = T.weight.data(); R.huber = T.huber.empty() ? nullptr : T.huber.data();
+    R.ia = T.ia.data(); R.ib = T.ib.data(); R.perm = nullptr; R.weight = T.weight.data(); R.huber = T.huber.empty() ? nullptr : T.huber.data();
   }
   P.pos_r3 = L.pos_r3.data(); P.pos_so3 = L.pos_so3.data(); P.pos_rho = L.pos_rho.data();
   for (int b = 0; b < TB_COUNT; ++b) P.pos_sens[b] = L.pos_sens[b];

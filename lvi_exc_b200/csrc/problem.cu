@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
   double cost_acc = 0.0;
   const int stride = gridDim.x * kLinWarps * 32;
   for (int base = T.lo + (blockIdx.x * kLinWarps + warp) * 32; base < T.hi; base += stride) {
-    const int i = base + lane;
-    const bool valid = i < T.hi;
+    const bool valid = base + lane < T.hi;
+    const int i = valid ? (T.perm ? T.perm[base + lane] : base + lane) : 0;
     long long key = -1;
     if (valid) {
       ResOut o;
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
       const int s = __ffs(heads) - 1;
       heads &= heads - 1;
       const int e = heads ? (__ffs(heads) - 1) : nvalid;
-      for (int c = lane; c < COLS; c += 32) posw[c] = col_pos<TYPE>(P, base + s, c);
+      const int i_head = __shfl_sync(FULL, i, s);
+      for (int c = lane; c < COLS; c += 32) posw[c] = col_pos<TYPE>(P, i_head, c);
       __syncwarp();
       constexpr int NP = SC * (SC + 1) / 2;
       for (int p = lane; p < NP; p += 32) {
@@ -115,11 +116,12 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
       }
       if (TYPE == RT_CAM) {  // inverse-depth column: one parameter per landmark, kept out of the band (eliminated by Schur complement)
         for (int r = s; r < e; ++r) {
-          const int lm = T.ia[base + r];
+          const int ir = __shfl_sync(FULL, i, r);
+          const int lm = T.ia[ir];
           const int pr = P.pos_rho[lm];
           if (pr < 0) continue;
           const double* Jr = Jw + r * RC;
-          const int rs = SV.row_start[lm], obs_base = T.ib[base + r];
+          const int rs = SV.row_start[lm], obs_base = T.ib[ir];
           for (int c = lane; c <= SC; c += 32) {
             if (c < SC && posw[c] < 0) continue;
             double acc = 0.0;
@@ -391,7 +393,7 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
     ResTable& R = V.tab[t];
     R.n = T.n; R.active = T.active;
     shard_range(T.n, ctx->rank, ctx->world, R.lo, R.hi);
-    R.i0a = up_i(p->tab_i[t][0], T.i0a); R.i0b = up_i(p->tab_i[t][1], T.i0b); R.ia = up_i(p->tab_i[t][2], T.ia); R.ib = up_i(p->tab_i[t][3], T.ib);
+    R.i0a = up_i(p->tab_i[t][0], T.i0a); R.i0b = up_i(p->tab_i[t][1], T.i0b); R.ia = up_i(p->tab_i[t][2], T.ia); R.ib = up_i(p->tab_i[t][3], T.ib); R.perm = up_i(p->tab_i[t][4], T.perm);
     R.ua = up_d(p->tab_d[t][0], T.ua); R.ub = up_d(p->tab_d[t][1], T.ub); R.v = up_d(p->tab_d[t][2], T.v);
     R.weight = up_d(p->tab_d[t][3], T.weight); R.huber = up_d(p->tab_d[t][4], T.huber);
   }

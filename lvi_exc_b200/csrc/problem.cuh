@@ -85,7 +85,7 @@ struct lvi_problem {
   lvi::DBuf<lvi::FreeBlock> blocks;   // free blocks
   int n_blocks = 0;
   // tables
-  lvi::DBuf<int> tab_i[lvi::RT_COUNT][4];      // i0a, i0b, ia, ib
+  lvi::DBuf<int> tab_i[lvi::RT_COUNT][5];      // i0a, i0b, ia, ib, perm
   lvi::DBuf<double> tab_d[lvi::RT_COUNT][5];   // ua, ub, v, weight, huber
   lvi::DBuf<int> pos_r3, pos_so3, pos_rho;
   lvi::DBuf<double> planes;

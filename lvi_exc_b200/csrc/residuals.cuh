@@ -43,6 +43,7 @@ struct ResTable {   // one residual table, SoA, device (or host) pointers
   const double* v;                    // measurement vector(s): gyro w[3], accel a[3], surfel p[3], cam uv_ref[2]+uv_obs[2], camsurf uv[2], orient q[4]
   const int* ia;                      // plane id (surfel, camsurf) / landmark id (cam)
   const int* ib;                      // landmark id (camsurf)
+  const int* perm;                    // evaluation order of the normal-equation kernel (nullptr: table order)
   const double* weight; const double* huber;
 };
 
