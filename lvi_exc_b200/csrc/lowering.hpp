@@ -367,15 +367,16 @@ struct SpanAcc {
     for (int c = 0; c < 2; ++c) if (hi[c] >= 0) bw = std::max(bw, hi[c] - lo[c]);
   }
 };
-template <int TYPE> inline void bw_of_type(const ProblemView& P, SpanAcc& A) {
+template <int TYPE> inline void bw_of_type(const ProblemView& P, SpanAcc& A, const int* order = nullptr) {
   const ResTable& T = P.tab[TYPE];
   if (!T.active) return;
   // the band positions a residual touches depend only on its two spline windows (everything else it touches lives in the border or is
   // an eliminated inverse depth), and consecutive residuals are time-ordered: evaluate each distinct window pair once
   int last_a = -1, last_b = -1;
-  for (int i = 0; i < T.n; ++i) {
+  for (int q = 0; q < T.n; ++q) {
+    const int i = order ? order[q] : q;
     const int wa = T.i0a ? T.i0a[i] : 0, wb = T.i0b ? T.i0b[i] : 0;
-    if (i > 0 && wa == last_a && wb == last_b) continue;
+    if (q > 0 && wa == last_a && wb == last_b) continue;
     last_a = wa; last_b = wb;
     A.begin();
     for (int c = 0; c < rt_cols(TYPE); ++c) A.add(col_pos<TYPE>(P, i, c));
@@ -388,7 +389,7 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
   SpanAcc acc;
   acc.c1 = L.chain1_start; acc.nb = L.nb;
   bw_of_type<RT_GYRO>(P, acc); bw_of_type<RT_ACCEL>(P, acc); bw_of_type<RT_SURFEL>(P, acc);
-  bw_of_type<RT_CAM>(P, acc); bw_of_type<RT_CAMSURF>(P, acc); bw_of_type<RT_ORIENT>(P, acc);
+  bw_of_type<RT_CAM>(P, acc, L.tab[RT_CAM].perm.empty() ? nullptr : L.tab[RT_CAM].perm.data()); bw_of_type<RT_CAMSURF>(P, acc); bw_of_type<RT_ORIENT>(P, acc);
   const LoweredTable& T = L.tab[RT_CAM];
   for (int i = 0; i < T.n; ++i) {
     const int l = T.ia[i];
