@@ -180,8 +180,10 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define LVI_TRACE(slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(tq) * 8 + (slot)] = gtime(); } while (0)
-#define LVI_TRACE_AT(row, slot) do { if (S.trace && tid == 0) S.trace[static_cast<size_t>(row) * 8 + (slot)] = gtime(); } while (0)
+// (the __syncwarp matters: without it the stamping lane can stay diverged from its warp through the code that follows, which made
+// the traced factorisation of the diagonal block 3x slower than the untraced one)
+#define LVI_TRACE(slot) do { if (S.trace) { if (tid == 0) S.trace[static_cast<size_t>(tq) * 8 + (slot)] = gtime(); __syncwarp(); } } while (0)
+#define LVI_TRACE_AT(row, slot) do { if (S.trace) { if (tid == 0) S.trace[static_cast<size_t>(row) * 8 + (slot)] = gtime(); __syncwarp(); } } while (0)
 // Tasks on the pivot chain (diagonal tile and first sub-diagonal tile) poll tightly; every other task backs off between polls so that the
 // CTAs that merely wait do not steal issue slots and L2 bandwidth from the ones that work (two CTAs share an SM).
 __device__ __forceinline__ void spin_until_set(const int* f, bool critical = true) {
@@ -280,28 +282,24 @@ __device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, uns
 
 // the warps that idle during the diagonal block's Cholesky fetch flagged tiles into shared memory, all their loads in flight at once;
 // the non-blocking form gives up as soon as the Cholesky has finished (its barrier must not wait for a tile that is still being made)
-template <bool BLOCKING>
+template <bool BLOCKING, int NTHREADS>
 __device__ __forceinline__ bool helper_fetch_tile(const unsigned long long* src, unsigned flag, double* dst, int ht, volatile int* progress) {
-  constexpr int kHelpers = 160, kPer = 7;   // 7 * 160 >= 1024
+  constexpr int kPer = kTileElems / NTHREADS;
+  static_assert(kPer * NTHREADS == kTileElems, "helper count must divide the tile");
   unsigned long long w0[kPer], w1[kPer];
   while (true) {
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int e = ht + kHelpers * q;
-      w0[q] = w1[q] = flag;
-      if (e < kTileElems) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(src + 2 * e) : "memory");
-    }
+    for (int q = 0; q < kPer; ++q)
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(src + 2 * (ht + NTHREADS * q)) : "memory");
     bool ok = true;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) ok = ok && ll_valid(w0[q], w1[q], flag);
     if (ok) break;
     if (!BLOCKING && *progress >= 32) return false;
+    __nanosleep(100);   // the Cholesky warps share this SM's load/store pipe: do not hammer it while waiting
   }
 #pragma unroll
-  for (int q = 0; q < kPer; ++q) {
-    const int e = ht + kHelpers * q;
-    if (e < kTileElems) dst[e] = ll_value(w0[q], w1[q]);
-  }
+  for (int q = 0; q < kPer; ++q) dst[ht + NTHREADS * q] = ll_value(w0[q], w1[q]);
   return true;
 }
 
@@ -389,14 +387,13 @@ __device__ __forceinline__ void panel_times_winv_t(const double* sP, const doubl
 __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
   const int tid = threadIdx.x, a = tid & 31, c0 = tid >> 5;
   const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
-  int* flags = S.work_i;
   const unsigned ep = S.epoch;
   const int c_start = chain == 0 ? 0 : S.NT0, c_end = chain == 0 ? S.NT0 : S.NT;
   const bool coupled = S.T >= 1;
-  double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sD = sh.buf[2]; double* sM = sh.buf[3]; double* sW = sh.sW;
+  double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sD = sh.buf[2]; double* sM = sh.buf[3]; double* sX = sh.buf[4]; double* sT = sh.buf[5];
+  double* sW = sh.sW;
+  const int warp = tid >> 5;
   bool have_next = false;   // Dpre_j already in sh.sD (fetched under the previous column's Cholesky)
-  int pending = -1;         // column whose ready flags still have to be released
-  bool pending_panel = false;
   for (int j = c_start; j < c_end; ++j) {
     const int tq = j * S.TPC;
     LVI_TRACE(0);
@@ -417,35 +414,64 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sD[acc_elem(rp, cp, q4)];
       LVI_TRACE(1);
-      rank32_update_2x2(sA, sA, rp, cp, acc);   // X_{j-1} is still in sA
-      __syncthreads();
+      rank32_update_2x2(sX, sX, rp, cp, acc);   // X_{j-1} is still in sX
     }
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) sA[acc_elem(rp, cp, q4)] = acc[q4];
-    if (tid == 64) sh.progress = 0;
+    if (tid == 96) sh.progress = 0;
     __syncthreads();
     LVI_TRACE(2);
     const bool has_panel = coupled && j + 1 < c_end;
     int got_next = 1;
-    if (tid < 32) {
-      const bool ok = warp_potrf_cols(sA, 32, sM, sh.sR, &sh.progress);
+    if (warp == 0) {         // columns 0..15 and pivots 0..15
+      const long long cyc0 = clock64();
+      const bool ok = warp_potrf_head(sA, 32, sM, sh.sR, &sh.progress);
       if (!ok && tid == 0) *S.fail = 1;
-    } else if (tid < 64) {
-      warp_inverse_cols(sM, sh.sR, &sh.progress, sW);
-    } else if (tid < 224) {
-      if (has_panel) {
-        if (j == c_start) {
-          const double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
-          for (int e = tid - 64; e < kTileElems; e += 160) sB[e] = tile[e];
-        } else {
-          helper_fetch_tile<true>(ll_P(S, j), ep, sB, tid - 64, &sh.progress);
-        }
-        got_next = helper_fetch_tile<false>(ll_tile(S, tq + S.TPC), ep, sD, tid - 64, &sh.progress) ? 1 : 0;
+      if (S.trace) {   // slot 7: wall time; slot 1: SM cycles the head took (their ratio is the SM clock under this load)
+        if (a == 0) { S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 7] = gtime(); S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 1] = static_cast<unsigned long long>(clock64() - cyc0); }
+        __syncwarp();
       }
-    } else if (tid == 224 && pending >= 0) {
-      __threadfence();
-      st_release(flags + pending * S.TPC, 1);
-      if (pending_panel) st_release(flags + pending * S.TPC + 1, 1);
+    } else if (warp == 1) {  // columns 16..31: follows the head, then pivots 16..31
+      const bool ok = warp_potrf_tail(sA, 32, sM, sh.sR, &sh.progress, S.trace ? S.trace + static_cast<size_t>(tq + S.T + 1) * 8 + 0 : nullptr);
+      if (!ok && a == 0) *S.fail = 1;
+      if (S.trace && a == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 5] = gtime();
+    } else if (warp == 2) {  // W = L^-1, one chunk of pivots behind
+      warp_inverse_cols(sM, sh.sR, &sh.progress, sW);
+      if (S.trace && a == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 6] = gtime();
+    } else if (warp == 4) {   // shares its scheduler with the head warp: stays idle
+    } else if (has_panel) {   // warps 3, 5, 6, 7: Ppre_j, and its last update  Ppre_j -= L(j+1,j-1) X_{j-1}^T  (the freshest pair of tiles)
+      const int h = (warp == 3 ? 0 : warp - 4) * 32 + a;   // 0..127
+      if (j == c_start) {
+        const double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
+        for (int e = h; e < kTileElems; e += 128) sB[e] = tile[e];
+      } else {
+        const int hrow = tq + S.T + 1;   // diagnostics: the helpers stamp into the (otherwise unstamped) first border row of the column
+        helper_fetch_tile<true, 128>(ll_P(S, j), ep, sB, h, &sh.progress);
+        if (S.T >= 2) {
+          helper_fetch_tile<true, 128>(ll_tile(S, tq - S.TPC + 2), ep, sT, h, &sh.progress);
+          if (S.trace && h == 0) S.trace[static_cast<size_t>(hrow) * 8 + 2] = gtime();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int rq = h & 15, cq = h >> 4;   // 2 x 4 block: rows 2rq.., columns 4cq..
+          double p8[8];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) { p8[2 * cc] = sB[2 * rq + 32 * (4 * cq + cc)]; p8[2 * cc + 1] = sB[2 * rq + 1 + 32 * (4 * cq + cc)]; }
+#pragma unroll 8
+          for (int m = 0; m < 32; ++m) {
+            const double2 xa = *reinterpret_cast<const double2*>(sT + 2 * rq + 32 * m);
+            const double2 x01 = *reinterpret_cast<const double2*>(sX + 4 * cq + 32 * m);
+            const double2 x23 = *reinterpret_cast<const double2*>(sX + 4 * cq + 2 + 32 * m);
+            p8[0] = fma(-xa.x, x01.x, p8[0]); p8[1] = fma(-xa.y, x01.x, p8[1]);
+            p8[2] = fma(-xa.x, x01.y, p8[2]); p8[3] = fma(-xa.y, x01.y, p8[3]);
+            p8[4] = fma(-xa.x, x23.x, p8[4]); p8[5] = fma(-xa.y, x23.x, p8[5]);
+            p8[6] = fma(-xa.x, x23.y, p8[6]); p8[7] = fma(-xa.y, x23.y, p8[7]);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) { sB[2 * rq + 32 * (4 * cq + cc)] = p8[2 * cc]; sB[2 * rq + 1 + 32 * (4 * cq + cc)] = p8[2 * cc + 1]; }
+        }
+      }
+      if (S.trace && h == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 3] = gtime();
+      got_next = helper_fetch_tile<false, 128>(ll_tile(S, tq + S.TPC), ep, sD, h, &sh.progress) ? 1 : 0;
+      if (S.trace && h == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 4] = gtime();
     }
     have_next = __syncthreads_and(got_next) != 0 && has_panel;
     LVI_TRACE(3);
@@ -472,19 +498,16 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
         const int e = a + 32 * (c0 + 8 * jj);
         ll_store(sll + 2 * e, out[jj], ep);
         tile[e] = out[jj];
-        sA[e] = out[jj];     // stays here for the next diagonal tile
+        sX[e] = out[jj];     // stays here for the next diagonal tile and the next Ppre update
       }
       LVI_TRACE(6);
     }
-    __syncthreads();  // every thread's stores are issued (and ordered before warp 7's fence + release under the next Cholesky); X_j is in sA
-    pending = j; pending_panel = has_panel;
+    __syncthreads();  // X_j is in sX
     LVI_TRACE(7);
   }
-  if (tid == 0 && pending >= 0) {
-    __threadfence();
-    st_release(flags + pending * S.TPC, 1);
-    if (pending_panel) st_release(flags + pending * S.TPC + 1, 1);
-  }
+  // No ready flags for the chain's tiles: inside this kernel W_j and X_j are only ever consumed as flagged copies (they are the
+  // freshest inputs of their consumers by construction), and the plain copies are for the back-substitution kernel.  A fence + release
+  // here is not just unnecessary: the membar stalled the whole CTA's shared-memory traffic for ~1.7 us per column (measured).
 }
 
 // ---- flag-driven left-looking band Cholesky -----------------------------------------------------------------------------------
@@ -570,7 +593,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
     const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
-    const int kend = (band && s == 0) ? j - 1 : j;   // the diagonal task leaves the last contribution (X_{j-1}) to the chain CTA
+    const int kend = (band && s <= 1) ? j - 1 : j;   // the two pre-accumulation tasks leave the update from column j-1 to the chain CTA
     // Updates from the older columns: their source tiles are staged into shared memory by bulk async copies (TMA) running two steps
     // ahead of the arithmetic, one elected thread issuing them as soon as the ready flags allow (one warp looks at the flags of up to 32
     // steps at once: one L2 round trip per batch, not per step).  The LAST update takes the flagged copies (below).
@@ -711,8 +734,14 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 // old) is one task of a worker CTA, which hands u_m = z_m - Lb^T x2 - sum_{d > kBsLocal} ... to the chain as a flagged vector; workers
 // pick up each x_m as a flagged vector as well.  (The previous version passed x_m from CTA to CTA through a flagged mailbox: ~1 us of
 // hand-off plus a one-warp product per column, 4.4 us per column; this one is bound by the chain SM's copy bandwidth, ~0.5 us per column.)
-constexpr int kBsLocal = 6;
-constexpr int kBsStages = 3;
+#ifndef LVI_BS_LOCAL
+#define LVI_BS_LOCAL 6
+#endif
+#ifndef LVI_BS_STAGES
+#define LVI_BS_STAGES 3
+#endif
+constexpr int kBsLocal = LVI_BS_LOCAL;
+constexpr int kBsStages = LVI_BS_STAGES;
 struct BsShared {
   double tiles[kBsStages][kBsLocal + 1][kTileElems];   // [stage][0] = W_m, [stage][d] = L(m+d, m)
   double x2s[1024];                                      // border solution (workers)
@@ -743,7 +772,7 @@ __device__ void backsolve_chain(const BandSys& S, const int chain, BsShared& sh)
   if (tid == 0) {
     for (int st = 0; st < kBsStages; ++st) mbar_init(&sh.full[st], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int t = 0; t < min(2, n_cols); ++t) issue(t);
+    for (int t = 0; t < min(kBsStages - 1, n_cols); ++t) issue(t);
   }
   // u_m arrives as a flagged vector: warp 0 keeps the loads of the next two steps in flight
   unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
@@ -760,7 +789,7 @@ __device__ void backsolve_chain(const BandSys& S, const int chain, BsShared& sh)
     const int m = c_end - 1 - t;
     const int Dm = min(kBsLocal, min(S.T, t));
     const int st = t % kBsStages;
-    if (tid == 0 && t + 2 < n_cols) issue(t + 2);   // its stage was released by the barrier that ended step t - 1
+    if (tid == 0 && t + kBsStages - 1 < n_cols) issue(t + kBsStages - 1);   // its stage was released by the barrier that ended step t - 1
     if (warp == 0) {
       unsigned long long w0 = a0, w1 = a1;
       a0 = b0; a1 = b1;

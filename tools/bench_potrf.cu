@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, 2) bench_kernel(const double* tile_g, dou
   __shared__ double sM[32 * kLP], sW[32 * kLP], sR[32];
   __shared__ volatile int s_progress;
   const int tid = threadIdx.x;
-  long long best = 1ll << 60;
+  long long best = 1ll << 60, first = 0;
   for (int r = 0; r < reps; ++r) {
     for (int e = tid; e < 1024; e += 256) sA[e] = tile_g[e];
     if (tid == 64) s_progress = 0;
@@ -205,6 +205,13 @@ __global__ void __launch_bounds__(256, 2) bench_kernel(const double* tile_g, dou
     } else if (MODE == 10) {
       if (tid < 32) lvi::warp_potrf_cols(sA, 32, sM, sR, &s_progress);
       else if (tid < 64) lvi::warp_inverse_cols(sM, sR, &s_progress, sW);
+    } else if (MODE == 11) {
+      if (tid < 32) lvi::warp_potrf_head(sA, 32, sM, sR, &s_progress);
+      else if (tid < 64) lvi::warp_potrf_tail(sA, 32, sM, sR, &s_progress);
+      else if (tid < 96) lvi::warp_inverse_cols(sM, sR, &s_progress, sW);
+    } else if (MODE == 12) {
+      if (tid < 32) lvi::warp_potrf_head(sA, 32, sM, sR, &s_progress);
+      else if (tid < 64) lvi::warp_potrf_tail(sA, 32, sM, sR, &s_progress);
     } else if (MODE == 8) {
       if (tid < 32) potrf_v2<8>(sA, 32, sM, sR, &s_progress);
       else if (tid < 64) inverse_v1<8>(sM, sR, &s_progress, sW);
@@ -216,8 +223,9 @@ __global__ void __launch_bounds__(256, 2) bench_kernel(const double* tile_g, dou
     __syncthreads();
     const long long t1 = clock64();
     if (t1 - t0 < best) best = t1 - t0;
+    if (r == 0) first = t1 - t0;
   }
-  if (tid == 0) cycles[blockIdx.x] = best;
+  if (tid == 0) { cycles[blockIdx.x] = best; cycles[512 + blockIdx.x] = first; }
   if (blockIdx.x == 0)
     for (int e = tid; e < 1024; e += 256) W_out[e] = sW[(e & 31) * kLP + (e >> 5)];
 }
@@ -249,6 +257,8 @@ int main() {
       for (int k = 0; k < r; ++k) s -= L[r + 32 * k] * W[k + 32 * c];
       W[r + 32 * c] = s / L[r + 32 * r];
     }
+  if (getenv("POTRF_UPPER_ZERO")) for (int i = 0; i < 32; ++i) for (int j = i + 1; j < 32; ++j) A[i + 32 * j] = 0.0;
+  if (getenv("POTRF_SCALE")) { const double sc = atof(getenv("POTRF_SCALE")); for (auto& v : A) v *= sc; }
   double *dA, *dW;
   long long* dC;
   cudaMalloc(&dA, 8192); cudaMalloc(&dW, 8192); cudaMalloc(&dC, 8 * 1024);
@@ -256,9 +266,9 @@ int main() {
   int khz = 0;
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
   const char* names[] = {"v0 pipelined (first version)", "v0 potrf alone", "v1 ch8 pipelined", "v1 potrf alone", "v1 ch8 fast-rsqrt pipelined",
-                         "v1 fast-rsqrt potrf alone", "v1 ch4 fast-rsqrt pipelined", "v1 fast potrf then inverse, one warp", "v2 ch8 pipelined", "v2 potrf alone", "library (tile_chol.cuh)"};
+                         "v1 fast-rsqrt potrf alone", "v1 ch4 fast-rsqrt pipelined", "v1 fast potrf then inverse, one warp", "v2 ch8 pipelined", "v2 potrf alone", "library one-warp potrf + inverse", "library head + tail + inverse (3 warps)", "library head + tail alone"};
   for (int grid : {1, 296}) {
-    for (int mode = 0; mode < 11; ++mode) {
+    for (int mode = 0; mode < 13; ++mode) {
       cudaMemset(dW, 0, 8192);
       switch (mode) {
         case 0: bench_kernel<0><<<grid, 256>>>(dA, dW, dC, 20); break;
@@ -272,18 +282,21 @@ int main() {
         case 8: bench_kernel<8><<<grid, 256>>>(dA, dW, dC, 20); break;
         case 9: bench_kernel<9><<<grid, 256>>>(dA, dW, dC, 20); break;
         case 10: bench_kernel<10><<<grid, 256>>>(dA, dW, dC, 20); break;
+        case 11: bench_kernel<11><<<grid, 256>>>(dA, dW, dC, 20); break;
+        case 12: bench_kernel<12><<<grid, 256>>>(dA, dW, dC, 20); break;
       }
       cudaError_t err = cudaDeviceSynchronize();
-      long long cyc = 0;
+      long long cyc = 0, cyc_first = 0;
       cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(&cyc_first, dC + 512, 8, cudaMemcpyDeviceToHost);
       std::vector<double> Wg(1024);
       cudaMemcpy(Wg.data(), dW, 8192, cudaMemcpyDeviceToHost);
       double emax = 0;
-      const bool has_w = mode != 1 && mode != 3 && mode != 5 && mode != 9;
+      const bool has_w = mode != 1 && mode != 3 && mode != 5 && mode != 9 && mode != 12;
       if (has_w)
         for (int e = 0; e < 1024; ++e) emax = std::fmax(emax, std::fabs(Wg[e] - W[e]));
-      printf("grid %3d  %-40s %7lld cycles (%.2f us at %d MHz)  max|W - W_host| %.2e  %s\n", grid, names[mode], cyc, cyc / (khz / 1e3), khz / 1000,
-             emax, cudaGetErrorString(err));
+      printf("grid %3d  %-40s %7lld cycles (%.2f us at %d MHz; first call, cold instruction cache: %.2f us)  max|W - W_host| %.2e  %s\n", grid, names[mode],
+             cyc, cyc / (khz / 1e3), khz / 1000, cyc_first / (khz / 1e3), emax, cudaGetErrorString(err));
     }
   }
   return 0;
