@@ -255,7 +255,8 @@ def main():
            "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
                    "iterations": e2e_iters, "wall_s": e2e_s,
                    "host_s": {"create": t_create - t0, "solve": t_solve - t_create, "destroy": t_close - t_solve},
-                   "solver_ms": {"total": s.time_total_ms, "jacobian": s.time_jacobian_ms, "linear_solve": s.time_linear_solve_ms}},
+                   "solver_ms": {"total": s.time_total_ms, "jacobian": s.time_jacobian_ms, "linear_solve": s.time_linear_solve_ms},
+                   "initial_cost": s.initial_cost, "final_cost": s.final_cost},   # identical at every N: the data-parallel sum is the same problem
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
            "map_path": info}
 

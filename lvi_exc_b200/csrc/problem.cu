@@ -315,6 +315,26 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
     p->schur = SchurView{L.n_rho, L.nb + L.nbo, p->row_start.p, p->row_pos.p, p->lm_of_rho.p, p->Hrx.p, p->Hrr.p, p->yrho.p};
   }
   p->g.alloc(nt); p->scale.alloc(nt); p->diag.alloc(nt); p->y.alloc(nt); p->delta.alloc(nt);
+  if (p->ctx->world > 1) {  // the all-reduce of H moves only the tiles that can be non-zero (about half of the store at C2)
+    const BandSys& H = p->H;
+    const int RBsep = H.n_mid >> kTileLog;
+    std::vector<int> map;
+    for (int j = 0; j < H.NT; ++j) {
+      const int c_start = j < H.NT0 ? 0 : H.NT0, c_end = j < H.NT0 ? H.NT0 : H.NT;
+      const int sep_first = std::max(c_start, c_end - H.T - 1);
+      for (int s = 0; s < H.TPC; ++s) {
+        const bool band = s <= H.T;
+        if (band && j + s >= c_end) continue;                              // below the end of the chain: never referenced
+        if (!band && (s - H.T - 1) < RBsep && j < sep_first) continue;     // separator row outside its coupling range: structurally zero
+        map.push_back(j * H.TPC + s);
+      }
+    }
+    p->pack_map.alloc(std::max<size_t>(map.size(), 1));
+    p->pack_map.upload(map.data(), map.size(), p->ctx->stream);
+    p->pack_buf.alloc(std::max<size_t>(map.size() * kTileElems, 1));
+    p->n_pack = static_cast<int>(map.size());
+    LVI_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  }
   p->has_solver_buffers = true;
 }
 

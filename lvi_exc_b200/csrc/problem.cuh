@@ -95,6 +95,9 @@ struct lvi_problem {
   lvi::DBuf<double> H_tiles, H_C, A_tiles, A_C, A_Linv, A_x, A_work_d, A2_tiles, A2_C, A2_Linv, A2_x, A2_work_d;
   lvi::DBuf<int> A_work_i, A2_work_i;
   lvi::DBuf<unsigned long long> A_ll, A2_ll;
+  lvi::DBuf<int> pack_map;       // multi-GPU: indices of the structurally non-zero tiles of H (what the all-reduce has to move)
+  lvi::DBuf<double> pack_buf;    // ... and their contiguous staging copy
+  int n_pack = 0;
   lvi::SchurView schur{};
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;

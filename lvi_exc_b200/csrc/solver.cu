@@ -1146,6 +1146,16 @@ struct Scalars {  // mirrors p->scal (+ the factorisation failure flag)
   int failed;
 };
 
+// gather / scatter of the structurally non-zero tiles of H around the all-reduce (one CTA per tile)
+__global__ void __launch_bounds__(256) pack_tiles_kernel(double* __restrict__ tiles, const int* __restrict__ map, double* __restrict__ packed, int unpack) {
+  double2* t = reinterpret_cast<double2*>(tiles + static_cast<size_t>(map[blockIdx.x]) * kTileElems);
+  double2* q = reinterpret_cast<double2*>(packed + static_cast<size_t>(blockIdx.x) * kTileElems);
+  for (int e = threadIdx.x; e < kTileElems / 2; e += 256) {
+    if (unpack) t[e] = q[e];
+    else q[e] = t[e];
+  }
+}
+
 static void allreduce_sum(lvi_ctx* ctx, double* buf, size_t count) {
   if (ctx->world <= 1 || count == 0) return;
   ncclResult_t r = nccl().AllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl), ctx->stream);
@@ -1167,7 +1177,13 @@ static void linearize(lvi_problem* p) {
   problem_linearize(p, nullptr);
   lvi_ctx* ctx = p->ctx;
   if (ctx->world > 1) {
-    allreduce_sum(ctx, p->H_tiles.p, p->H_tiles.n);
+    if (p->n_pack > 0) {
+      LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, p->pack_buf.p, 0);
+      allreduce_sum(ctx, p->pack_buf.p, static_cast<size_t>(p->n_pack) * kTileElems);
+      LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, p->pack_buf.p, 1);
+    } else {
+      allreduce_sum(ctx, p->H_tiles.p, p->H_tiles.n);
+    }
     allreduce_sum(ctx, p->H_C.p, p->H_C.n);
     allreduce_sum(ctx, p->g.p, p->g.n);
     allreduce_sum(ctx, p->Hrx.p, p->Hrx.n);

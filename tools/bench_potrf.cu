@@ -267,23 +267,25 @@ int main() {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
   const char* names[] = {"v0 pipelined (first version)", "v0 potrf alone", "v1 ch8 pipelined", "v1 potrf alone", "v1 ch8 fast-rsqrt pipelined",
                          "v1 fast-rsqrt potrf alone", "v1 ch4 fast-rsqrt pipelined", "v1 fast potrf then inverse, one warp", "v2 ch8 pipelined", "v2 potrf alone", "library one-warp potrf + inverse", "library head + tail + inverse (3 warps)", "library head + tail alone"};
+  const int dyn = getenv("POTRF_DYN_SMEM") ? atoi(getenv("POTRF_DYN_SMEM")) : 0;   // extra dynamic shared memory per block (changes the L1 / shared carve-out)
   for (int grid : {1, 296}) {
     for (int mode = 0; mode < 13; ++mode) {
       cudaMemset(dW, 0, 8192);
+      if (dyn) { cudaFuncSetAttribute(bench_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); cudaFuncSetAttribute(bench_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); }
       switch (mode) {
-        case 0: bench_kernel<0><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 1: bench_kernel<1><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 2: bench_kernel<2><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 3: bench_kernel<3><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 4: bench_kernel<4><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 5: bench_kernel<5><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 6: bench_kernel<6><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 7: bench_kernel<7><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 8: bench_kernel<8><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 9: bench_kernel<9><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 10: bench_kernel<10><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 11: bench_kernel<11><<<grid, 256>>>(dA, dW, dC, 20); break;
-        case 12: bench_kernel<12><<<grid, 256>>>(dA, dW, dC, 20); break;
+        case 0: bench_kernel<0><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 1: bench_kernel<1><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 2: bench_kernel<2><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 3: bench_kernel<3><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 4: bench_kernel<4><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 5: bench_kernel<5><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 6: bench_kernel<6><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 7: bench_kernel<7><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 8: bench_kernel<8><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 9: bench_kernel<9><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 10: bench_kernel<10><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 11: bench_kernel<11><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
+        case 12: bench_kernel<12><<<grid, 256, dyn>>>(dA, dW, dC, 20); break;
       }
       cudaError_t err = cudaDeviceSynchronize();
       long long cyc = 0, cyc_first = 0;
