@@ -25,7 +25,10 @@ def _spd_band(rng, nb, nbo, bw):
 
 
 @pytest.mark.parametrize("nb,nbo,bw", [(1, 0, 0), (31, 0, 5), (32, 3, 31), (100, 0, 0), (257, 44, 23), (700, 20, 130), (64, 0, 63),
-                                       (0, 7, 0), (1500, 116, 400), (333, 1, 332)])
+                                       (0, 7, 0), (1500, 116, 400), (333, 1, 332),
+                                       # half bandwidths of 2, 3, 6, 7, 8 and 22 tiles: the factor kernel's pre-accumulation / flagged hand-off cases
+                                       # and both sides of the back substitution's local window (6 tiles)
+                                       (200, 5, 64), (400, 12, 96), (700, 9, 190), (900, 40, 200), (1200, 33, 250), (2400, 70, 700)])
 def test_band_solver_matches_numpy(cuda_backend, nb, nbo, bw):
     rng = np.random.default_rng(nb * 1000 + nbo * 10 + bw)
     A = _spd_band(rng, nb, nbo, bw)
@@ -36,7 +39,7 @@ def test_band_solver_matches_numpy(cuda_backend, nb, nbo, bw):
 
 
 @pytest.mark.parametrize("n0,n1,nbo,n_mid,bw", [(64, 64, 10, 10, 20), (320, 288, 70, 40, 45), (96, 640, 44, 0, 23), (1024, 992, 200, 150, 130),
-                                                (32, 32, 3, 3, 31)])
+                                                (32, 32, 3, 3, 31), (1600, 1568, 300, 256, 260), (96, 96, 70, 64, 64)])
 def test_two_sided_band_solver_matches_numpy(cuda_backend, n0, n1, nbo, n_mid, bw):
     """two chains [0, n0) and [n0, n0+n1) that only meet in the border; the first n_mid border dims go through the second-level system"""
     rng = np.random.default_rng(n0 + 7 * n1 + nbo)
