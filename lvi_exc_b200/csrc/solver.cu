@@ -1051,6 +1051,39 @@ __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ a, 
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+// diagnostics (LVI_POTRF_SELFTEST): the three Cholesky warps on one tile, alone on the device, timed with clock64
+__global__ void __launch_bounds__(kFacThreads, 2) potrf_selftest_kernel(const double* tile_g, long long* cycles, const double2* bg, size_t bg_n, volatile int* stop) {
+  extern __shared__ __align__(128) unsigned char selftest_pad[];   // sized at launch so that every block has an SM to itself
+  if (blockIdx.x != 0) {   // background: stream a large buffer through L2 until block 0 is done
+    double2 acc = make_double2(0.0, 0.0);
+    size_t i = (static_cast<size_t>(blockIdx.x) * 7919 * 256 + threadIdx.x) % bg_n;
+    while (*stop == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const double2 v = __ldcg(bg + i); acc.x += v.x; acc.y += v.y; i += 256 * 149; if (i >= bg_n) i -= bg_n; }
+    }
+    if (acc.x == 12345.678) cycles[7] = 1;
+    return;
+  }
+  if (bg) __nanosleep(30000);
+  // same shared-memory layout as the factor kernel's chain CTA
+  FacShared& sh = *reinterpret_cast<FacShared*>(selftest_pad);
+  double* sA = sh.buf[0]; double* sM = sh.buf[3]; double* sW = sh.sW; double* sR = sh.sR;
+  volatile int& s_progress = sh.progress;
+  const int tid = threadIdx.x;
+  for (int r = 0; r < 4; ++r) {
+    for (int e = tid; e < kTileElems; e += kFacThreads) sA[e] = tile_g[e];
+    if (tid == 96) s_progress = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (tid < 32) warp_potrf_head(sA, 32, sM, sR, &s_progress);
+    else if (tid < 64) warp_potrf_tail(sA, 32, sM, sR, &s_progress);
+    else if (tid < 96) warp_inverse_cols(sM, sR, &s_progress, sW);
+    __syncthreads();
+    if (tid == 0) cycles[r] = clock64() - t0;
+  }
+  if (tid == 0) { cycles[4] = static_cast<long long>(sW[5 * kLP + 3] * 1e6); __threadfence(); *stop = 1; }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 static int resident_ctas(lvi_ctx* ctx, const void* kernel, int threads, size_t smem) {
   int per_sm = 0;
@@ -1068,6 +1101,29 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
   if (A.NT == 0) return;
   LVI_REQUIRE(A.work_i && A.work_d && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
   A.epoch = next_epoch();   // flag value of this factorisation's flagged tile copies (never cleared)
+  if (std::getenv("LVI_POTRF_SELFTEST")) {
+    static bool done = false;
+    if (!done) {
+      done = true;
+      std::vector<double> h(kTileElems);
+      for (int i = 0; i < 32; ++i) for (int j = 0; j < 32; ++j) h[i + 32 * j] = i == j ? 40.0 : 1.0 / (1 + i + j);
+      DBuf<double> dt(kTileElems); DBuf<long long> dc(8);
+      dt.upload(h.data(), kTileElems, st);
+      LVI_CUDA(cudaStreamSynchronize(st));
+      DBuf<int> stop(1);
+      LVI_CUDA(cudaFuncSetAttribute(potrf_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      for (int bgload = 0; bgload < 2; ++bgload) {
+        stop.zero(st);
+        potrf_selftest_kernel<<<bgload ? 148 : 1, kFacThreads, 120 * 1024, st>>>(dt.p, dc.p, bgload ? reinterpret_cast<const double2*>(A.ll) : nullptr,
+                                                                                A.ll_count() / 2, stop.p);
+        long long hc[8] = {0};
+        LVI_CUDA(cudaMemcpyAsync(hc, dc.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        LVI_CUDA(cudaStreamSynchronize(st));
+        std::fprintf(stderr, "[lvi] potrf selftest (head + tail + inverse on an SM of its own, %s): %lld %lld %lld %lld cycles\n",
+                     bgload ? "147 other SMs streaming through L2" : "device otherwise idle", hc[0], hc[1], hc[2], hc[3]);
+      }
+    }
+  }
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
   constexpr size_t smem = sizeof(FacShared);
