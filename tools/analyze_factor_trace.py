@@ -8,8 +8,8 @@ import numpy as np
 raw = open(sys.argv[1], "rb").read()
 NT, TPC, T, RB = np.frombuffer(raw[:16], np.int32)
 tr = np.frombuffer(raw[16:], np.uint64).reshape(NT, TPC, 8).astype(np.float64)
-t0 = tr[tr > 0].min()
-tr = np.where(tr > 0, (tr - t0) / 1e3, np.nan)   # us
+t0 = tr[tr > 1e12].min()
+tr = np.where(tr > 1e12, (tr - t0) / 1e3, np.nan)   # us
 print(f"NT {NT} TPC {TPC} T {T} RB {RB}; last stamp {np.nanmax(tr):.1f} us")
 d = tr[:, 0, :]
 pub = d[:, 7]
@@ -26,20 +26,3 @@ for c, (lo, hi) in enumerate(((0, split), (split, NT))):
     dd = np.diff(pub[lo:hi])
     print("   period along the chain (30-column means):", " ".join(f"{np.nanmean(dd[k:k + 30]):.1f}" for k in range(0, len(dd), 30)))
 
-# worker tasks next to the chain: row 1 = Ppre task (j,1), row 2 = tile (j+2,j); stamps: 0 fetched, 1 step k=j-2 starts, 2 step k=j-1 starts,
-# 3 its inputs are in shared memory, 4 accumulation done, 5 (row 2) W_j in, 7 flagged copy stored
-if TPC > 2 and T >= 2:
-    p1, p2 = tr[:, 1, :], tr[:, 2, :]
-    lo, hi = 6, split - 6
-    j = np.arange(lo, hi)
-    m = np.nanmean
-    print("worker path, chain 0 (us, means):")
-    print("   tile (j+2,j):  W_j stores issued -> W_j in          %6.2f" % m(p2[j, 5] - d[j, 4]))
-    print("                  W_j in -> flagged copy stored         %6.2f" % m(p2[j, 7] - p2[j, 5]))
-    print("                  idle before W_j (accum done -> W in)  %6.2f" % m(p2[j, 5] - p2[j, 4]))
-    print("   Ppre_j:        L(j+1,j-1) stored -> inputs of k=j-1 in %6.2f" % m(p1[j, 3] - p2[j - 1, 7]))
-    print("                  X_{j-1} stores issued -> inputs in      %6.2f" % m(p1[j, 3] - d[j - 1, 6]))
-    print("                  step k=j-1 start -> inputs in           %6.2f" % m(p1[j, 3] - p1[j, 2]))
-    print("                  inputs in -> Ppre stored                %6.2f" % m(p1[j, 7] - p1[j, 3]))
-    print("   chain:         Ppre_j stored -> chain has it (stamp 3) %6.2f" % m(d[j, 3] - p1[j, 7]))
-    print("                  W_{j-1} stores issued -> Ppre_j stored  %6.2f" % m(p1[j, 7] - d[j - 1, 4]))

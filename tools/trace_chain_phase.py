@@ -2,7 +2,7 @@ import numpy as np,sys
 raw=open(sys.argv[1],'rb').read()
 NT,TPC,T,RB=np.frombuffer(raw[:16],np.int32)
 tr=np.frombuffer(raw[16:],np.uint64).reshape(NT,TPC,8).astype(np.float64)
-t0=tr[tr>0].min(); tr=np.where(tr>0,(tr-t0)/1e3,np.nan)
+t0=tr[tr>1e12].min(); tr=np.where(tr>1e12,(tr-t0)/1e3,np.nan)
 d=tr[:,0,:]; h=tr[:,T+1,:]
 j=np.arange(30,240)
 pc=lambda x: np.round(np.nanpercentile(x,[5,25,50,75,95]),2)

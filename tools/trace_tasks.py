@@ -4,7 +4,7 @@ import numpy as np
 raw = open(sys.argv[1], 'rb').read()
 NT, TPC, T, RB = np.frombuffer(raw[:16], np.int32)
 tr = np.frombuffer(raw[16:], np.uint64).reshape(NT, TPC, 8).astype(np.float64)
-t0 = tr[tr > 0].min(); tr = np.where(tr > 0, (tr - t0) / 1e3, np.nan)
+t0 = tr[tr > 1e12].min(); tr = np.where(tr > 1e12, (tr - t0) / 1e3, np.nan)
 d = tr[:, 0, :]; p0 = tr[:, TPC - 1, :]; p1 = tr[:, 1, :]
 split = NT // 2
 per = np.diff(d[:split, 7])
