@@ -6,13 +6,15 @@
 // LevenbergMarquardtStrategy step by step and is kept line-for-line comparable with the CPU oracle (oracle/orc_solve.cpp).
 //
 // Linear algebra: (S H S + D^2) y = -S g with H in 32x32 tile storage (problem.cuh), inverse depths eliminated first (Schur).
-//   band_factor_ll_kernel     flag-driven left-looking tile Cholesky: one task per 32x32 tile of the factor, fetched in column-major
-//                             order; the accumulator lives in registers and L(i,k) L(j,k)^T is subtracted as soon as both source tiles
-//                             are published (ld.acquire / st.release flags).  The diagonal task runs a fused Cholesky + inverse of its
-//                             block with the whole CTA in shared memory and publishes W = L_jj^-1; panel tiles (band + arrow border +
-//                             the rhs row, so the forward substitution comes for free) finish as X = P W^T.
+//   band_factor_ll_kernel     left-looking tile Cholesky without a grid-wide barrier.  One persistent CTA per pivot chain runs the serial
+//                             recurrence D_j -> W_j = L_jj^-1 -> X_j = L(j+1,j) -> D_{j+1} out of its shared memory (tile_chol.cuh: two
+//                             factoring warps + an inverse follower); every other tile of the factor (band + arrow border + the rhs row, so
+//                             the forward substitution comes for free) is one task of a worker CTA: accumulator in registers, older
+//                             source tiles staged by TMA bulk copies behind ld.acquire ready flags, the freshest pair and W_j taken
+//                             from flagged ("LL") copies, X = P W^T, each tile written once.
 //   corner_solve_kernel       dense Cholesky of the (<= ~100)^2 Schur complement of the arrow border + its triangular solves.
-//   band_backsolve_ll_kernel  flag-driven backward substitution, one task per block column.
+//   band_backsolve_ll_kernel  backward substitution: one persistent CTA per chain on TMA-staged tiles, far products and the border part
+//                             by one worker task per block column, x_m / u_m handed over as flagged vectors.
 // All fp64: the normal matrix of a 0.02 s-knot spline is too ill-conditioned for fp32/bf16 factors.
 #include <atomic>
 #include <chrono>
@@ -379,11 +381,11 @@ __device__ __forceinline__ void panel_times_winv_t(const double* sP, const doubl
 
 // ---- the pivot chain: one CTA per chain walks its block columns ---------------------------------------------------------------
 //   D_j = Dpre_j - X_{j-1} X_{j-1}^T ; L_jj L_jj^T = D_j, W_j = L_jj^-1 ; X_j = L(j+1,j) = Ppre_j W_j^T
-// Dpre_j (all contributions of columns <= j-2 to the diagonal tile) and Ppre_j (all contributions of columns <= j-1 to tile (j+1,j)) are
-// pre-accumulated by worker CTAs and arrive as flagged copies; X_{j-1} and W_j never leave this CTA's shared memory on their way to the
-// next step, so the serial chain itself has no global-memory hand-off.  While warps 0 and 1 factor and invert the diagonal block, warps
-// 2..6 fetch Ppre_j and (if it is there in time) Dpre_{j+1}, and warp 7 releases the ready flags of the previous column (the fence in
-// front of a release waits for 24 KB of stores to be acknowledged, ~1.5 us: kept off the chain).
+// Dpre_j and Ppre_j (the contributions of columns <= j-2 to the diagonal tile and to tile (j+1,j)) are pre-accumulated by worker CTAs
+// and arrive as flagged copies; X_{j-1} and W_j never leave this CTA's shared memory on their way to the next step, so the serial chain
+// itself has no global-memory hand-off.  While warps 0-2 factor and invert the diagonal block (tile_chol.cuh), warps 3, 5, 6, 7 fetch
+// Ppre_j and the freshest tile L(j+1,j-1), apply the last update  Ppre_j -= L(j+1,j-1) X_{j-1}^T  and try to fetch Dpre_{j+1}; warp 4
+// shares its scheduler with the head warp and stays idle.
 __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
   const int tid = threadIdx.x, a = tid & 31, c0 = tid >> 5;
   const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
