@@ -395,33 +395,15 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
   double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sD = sh.buf[2]; double* sM = sh.buf[3]; double* sX = sh.buf[4]; double* sT = sh.buf[5];
   double* sW = sh.sW;
   const int warp = tid >> 5;
-  bool have_next = false;   // Dpre_j already in sh.sD (fetched under the previous column's Cholesky)
-  for (int j = c_start; j < c_end; ++j) {
-    const int tq = j * S.TPC;
-    LVI_TRACE(0);
-    double acc[4];
-    if (j == c_start || !coupled) {   // nothing precedes this column: the tile is already final
-      const double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
-      LVI_TRACE(1);
-    } else {
-      if (!have_next) {
-        double v[4];
-        ll_load_n<4>(ll_tile(S, tq) + 2 * tid, 2 * kFacThreads, v, ep);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) sD[tid + kFacThreads * q4] = v[q4];
-        __syncthreads();
-      }
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sD[acc_elem(rp, cp, q4)];
-      LVI_TRACE(1);
-      rank32_update_2x2(sX, sX, rp, cp, acc);   // X_{j-1} is still in sX
-    }
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) sA[acc_elem(rp, cp, q4)] = acc[q4];
+  bool have_next = false;   // Dpre_{j+1} already in sD (fetched under column j's Cholesky)
+  {  // the first column of a chain has nothing before it: its tile is already final
+    const double* tile = S.tiles + static_cast<size_t>(c_start) * S.TPC * kTileElems;
+    for (int e = tid; e < kTileElems; e += kFacThreads) sA[e] = tile[e];
     if (tid == 96) sh.progress = 0;
     __syncthreads();
+  }
+  for (int j = c_start; j < c_end; ++j) {
+    const int tq = j * S.TPC;
     LVI_TRACE(2);
     const bool has_panel = coupled && j + 1 < c_end;
     int got_next = 1;
@@ -477,34 +459,77 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
     }
     have_next = __syncthreads_and(got_next) != 0 && has_panel;
     LVI_TRACE(3);
-    {  // publish W_j: flagged copy for the tasks waiting on it, plain copy for the back substitution
-      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+    {  // W_j goes out at once as a flagged copy: a whole block column of panel tasks is waiting for it
       unsigned long long* wll = ll_W(S, j);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int e = tid + kFacThreads * q4;
-        const double w = sW[(e & 31) * kLP + (e >> 5)];
-        ll_store(wll + 2 * e, w, ep);
-        Wg[e] = w;
+        ll_store(wll + 2 * e, sW[(e & 31) * kLP + (e >> 5)], ep);
       }
     }
     LVI_TRACE(4);
     if (has_panel) {
       double out[4];
       panel_times_winv_t(sB, sW, a, c0, out);
-      LVI_TRACE(5);
-      unsigned long long* sll = ll_tile(S, tq + 1);
-      double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int e = a + 32 * (c0 + 8 * jj);
-        ll_store(sll + 2 * e, out[jj], ep);
-        tile[e] = out[jj];
-        sX[e] = out[jj];     // stays here for the next diagonal tile and the next Ppre update
-      }
-      LVI_TRACE(6);
+      for (int jj = 0; jj < 4; ++jj) sX[a + 32 * (c0 + 8 * jj)] = out[jj];   // stays here for the next diagonal tile and the next Ppre update
     }
     __syncthreads();  // X_j is in sX
+    LVI_TRACE(5);
+    // The CTA splits: warps 4-7 write X_j (flagged + plain) and the plain copy of W_j to global memory (48 KB of stores: pure issue time),
+    // warps 0-3 build the next diagonal tile  D_{j+1} = Dpre_{j+1} - X_j X_j^T  with 2 x 4 register blocks (four warps with 8 outputs per
+    // thread finish this shared-memory-bound update sooner than eight warps with 4).
+    if (warp >= 4) {
+      const int h = tid - 128;
+      if (has_panel) {
+        unsigned long long* sll = ll_tile(S, tq + 1);
+        double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const int e = h + 128 * q8;
+          const double x = sX[e];
+          ll_store(sll + 2 * e, x, ep);
+          tile[e] = x;
+        }
+      }
+      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) {
+        const int e = h + 128 * q8;
+        Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
+      }
+    } else if (j + 1 < c_end) {
+      const int h = tid;                    // 0..127
+      const int rq = h & 15, cq = h >> 4;   // 2 x 4 block: rows 2rq.., columns 4cq..
+      double p8[8];
+      if (!coupled) {
+        const double* tile = S.tiles + static_cast<size_t>(tq + S.TPC) * kTileElems;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) { p8[2 * cc] = tile[2 * rq + 32 * (4 * cq + cc)]; p8[2 * cc + 1] = tile[2 * rq + 1 + 32 * (4 * cq + cc)]; }
+      } else {
+        if (!have_next) {
+          helper_fetch_tile<true, 128>(ll_tile(S, tq + S.TPC), ep, sD, h, &sh.progress);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        LVI_TRACE(6);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) { p8[2 * cc] = sD[2 * rq + 32 * (4 * cq + cc)]; p8[2 * cc + 1] = sD[2 * rq + 1 + 32 * (4 * cq + cc)]; }
+#pragma unroll 8
+        for (int m = 0; m < 32; ++m) {
+          const double2 xa = *reinterpret_cast<const double2*>(sX + 2 * rq + 32 * m);
+          const double2 x01 = *reinterpret_cast<const double2*>(sX + 4 * cq + 32 * m);
+          const double2 x23 = *reinterpret_cast<const double2*>(sX + 4 * cq + 2 + 32 * m);
+          p8[0] = fma(-xa.x, x01.x, p8[0]); p8[1] = fma(-xa.y, x01.x, p8[1]);
+          p8[2] = fma(-xa.x, x01.y, p8[2]); p8[3] = fma(-xa.y, x01.y, p8[3]);
+          p8[4] = fma(-xa.x, x23.x, p8[4]); p8[5] = fma(-xa.y, x23.x, p8[5]);
+          p8[6] = fma(-xa.x, x23.y, p8[6]); p8[7] = fma(-xa.y, x23.y, p8[7]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) { sA[2 * rq + 32 * (4 * cq + cc)] = p8[2 * cc]; sA[2 * rq + 1 + 32 * (4 * cq + cc)] = p8[2 * cc + 1]; }
+    }
+    if (tid == 96) sh.progress = 0;
+    __syncthreads();  // D_{j+1} is in sA; the stores of column j are issued
     LVI_TRACE(7);
   }
   // No ready flags for the chain's tiles: inside this kernel W_j and X_j are only ever consumed as flagged copies (they are the
@@ -536,9 +561,11 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
   const int rp = tid & 15, cp = tid >> 4;   // 2x2 accumulator block: rows 2rp, 2rp+1, columns 2cp, 2cp+1
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (static_cast<int>(blockIdx.x) < n_chains) {
-    if (tid == 0) st_release(chain_sm + blockIdx.x, static_cast<int>(smid) + 1);
-    factor_chain(S, blockIdx.x, sh);
+  // chain CTAs: blocks 0 and 2 (consecutive blocks land on the two SMs of one TPC; the chains get a TPC each)
+  const int chain_id = blockIdx.x == 0 ? 0 : (blockIdx.x == 2 && n_chains == 2 && gridDim.x > 3) ? 1 : (blockIdx.x == 1 && n_chains == 2 && gridDim.x <= 3) ? 1 : -1;
+  if (chain_id >= 0) {
+    if (tid == 0) st_release(chain_sm + chain_id, static_cast<int>(smid) + 1);
+    factor_chain(S, chain_id, sh);
     return;
   }
   // a worker that shares its SM with a chain CTA steps aside: the chain is the critical path and runs ~1.5x faster alone on the SM

@@ -1,8 +1,8 @@
 """Critical-path breakdown of band_factor_ll_kernel from an LVI_TRACE_FACTOR dump (diagnostics).
 
-The chain CTAs stamp, per block column j (row j*TPC of the trace): 0 loop top, 1 Dpre_j in registers, 2 D_j final (after the rank-32
-update with X_{j-1}), 3 potrf + inverse done (and Ppre_j in shared memory), 4 W_j stores issued, 5 X_j computed, 6 X_j stores issued,
-7 flags released."""
+The chain CTAs stamp, per block column j (row j*TPC of the trace): 2 D_j final in shared memory (start of the diagonal-block phase),
+3 Cholesky + inverse done (and Ppre_j complete in shared memory), 4 flagged copy of W_j issued, 5 X_j computed (in shared memory),
+6 Dpre_{j+1} available to the warps that build the next diagonal tile, 7 D_{j+1} built and the stores of column j issued."""
 import sys
 import numpy as np
 raw = open(sys.argv[1], "rb").read()
@@ -14,15 +14,15 @@ print(f"NT {NT} TPC {TPC} T {T} RB {RB}; last stamp {np.nanmax(tr):.1f} us")
 d = tr[:, 0, :]
 pub = d[:, 7]
 split = int(np.nanargmin(np.diff(pub))) + 1 if NT > 2 and np.nanmin(np.diff(pub)) < 0 else NT
-names = ["wait for Dpre", "rank-32 update with X_{j-1}", "potrf + inverse (+ Ppre in)", "W stores", "X = Ppre W^T", "X stores", "barrier + flags"]
+names = [None, None, "Cholesky + inverse (+ Ppre complete)", "flagged W stores", "X = Ppre W^T", "wait for Dpre (next column)", "rank-32 update -> D_{j+1} || stores"]
 for c, (lo, hi) in enumerate(((0, split), (split, NT))):
     if hi - lo < 8:
         continue
     sl = slice(lo + 3, hi - 3)
     print(f"chain {c}: columns {lo}..{hi - 1}, first flag {pub[lo]:.1f} us, last flag {pub[hi - 1]:.1f} us, "
           f"period {np.nanmean(np.diff(pub[sl])):.2f} us per column")
-    for k in range(7):
-        print(f"   {names[k]:<32} {np.nanmean(d[sl, k + 1] - d[sl, k]):6.2f}")
+    for k in range(2, 7):
+        print(f"   {names[k]:<40} {np.nanmean(d[sl, k + 1] - d[sl, k]):6.2f}")
     dd = np.diff(pub[lo:hi])
     print("   period along the chain (30-column means):", " ".join(f"{np.nanmean(dd[k:k + 30]):.1f}" for k in range(0, len(dd), 30)))
 

@@ -10,4 +10,4 @@ base=d[j,2]
 print("period", pc(np.diff(d[30:240,7])))
 for k,n in enumerate(["tail: follow done","Ppre in","T tile in","GEMM done","Dpre next tried","potrf tail done","inverse done","potrf head done"]):
     print(" %-16s"%n, pc(h[j,k]-base))
-print(" barrier passed  ", pc(d[j,3]-base), " syrk", pc(d[j,2]-d[j,1]), " X", pc(d[j,5]-d[j,4]))
+print(" barrier passed  ", pc(d[j,3]-base), " X", pc(d[j,5]-d[j,4]), " Dpre wait", pc(d[j,6]-d[j,5]), " update||stores", pc(d[j,7]-d[j,6]))
