@@ -42,6 +42,11 @@ static void ctx_init(lvi_ctx* c, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   LVI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    LVI_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    LVI_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
+  LVI_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   // device buffers come from the stream-ordered pool (common.cuh, DBuf): keep freed blocks cached instead of returning them to the driver
   cudaMemPool_t pool;
   LVI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -98,6 +103,8 @@ int lvi_ctx_destroy(lvi_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // hand cached blocks back to the driver
+    for (int i = 0; i < 2; ++i) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->stream);
     if (tl_stream == ctx->stream) tl_stream = nullptr;
   }

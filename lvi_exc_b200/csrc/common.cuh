@@ -58,6 +58,9 @@ struct lvi_ctx {
   int rank = 0, world = 1;
   int64_t launches = 0;
   int sm_count = lvi::kNumSMs;
+  // two auxiliary streams + fork/join events: independent kernels of one phase (the per-type normal-equation kernels) run side by side
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 namespace lvi {

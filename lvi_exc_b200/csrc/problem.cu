@@ -249,8 +249,23 @@ void problem_linearize(lvi_problem* p, double* cost_d) {
   p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st); p->Hrx.zero(st); p->Hrr.zero(st);
   LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
   problem_set_param_source(p, p->X.p);
-  launch_linearize<RT_GYRO>(p); launch_linearize<RT_ACCEL>(p); launch_linearize<RT_SURFEL>(p);
-  launch_linearize<RT_CAM>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
+  // The per-type kernels only meet in fp64 atomics, and each of them leaves most of the machine idle (the camera kernel is 502 CTAs of
+  // 64 threads at 255 registers): they run side by side on three streams -- camera | surfel | IMU and the rest -- and join again.
+  lvi_ctx* ctx = p->ctx;
+  LVI_CUDA(cudaEventRecord(ctx->ev_fork, st));
+  for (int i = 0; i < 2; ++i) LVI_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+  launch_linearize<RT_CAM>(p);
+  {
+    struct Restore { lvi_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, st};   // LVI_LAUNCH goes to ctx->stream
+    ctx->stream = ctx->aux[0];
+    launch_linearize<RT_SURFEL>(p);
+    ctx->stream = ctx->aux[1];
+    launch_linearize<RT_ACCEL>(p); launch_linearize<RT_GYRO>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
+  }
+  for (int i = 0; i < 2; ++i) {
+    LVI_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+    LVI_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+  }
   if (cost_d && cost_d != p->scal.p) LVI_CUDA(cudaMemcpyAsync(cost_d, p->scal.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
 }
 
