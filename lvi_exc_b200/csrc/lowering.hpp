@@ -19,6 +19,8 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <exception>
 #include <vector>
 
 #include "../../include/lvi_exc_b200.h"
@@ -177,8 +179,13 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     }
   }
   // ---- surfel (map time first: spans must be ordered, Q12)
+  // The surfel table (the largest: 110 k rows at C2) is lowered on a second host thread while this one does the camera tables; it
+  // marks knots in its own array, merged after the join.
   std::vector<char> border_flag(n + 4, 0);   // knots of the map-time windows (they go to the arrow border)
-  {
+  std::vector<char> knot_used_surfel(n, 0), border_flag_cs(n + 4, 0);
+  bool surfel_sens = false;
+  auto lower_surfel = [&]() {
+    auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) knot_used_surfel[k] = 1; };
     LoweredTable& T = L.tab[RT_SURFEL];
     need(d.surfel_t, d.n_surfel, "surfel_t"); need(d.surfel_point, d.n_surfel, "surfel_point"); need(d.surfel_plane, d.n_surfel, "surfel_plane");
     if (d.n_surfel && !L.has_r3) throw std::invalid_argument("surfel residuals need the R3 spline");
@@ -193,8 +200,11 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
       locate2(d, d.surfel_tmap[i], d.surfel_t[i], d.surfel_tmap[i] + d.lidar_toff, d.surfel_t[i] + d.lidar_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
       if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) border_flag[T.i0a[i] + k] = 1; }
     }
-    if (T.n && T.active) sens_used[TB_LQ] = sens_used[TB_LP] = true;
-  }
+    if (T.n && T.active) surfel_sens = true;
+  };
+  std::exception_ptr surfel_error;
+  std::thread surfel_thread([&] { try { lower_surfel(); } catch (...) { surfel_error = std::current_exception(); } });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } surfel_joiner{surfel_thread};
   // ---- camera
   std::vector<int> rho_anchor(std::max(d.n_landmarks, 1), -1);
   {
@@ -243,12 +253,16 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
       if (T.ia[i] < 0 || T.ia[i] >= d.n_planes || T.ib[i] < 0 || T.ib[i] >= d.n_landmarks) throw std::invalid_argument("camera-surfel id out of range");
       locate2(d, d.cs_tmap[i], d.cs_t[i], d.cs_tmap[i] + d.cam_toff, d.cs_t[i] + d.cam_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
       use_window(T.i0a[i]); use_window(T.i0b[i]);
-      for (int k = 0; k < 4; ++k) border_flag[T.i0a[i] + k] = 1;
+      for (int k = 0; k < 4; ++k) border_flag_cs[T.i0a[i] + k] = 1;
       rho_used[T.ib[i]] = 1;
       rho_anchor[T.ib[i]] = std::max(rho_anchor[T.ib[i]], T.i0b[i] + 3);
     }
     if (T.n) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
+  surfel_thread.join();
+  if (surfel_error) std::rethrow_exception(surfel_error);
+  for (int i = 0; i < n; ++i) { knot_used[i] |= knot_used_surfel[i]; border_flag[i] |= border_flag_cs[i]; }
+  if (surfel_sens) sens_used[TB_LQ] = sens_used[TB_LP] = true;
   std::set<int> border_knots;
   for (int i = 0; i < n; ++i) if (border_flag[i]) border_knots.insert(i);
   if (border_knots.size() > 16) border_knots.clear();  // not an arrow structure: leave those knots in the band
@@ -395,9 +409,19 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
     const int l = T.ia[i];
     const int rs = L.row_start[l];
     if (L.row_start[l + 1] == rs) continue;
-    for (int c = 0; c < 24; ++c) L.row_pos[rs + c] = col_pos<RT_CAM>(P, i, c);
-    for (int c = 24; c < 48; ++c) L.row_pos[rs + T.ib[i] + (c - 24)] = col_pos<RT_CAM>(P, i, c);
-    for (int c = 48; c < 54; ++c) L.row_pos[rs + 24 + (c - 48)] = col_pos<RT_CAM>(P, i, c);
+    // same values as col_pos<RT_CAM>(P, i, c), c = 0..53, written window by window (this loop is per camera residual: 32 k at C2)
+    auto window = [&](int i0, int* dst) {   // [r3 of knots i0..i0+3 | so3 of knots i0..i0+3], 3 dims each
+      for (int k = 0; k < 4; ++k) {
+        const int pr = P.pos_r3[i0 + k], ps = P.pos_so3[i0 + k];
+        for (int d3 = 0; d3 < 3; ++d3) { dst[3 * k + d3] = pr < 0 ? -1 : pr + d3; dst[12 + 3 * k + d3] = ps < 0 ? -1 : ps + d3; }
+      }
+    };
+    window(T.i0a[i], &L.row_pos[rs]);
+    window(T.i0b[i], &L.row_pos[rs + T.ib[i]]);
+    for (int d3 = 0; d3 < 3; ++d3) {
+      L.row_pos[rs + 24 + d3] = P.pos_sens[TB_CQ] < 0 ? -1 : P.pos_sens[TB_CQ] + d3;
+      L.row_pos[rs + 27 + d3] = P.pos_sens[TB_CP] < 0 ? -1 : P.pos_sens[TB_CP] + d3;
+    }
   }
   for (size_t l = 0; l + 1 < L.row_start.size(); ++l) {
     acc.begin();
