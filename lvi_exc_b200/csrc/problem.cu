@@ -272,9 +272,25 @@ void problem_linearize(lvi_problem* p, double* cost_d) {
 void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active, bool inactive) {
   LVI_CUDA(cudaMemsetAsync(cost_d, 0, sizeof(double), p->ctx->stream));
   problem_set_param_source(p, x_d);
-  launch_cost<RT_GYRO>(p, cost_d, active, inactive); launch_cost<RT_ACCEL>(p, cost_d, active, inactive);
-  launch_cost<RT_SURFEL>(p, cost_d, active, inactive); launch_cost<RT_CAM>(p, cost_d, active, inactive);
-  launch_cost<RT_CAMSURF>(p, cost_d, active, inactive); launch_cost<RT_ORIENT>(p, cost_d, active, inactive);
+  {  // like the normal-equation kernels: camera | surfel | the rest, side by side
+    lvi_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    LVI_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    for (int i = 0; i < 2; ++i) LVI_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+    launch_cost<RT_CAM>(p, cost_d, active, inactive);
+    {
+      struct Restore { lvi_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, st};
+      ctx->stream = ctx->aux[0];
+      launch_cost<RT_SURFEL>(p, cost_d, active, inactive);
+      ctx->stream = ctx->aux[1];
+      launch_cost<RT_GYRO>(p, cost_d, active, inactive); launch_cost<RT_ACCEL>(p, cost_d, active, inactive);
+      launch_cost<RT_CAMSURF>(p, cost_d, active, inactive); launch_cost<RT_ORIENT>(p, cost_d, active, inactive);
+    }
+    for (int i = 0; i < 2; ++i) {
+      LVI_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+      LVI_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+    }
+  }
   problem_set_param_source(p, p->X.p);
 }
 

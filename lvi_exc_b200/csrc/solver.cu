@@ -923,13 +923,25 @@ __global__ void __launch_bounds__(256) band_backsolve_ll_kernel(BandSys S) {
 
 // dense Cholesky of the border Schur complement S (nbo x nbo, lower, column-major ld = ldc) with the rhs carried as row nbo,
 // then x2 = L^-T z2.  One CTA.
-__global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
-  const int n = S.nbo, ld = S.ldc, tid = threadIdx.x;
-  double* C = S.C;
+__global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S, int in_smem) {
+  extern __shared__ double corner_smem[];
+  const int n = S.nbo, tid = threadIdx.x;
   double* x2 = S.x + static_cast<size_t>(S.NT) * kTile;
   __shared__ double xs[1024];
   __shared__ int bad;
   if (tid == 0) bad = 0;
+  // the corner is small (45 rows at C2) and every pivot is three dependent passes over it: from shared memory a pass costs a barrier,
+  // from global memory an L2 round trip (64 us -> 10 us at C2); large corners (no shared-memory budget) stay in global memory
+  double* C = S.C;
+  int ld = S.ldc;
+  if (in_smem) {
+    const int lds = n + 2;
+    for (int e = tid; e < (n + 1) * (n + 1); e += 256) {
+      const int i = e % (n + 1), c = e / (n + 1);
+      corner_smem[i + lds * c] = S.C[i + static_cast<size_t>(S.ldc) * c];
+    }
+    C = corner_smem; ld = lds;
+  }
   __syncthreads();
   for (int j = 0; j < n; ++j) {
     double d = C[j + static_cast<size_t>(ld) * j];
@@ -946,7 +958,7 @@ __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
     }
     __syncthreads();
   }
-  for (int i = tid; i < ld; i += 256) xs[i] = 0.0;
+  for (int i = tid; i < S.ldc; i += 256) xs[i] = 0.0;
   __syncthreads();
   if (tid < 32) {
     for (int c = n - 1; c >= 0; --c) {
@@ -959,7 +971,7 @@ __global__ void __launch_bounds__(256) corner_solve_kernel(BandSys S) {
     }
   }
   __syncthreads();
-  for (int i = tid; i < ld; i += 256) x2[i] = xs[i];
+  for (int i = tid; i < S.ldc; i += 256) x2[i] = xs[i];
   if (tid == 0 && bad) *S.fail = 1;
 }
 
@@ -1206,17 +1218,24 @@ void init_second_level(const BandSys& A, BandSys& B) {
   B.T = B.NT - 1;                                   // dense
   B.RB = (B.nbo + 1 + kTile - 1) / kTile; B.TPC = B.T + 1 + B.RB; B.ldc = B.RB * kTile;
 }
+static void launch_corner_solve(lvi_ctx* ctx, const BandSys& S) {
+  const size_t need = static_cast<size_t>(S.nbo + 1) * (S.nbo + 2) * sizeof(double);
+  const bool in_smem = need <= 160 * 1024;
+  static size_t attr = 48 * 1024;
+  if (in_smem && need > attr) { LVI_CUDA(cudaFuncSetAttribute(corner_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need))); attr = need; }
+  LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, in_smem ? need : 0, S, in_smem ? 1 : 0);
+}
 // everything after the factorisation of A: corner (directly, or through the second-level system), then the back substitution
 static void band_solve_only(lvi_ctx* ctx, BandSys& A, BandSys& A2) {
   if (A.n_mid > 0) {
     const int ntile = A2.NT * A2.TPC;
     LVI_LAUNCH(ctx, corner_to_second_level_kernel, ntile + 4, 256, 0, A, A2);
     band_factor_only(ctx, A2, false);
-    LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A2);
+    launch_corner_solve(ctx, A2);
     band_backsolve_only(ctx, A2);
     LVI_LAUNCH(ctx, second_level_solution_kernel, (A.ldc + 255) / 256, 256, 0, A, A2);
   } else {
-    LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, 0, A);
+    launch_corner_solve(ctx, A);
   }
   band_backsolve_only(ctx, A);
 }
