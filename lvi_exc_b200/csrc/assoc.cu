@@ -93,13 +93,15 @@ __device__ __forceinline__ int sel_hash_slot(int* hkey, int plane) {  // find-or
 }
 
 __global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw, int n_rings,
-                                                                       int W, int H, int k_per_ring, int32_t* __restrict__ sel, int* __restrict__ overflow) {
+                                                                       int W, int H, int k_per_ring, int32_t* __restrict__ sel, int* __restrict__ overflow,
+                                                                       int32_t* __restrict__ ring_overflow) {
   __shared__ int hkey[kSelWarps][kSelHash], hcnt[kSelWarps][kSelHash];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
   const int ring = blockIdx.x * kSelWarps + warp;
   if (ring >= n_rings) return;
   const int scan = ring / H, h = ring % H;
+  bool full = false;   // this lane could not place its plane in the table
   int* hk = hkey[warp]; int* hc = hcnt[warp];
   for (int i = lane; i < kSelHash; i += 32) { hk[i] = -1; hc[i] = 0; }
   __syncwarp();
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int3
         leaders &= leaders - 1;
         if (lane == l) {
           const int sl = sel_hash_slot(hk, c);
-          if (sl < 0) { atomicExch(overflow, 1); base = 0; }
+          if (sl < 0) { full = true; base = 0; }
           else { base = hc[sl]; hc[sl] = base + __popc(grp); }
         }
         __syncwarp(hits);
@@ -133,6 +135,12 @@ __global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int3
     if (w < W) selrow[static_cast<int64_t>(w) * H] = rank;
   }
   __syncwarp();
+  // More than kSelHash distinct surfels on one ring (a ground ring at 20 - 30 m radius crosses 250 - 380 half-metre voxels): the ring is
+  // handed to assoc_select_dense_kernel, which has no table.  The reference has no such limit (surfel_association.cpp:111-159).
+  if (__any_sync(FULL, full)) {
+    if (lane == 0) { ring_overflow[ring] = 1; atomicExch(overflow, 1); }
+    return;
+  }
   // pass 2: keep hits[step*(s+1)-1], s < k, of planes with >= 2k hits (:128-136); timestamp == 0 points are never emitted (:141-143)
   for (int w0 = 0; w0 < W; w0 += 32) {
     const int w = w0 + lane;
@@ -155,6 +163,41 @@ __global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int3
       }
     }
     selrow[static_cast<int64_t>(w) * H] = out;
+  }
+}
+
+// Fallback for the rings assoc_select_kernel flagged: one CTA per such ring, the ring's candidates in shared memory, rank and total of
+// every hit by direct counting over the ring (O(W^2) compares: at most 8 M for W = 4096, and only for the few rings that need it).
+__global__ void __launch_bounds__(256) assoc_select_dense_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw, int n_rings,
+                                                                 int W, int H, int k_per_ring, int32_t* __restrict__ sel,
+                                                                 const int32_t* __restrict__ ring_overflow) {
+  __shared__ int32_t row_s[4096];
+  for (int ring = blockIdx.x; ring < n_rings; ring += gridDim.x) {
+    if (!ring_overflow[ring]) continue;   // block-uniform
+    const int scan = ring / H, h = ring % H;
+    const int32_t* row = cand + (static_cast<int64_t>(scan) * H + h) * W;
+    int32_t* selrow = sel + static_cast<int64_t>(scan) * W * H + h;
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) row_s[w] = row[w];
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+      const int c = row_s[w];
+      int out = -1;
+      if (c >= 0) {
+        int rank = 0, total = 0;
+        for (int v = 0; v < W; ++v) { const int same = row_s[v] == c; total += same; rank += same & (v < w); }
+        if (total >= k_per_ring * 2) {
+          int step = total / (k_per_ring + 1);
+          step = step > 1 ? step : 1;
+          const int r1 = rank + 1;
+          if (r1 % step == 0 && r1 / step >= 1 && r1 / step <= k_per_ring) {
+            const double ts = raw[(static_cast<int64_t>(scan) * H + h) * W + w].timestamp;
+            if (ts != 0.0) out = c;
+          }
+        }
+      }
+      selrow[static_cast<int64_t>(w) * H] = out;
+    }
   }
 }
 
@@ -225,22 +268,25 @@ static void associate_device(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_sur
   LVI_LAUNCH(ctx, assoc_hit_kernel, grid_for(n, 256, ctx->sm_count, 8), 256, 0, static_cast<const char*>(map_d), stride, n, m->grid_d.p,
              m->cell2leaf.n ? m->cell2leaf.p : nullptr, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p, s->p4.p, s->bmin.p, s->bmax.p,
              radius, cand.p);
-  DBuf<int> overflow(1);
-  overflow.zero(st);
   const int n_rings = n_scans * H;
-  LVI_LAUNCH(ctx, assoc_select_kernel, (n_rings + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, cand.p, raw_d, n_rings, W, H, k, sel.p, overflow.p);
+  DBuf<int> overflow(1);
+  DBuf<int32_t> ring_overflow(n_rings);
+  overflow.zero(st); ring_overflow.zero(st);
+  LVI_LAUNCH(ctx, assoc_select_kernel, (n_rings + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, cand.p, raw_d, n_rings, W, H, k, sel.p, overflow.p,
+             ring_overflow.p);
+  // rings with more distinct surfels than the warp table holds (rare; none at C2): every CTA looks at its rings' flags and leaves at once
+  // when there is nothing to do, so the launch costs a few microseconds and saves a host round trip
+  LVI_LAUNCH(ctx, assoc_select_dense_kernel, std::min(n_rings, ctx->sm_count * 8), 256, 0, cand.p, raw_d, n_rings, W, H, k, sel.p, ring_overflow.p);
   LVI_LAUNCH(ctx, assoc_flag_kernel, grid_for(n, 256, ctx->sm_count, 8), 256, 0, sel.p, n, flag.p);
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, static_cast<int>(n), st);
   DBuf<char> tmp(tb + 16);
   LVI_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, rank.p, static_cast<int>(n), st));
   ctx->launches += 2;
-  int last_rank = 0, last_flag = 0, h_overflow = 0;
-  LVI_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, 4, cudaMemcpyDeviceToHost, st));
+  int last_rank = 0, last_flag = 0;
   LVI_CUDA(cudaMemcpyAsync(&last_rank, rank.p + n - 1, 4, cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaMemcpyAsync(&last_flag, flag.p + n - 1, 4, cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaStreamSynchronize(st));
-  LVI_REQUIRE(h_overflow == 0, LVI_ERR_INVALID, "lvi_associate: more than 256 distinct surfels hit by one ring (not supported)");
   const int64_t total = static_cast<int64_t>(last_rank) + last_flag;
   if (n_all) *n_all = total;
   if (n_out) *n_out = (total + time_step - 1) / time_step;

@@ -1,4 +1,5 @@
 // capi.cu — context management and misc entry points of the C-ABI (include/lvi_exc_b200.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -53,6 +54,21 @@ static void ctx_init(lvi_ctx* c, int device) {
   uint64_t keep = UINT64_MAX;
   LVI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   tl_stream = c->stream;
+  // Grow the pool ONCE, here, instead of inside the first solve: a C2 problem takes ~1.1 GB of solver buffers (tile stores + flagged
+  // copies) and the first cudaMallocAsync of that size is a synchronous driver allocation of tens of milliseconds.  LVI_POOL_RESERVE_MB
+  // overrides the default (2 GB of the 180 GB); 0 disables it.
+  {
+    size_t mb = 2048;
+    if (const char* e = std::getenv("LVI_POOL_RESERVE_MB")) mb = static_cast<size_t>(std::strtoull(e, nullptr, 10));
+    if (mb > 0) {
+      void* p = nullptr;
+      if (cudaMallocAsync(&p, mb << 20, c->stream) == cudaSuccess) cudaFreeAsync(p, c->stream);
+      else cudaGetLastError();   // a smaller device: the pool simply grows on demand
+    }
+  }
+  LVI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scal), 64 * sizeof(double)));
+  for (int i = 0; i < 16; ++i) { cudaEvent_t e; LVI_CUDA(cudaEventCreate(&e)); c->timing_events.push_back(e); }
+  LVI_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 int lvi_ctx_create(int device, void* nccl_comm, int rank, int world, lvi_ctx** out) {
@@ -105,6 +121,8 @@ int lvi_ctx_destroy(lvi_ctx* ctx) {
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // hand cached blocks back to the driver
     for (int i = 0; i < 2; ++i) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     cudaStreamDestroy(ctx->stream);
     if (tl_stream == ctx->stream) tl_stream = nullptr;
   }

@@ -61,6 +61,25 @@ struct lvi_ctx {
   // two auxiliary streams + fork/join events: independent kernels of one phase (the per-type normal-equation kernels) run side by side
   cudaStream_t aux[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  // Per-context kernel state.  Function attributes (opt-in dynamic shared memory), occupancy figures and __device__ symbols belong to
+  // ONE device: a process that drives two GPUs has two contexts, and each sets them up for its own device on first use.
+  struct KernelState {
+    bool pair_table = false;          // problem.cu: g_pair_table uploaded to this device
+    bool lin_attr[8] = {};            // problem.cu: linearize_kernel<TYPE> shared-memory attribute set
+    int fac_resident = 0;             // solver.cu: co-resident CTAs of band_factor_ll_kernel (0 = not yet queried)
+    int bs_resident = 0;              //            ... of band_backsolve_ll_kernel
+    size_t corner_attr = 48 * 1024;   //            dynamic shared memory granted to corner_solve_kernel so far
+    size_t schur_attr = 48 * 1024;    //            ... to schur_eliminate_kernel
+    bool selftest_done = false;
+  } ks;
+  // host-side resources every solve needs, made once per context (cudaMallocHost / cudaEventCreate cost 0.1 - 1 ms each on a cold driver)
+  double* h_scal = nullptr;           // pinned mirror of a problem's scalar block (64 doubles)
+  std::vector<cudaEvent_t> timing_events;   // reused by the LM loop's phase timers
+  size_t timing_used = 0;
+  cudaEvent_t timing_event() {
+    if (timing_used == timing_events.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; timing_events.push_back(e); }
+    return timing_events[timing_used++];
+  }
 };
 
 namespace lvi {

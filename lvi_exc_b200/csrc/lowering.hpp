@@ -169,7 +169,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   }
   {
     LoweredTable& T = L.tab[RT_ORIENT];
-    need(d.orient_t, d.n_orient, "orient_t"); need(d.orient_q, d.n_orient, "orient_q");
+    need(d.orient_t, d.n_orient, "orient_t"); need(d.orient_q, d.n_orient, "orient_q"); need(d.orient_weight, d.n_orient, "orient_weight");
     T.n = d.n_orient; T.active = so3_free;
     T.i0a.resize(T.n); T.ua.resize(T.n); T.v.assign(d.orient_q, d.orient_q + 4 * static_cast<size_t>(T.n)); T.weight.assign(d.orient_weight, d.orient_weight + T.n);
     for (int i = 0; i < T.n; ++i) {
@@ -188,6 +188,8 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) knot_used_surfel[k] = 1; };
     LoweredTable& T = L.tab[RT_SURFEL];
     need(d.surfel_t, d.n_surfel, "surfel_t"); need(d.surfel_point, d.n_surfel, "surfel_point"); need(d.surfel_plane, d.n_surfel, "surfel_plane");
+    need(d.surfel_tmap, d.n_surfel, "surfel_tmap"); need(d.surfel_weight, d.n_surfel, "surfel_weight"); need(d.surfel_huber, d.n_surfel, "surfel_huber");
+    need(d.planes, d.n_surfel, "planes");
     if (d.n_surfel && !L.has_r3) throw std::invalid_argument("surfel residuals need the R3 spline");
     T.n = d.n_surfel; T.active = traj_free || !d.lock_lidar_q || !d.lock_lidar_p;
     T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n);
@@ -210,9 +212,18 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   {
     LoweredTable& T = L.tab[RT_CAM];
     need(d.cam_t0_ref, d.n_cam, "cam_t0_ref"); need(d.cam_uv_ref, d.n_cam, "cam_uv_ref"); need(d.cam_landmark, d.n_cam, "cam_landmark");
+    need(d.cam_t0_obs, d.n_cam, "cam_t0_obs"); need(d.cam_uv_obs, d.n_cam, "cam_uv_obs"); need(d.cam_weight, d.n_cam, "cam_weight");
+    need(d.cam_huber, d.n_cam, "cam_huber"); need(d.rho, d.n_cam, "rho");
     if (d.n_cam && !L.has_r3) throw std::invalid_argument("camera residuals need the R3 spline");
     T.n = d.n_cam;
-    T.active = traj_free || !d.lock_cam_q || !d.lock_cam_p || d.rho_locked == nullptr;
+    // Ceres keeps a residual block while ANY of its parameter blocks is free.  Landmarks are unlocked by default (K/sfm/landmark.h), so
+    // what counts is whether some landmark of this table is actually free, not whether the caller passed a lock array.
+    bool any_rho_free = false;
+    for (int i = 0; i < d.n_cam && !any_rho_free; ++i) {
+      const int l = d.cam_landmark[i];
+      any_rho_free = l >= 0 && l < d.n_landmarks && !(d.rho_locked && d.rho_locked[l]);
+    }
+    T.active = traj_free || !d.lock_cam_q || !d.lock_cam_p || any_rho_free;
     T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n); T.v.resize(4 * static_cast<size_t>(T.n));
     T.ia.assign(d.cam_landmark, d.cam_landmark + T.n);
     T.weight.assign(d.cam_weight, d.cam_weight + T.n); T.huber.assign(d.cam_huber, d.cam_huber + T.n);
@@ -241,9 +252,18 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   {
     LoweredTable& T = L.tab[RT_CAMSURF];
     need(d.cs_t, d.n_camsurf, "cs_t"); need(d.cs_uv, d.n_camsurf, "cs_uv"); need(d.cs_landmark, d.n_camsurf, "cs_landmark"); need(d.cs_plane, d.n_camsurf, "cs_plane");
+    need(d.cs_tmap, d.n_camsurf, "cs_tmap"); need(d.cs_weight, d.n_camsurf, "cs_weight"); need(d.cs_huber, d.n_camsurf, "cs_huber");
+    need(d.planes, d.n_camsurf, "planes"); need(d.rho, d.n_camsurf, "rho");
     if (d.n_camsurf && !L.has_r3) throw std::invalid_argument("camera-surfel residuals need the R3 spline");
     T.n = d.n_camsurf;
-    T.active = 1;  // the rho block is added (and read as a constant, Q4); with the camera unlocked in every caller the block set is never all-constant
+    // blocks: trajectory, camera q,p, lidar q,p, plane (constant), rho (added as a block, read as a constant, Q4): the table is dropped
+    // from the reduced program only when every one of them is constant
+    bool any_rho_free = false;
+    for (int i = 0; i < d.n_camsurf && !any_rho_free; ++i) {
+      const int l = d.cs_landmark[i];
+      any_rho_free = l >= 0 && l < d.n_landmarks && !(d.rho_locked && d.rho_locked[l]);
+    }
+    T.active = traj_free || !d.lock_cam_q || !d.lock_cam_p || !d.lock_lidar_q || !d.lock_lidar_p || any_rho_free;
     T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n);
     T.v.assign(d.cs_uv, d.cs_uv + 2 * static_cast<size_t>(T.n)); T.ia.assign(d.cs_plane, d.cs_plane + T.n); T.ib.assign(d.cs_landmark, d.cs_landmark + T.n);
     T.weight.assign(d.cs_weight, d.cs_weight + T.n); T.huber.assign(d.cs_huber, d.cs_huber + T.n);
@@ -252,12 +272,13 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
       if (d.cs_t[i] < d.cs_tmap[i]) throw RangeError("Time spans are not ordered");
       if (T.ia[i] < 0 || T.ia[i] >= d.n_planes || T.ib[i] < 0 || T.ib[i] >= d.n_landmarks) throw std::invalid_argument("camera-surfel id out of range");
       locate2(d, d.cs_tmap[i], d.cs_t[i], d.cs_tmap[i] + d.cam_toff, d.cs_t[i] + d.cam_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
+      if (!T.active) continue;
       use_window(T.i0a[i]); use_window(T.i0b[i]);
       for (int k = 0; k < 4; ++k) border_flag_cs[T.i0a[i] + k] = 1;
       rho_used[T.ib[i]] = 1;
       rho_anchor[T.ib[i]] = std::max(rho_anchor[T.ib[i]], T.i0b[i] + 3);
     }
-    if (T.n) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
+    if (T.n && T.active) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
   surfel_thread.join();
   if (surfel_error) std::rethrow_exception(surfel_error);

@@ -31,15 +31,14 @@ constexpr int kLinWarps = 2;
 // per accumulated pair.)
 constexpr int kMaxPairs = LVI_MAX_COLS * (LVI_MAX_COLS + 1) / 2;
 __device__ unsigned short g_pair_table[kMaxPairs];
-static void ensure_pair_table() {
-  static bool done = false;
-  if (done) return;
+static void ensure_pair_table(lvi_ctx* ctx) {   // the symbol lives on ONE device: uploaded once per context
+  if (ctx->ks.pair_table) return;
   std::vector<unsigned short> h(kMaxPairs);
   int p = 0;
   for (int c1 = 0; c1 < LVI_MAX_COLS; ++c1)
     for (int c2 = 0; c2 <= c1; ++c2) h[p++] = static_cast<unsigned short>(c1 << 8 | c2);
   LVI_CUDA(cudaMemcpyToSymbol(g_pair_table, h.data(), sizeof(unsigned short) * kMaxPairs));
-  done = true;
+  ctx->ks.pair_table = true;
 }
 
 template <int TYPE>
@@ -204,8 +203,9 @@ template <int TYPE>
 static void launch_linearize(lvi_problem* p) {
   const ResTable& T = p->view.tab[TYPE];
   if (T.n == 0 || !T.active) return;
-  ensure_pair_table();
-  static bool attr_set = false;
+  ensure_pair_table(p->ctx);
+  static_assert(RT_COUNT <= 8, "KernelState::lin_attr");
+  bool& attr_set = p->ctx->ks.lin_attr[TYPE];
   const size_t smem = static_cast<size_t>(kLinWarps) * RTr<TYPE>::warp_doubles * sizeof(double);
   if (!attr_set) {
     LVI_CUDA(cudaFuncSetAttribute(linearize_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -476,7 +476,7 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
   p->blocks.upload(fb.data(), fb.size(), st);
   p->nt = L.nt();
   p->scal.alloc(64);
-  LVI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_scal), 64 * sizeof(double)));
+  p->h_scal = ctx->h_scal;   // pinned mirror, owned by the context
   LVI_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope
   lap("rest + sync");
   return p.release();

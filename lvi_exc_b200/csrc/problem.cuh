@@ -103,10 +103,9 @@ struct lvi_problem {
   lvi::DBuf<double> Hrx, Hrr, yrho;
   lvi::DBuf<int> fail;
   lvi::DBuf<double> g, scale, diag, y, delta, scal;  // scal: small scalar scratch (cost etc.)
-  double* h_scal = nullptr;                          // pinned host mirror of scal
+  double* h_scal = nullptr;                          // pinned host mirror of scal (the context's)
   int nt = 0;
   bool has_solver_buffers = false;
-  ~lvi_problem() { if (h_scal) cudaFreeHost(h_scal); }
 };
 
 namespace lvi {

@@ -1143,7 +1143,7 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
   LVI_REQUIRE(A.work_i && A.work_d && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
   A.epoch = next_epoch();   // flag value of this factorisation's flagged tile copies (never cleared)
   if (std::getenv("LVI_POTRF_SELFTEST")) {
-    static bool done = false;
+    bool& done = ctx->ks.selftest_done;
     if (!done) {
       done = true;
       std::vector<double> h(kTileElems);
@@ -1168,7 +1168,7 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
   LVI_CUDA(cudaMemsetAsync(A.work_i, 0, A.work_i_count() * sizeof(int), st));
   LVI_CUDA(cudaMemsetAsync(A.work_d, 0, A.work_d_count() * sizeof(double), st));
   constexpr size_t smem = sizeof(FacShared);
-  static int resident = 0;
+  int& resident = ctx->ks.fac_resident;
   if (!resident) {
     LVI_CUDA(cudaFuncSetAttribute(band_factor_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
@@ -1202,7 +1202,7 @@ static void band_backsolve_only(lvi_ctx* ctx, BandSys& A) {
   if (A.NT == 0) return;
   LVI_REQUIRE(A.work_i && A.ll, LVI_ERR_INVALID, "band solver workspace missing");
   constexpr size_t smem = sizeof(BsShared);
-  static int resident = 0;
+  int& resident = ctx->ks.bs_resident;
   if (!resident) {
     LVI_CUDA(cudaFuncSetAttribute(band_backsolve_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_backsolve_ll_kernel), 256, smem);
@@ -1221,7 +1221,7 @@ void init_second_level(const BandSys& A, BandSys& B) {
 static void launch_corner_solve(lvi_ctx* ctx, const BandSys& S) {
   const size_t need = static_cast<size_t>(S.nbo + 1) * (S.nbo + 2) * sizeof(double);
   const bool in_smem = need <= 160 * 1024;
-  static size_t attr = 48 * 1024;
+  size_t& attr = ctx->ks.corner_attr;
   if (in_smem && need > attr) { LVI_CUDA(cudaFuncSetAttribute(corner_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need))); attr = need; }
   LVI_LAUNCH(ctx, corner_solve_kernel, 1, 256, in_smem ? need : 0, S, in_smem ? 1 : 0);
 }
@@ -1309,7 +1309,7 @@ static size_t max_row_len(const lvi_problem* p) {
 }
 static void schur_eliminate(lvi_problem* p, double inv_radius) {
   if (p->L.n_rho == 0) return;
-  static size_t attr = 48 * 1024;
+  size_t& attr = p->ctx->ks.schur_attr;
   const size_t smem = max_row_len(p) * 12 + 16;
   if (smem > attr) { LVI_CUDA(cudaFuncSetAttribute(schur_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = smem; }
   LVI_LAUNCH(p->ctx, schur_eliminate_kernel, p->L.n_rho, 128, smem, p->A, p->schur, p->scale.p, p->diag.p, inv_radius, p->g.p);
@@ -1360,9 +1360,10 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   struct Span { cudaEvent_t a, b; float* accu; };
   std::vector<Span> spans;
   float tj = 0, tl = 0;
+  ctx->timing_used = 0;   // events come from the context's pool (created once, reused by every solve)
   auto tic = [&](float& accu) {
-    Span sp{nullptr, nullptr, &accu};
-    LVI_CUDA(cudaEventCreate(&sp.a)); LVI_CUDA(cudaEventCreate(&sp.b));
+    Span sp{ctx->timing_event(), ctx->timing_event(), &accu};
+    LVI_REQUIRE(sp.a && sp.b, LVI_ERR_CUDA, "cudaEventCreate failed");
     LVI_CUDA(cudaEventRecord(sp.a, st));
     spans.push_back(sp);
   };
@@ -1486,7 +1487,6 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   for (Span& sp : spans) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.accu += ms;
-    cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
   }
   (void)cudaGetLastError();
   S.num_iterations = it;

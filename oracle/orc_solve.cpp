@@ -1066,6 +1066,8 @@ int orc_traj_eval(const lvi_problem_desc* d, double t, double* out) {
   } catch (const std::exception& e) { g_err = e.what(); return LVI_ERR_RANGE; }
 }
 int orc_num_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to every rank: callers that time the oracle set the thread count explicitly
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // ScanUndistortion::undistort (L/include/core/scan_undistortion.h:132-180) + evaluateLidarPose
 // (L/src/core/trajectory_manager_lvi.cpp:398-408) for n_scans x pts_per_scan raw points; target_time[s] is the pose the

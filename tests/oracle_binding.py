@@ -51,11 +51,19 @@ def lib() -> C.CDLL:
         L.orc_problem_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
         L.orc_traj_eval.argtypes = [C.POINTER(ProblemDesc), C.c_double, c_double_p]
         L.orc_last_error.restype = C.c_char_p
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_undistort.argtypes = [C.POINTER(ProblemDesc), vp, C.c_int32, C.c_int64, c_double_p, C.c_int, vp]
         L.orc_associate_landmarks.argtypes = [vp, c_double_p, C.c_int64, C.c_double, c_int32_p]
         L.orc_associate_landmarks.restype = None
         _lib = L
     return _lib
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1; timed runs set the count explicitly)"""
+    lib().orc_set_num_threads(int(n))
+    return lib().orc_num_threads()
 
 
 class OracleVoxelMap:

@@ -129,6 +129,42 @@ def test_association_ragged_scan(cuda_backend):
     gmap.close()
 
 
+def _cylinder_scans(S=8, H=16, W=1800, radius=30.0):
+    """organised scans of a cylindrical wall of 30 m radius: every ring crosses ~377 half-metre voxels, each a planar surfel"""
+    from lvi_exc_b200._capi import RAW_POINT_DTYPE
+    rng = np.random.default_rng(5)
+    az = 2 * np.pi * (np.arange(W) + 0.5) / W
+    r = radius + 0.003 * rng.standard_normal((S, H, W))
+    sm = np.zeros((S, H, W, 8), np.float32)
+    sm[..., 0] = r * np.cos(az); sm[..., 1] = r * np.sin(az)
+    sm[..., 2] = 0.03 + 0.027 * np.arange(H)[None, :, None] + 0.002 * np.arange(S)[:, None, None]
+    sm[..., 3] = 1.0
+    raw = np.zeros((S, H, W), RAW_POINT_DTYPE)
+    raw["x"], raw["y"], raw["z"] = sm[..., 0], sm[..., 1], sm[..., 2]
+    raw["timestamp"] = 1.0 + 0.1 * np.arange(S)[:, None, None] + 55.296e-6 * np.arange(W)[None, None, :]
+    return sm, raw
+
+
+def test_association_more_than_256_planes_on_one_ring(cuda_backend):
+    """the reference has no limit on the planes one ring may hit (L/src/core/surfel_association.cpp:111-159); the warp-table fast path
+    holds 256 and hands fuller rings to the dense fallback kernel"""
+    sm, raw = _cylinder_scans()
+    cloud = sm.reshape(-1, 8)
+    gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
+    ov = ob.OracleVoxelMap(cloud, 0.5); osf = ob.OracleSurfels(ov, 0.6)
+    assert gmap.num_planes == osf.count and gmap.num_planes > 300
+    for k, step in ((2, 1), (2, 10)):
+        sp_g = cuda_backend.associate(gmap, sm, raw, 0.05, k, step)
+        sp_o, n_all = osf.associate(sm, raw, 0.05, k, step, mode=0)
+        assert cuda_backend.last_n_all == n_all and len(sp_g) == len(sp_o)
+        for f in ("timestamp", "point", "point_in_map", "plane_id"):
+            assert np.array_equal(sp_g[f], sp_o[f]), f
+    sp_all, _ = osf.associate(sm[:1], raw[:1], 0.05, 2, 1, mode=1)
+    per_ring = [len(np.unique(sp_all["plane_id"][np.abs(sp_all["point"][:, 2] - (0.03 + 0.027 * h)) < 1e-3])) for h in range(16)]
+    assert max(per_ring) > 256, per_ring   # the case really exercises the fallback
+    gmap.close()
+
+
 def test_undistort_transform_traj_eval(cuda_backend):
     seq = _sequence(2.0, 400)
     mgr = _manager(seq)
