@@ -41,6 +41,7 @@ typedef enum lvi_status {
 typedef struct lvi_ctx lvi_ctx;         /* one CUDA device + stream (+ optional NCCL communicator) */
 typedef struct lvi_voxel_map lvi_voxel_map; /* replaces pclomp::VoxelGridCovariance (N/voxel_grid_covariance_omp.h:92-300) */
 typedef struct lvi_surfel_set lvi_surfel_set; /* replaces SurfelAssociation::surfel_planes_ (L/include/core/surfel_association.h:48-55) */
+typedef struct lvi_scan_batch lvi_scan_batch; /* replaces ScanUndistortion::scan_data_in_map_ / map_cloud_ (L/include/core/scan_undistortion.h:182-188) */
 typedef struct lvi_problem lvi_problem; /* replaces kontiki::TrajectoryEstimator + ceres::Problem (K/trajectory_estimator.h:19-135) */
 
 const char* lvi_last_error(void);
@@ -61,6 +62,11 @@ int lvi_ctx_synchronize(lvi_ctx* ctx);
 void* lvi_ctx_stream(lvi_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 int64_t lvi_ctx_launch_count(lvi_ctx* ctx);
+/* measurement: with timing enabled every kernel this context launches is bracketed by CUDA events on the stream it is launched on;
+ * lvi_ctx_kernel_times waits for the streams and drains what was recorded as text lines "kernel_name launches total_ms" (returns the
+ * length the full text needs; bench.py's per-kernel roofline figures come from here) */
+int lvi_ctx_kernel_timing(lvi_ctx* ctx, int enable);
+int64_t lvi_ctx_kernel_times(lvi_ctx* ctx, char* out, int64_t cap);
 /* host-side NCCL bootstrap helpers so a Python/C host can create the communicator without linking NCCL */
 int lvi_nccl_unique_id(void* id128 /* 128 bytes out */);
 int lvi_ctx_create_nccl(int device, const void* id128, int rank, int world, lvi_ctx** out);
@@ -285,6 +291,37 @@ int lvi_transform_scans(lvi_ctx* ctx, const void* scans_xyzi, int32_t n_scans, i
                         const double* poses, void* out_xyzi);
 int lvi_transform_scans_d(lvi_ctx* ctx, const void* scans_xyzi_d, int32_t n_scans, int64_t pts_per_scan,
                           const double* poses, void* out_xyzi_d);
+
+/* ---- scan batches: the map-frame scans kept in HBM between the steps of one data association ------------------------------- */
+/* The reference's ScanUndistortion keeps the de-skewed scans (scan_data_in_map_) and their concatenation (map_cloud_) as PCL clouds and
+ * hands them to LiDAROdometry / SurfelAssociation (L/include/core/scan_undistortion.h:59-116,182-188; driver T:1169-1210).  A scan batch is
+ * that object on the device: n_scans organised scans of pts_per_scan points in ONE frame, stored packed (16 B per point: x, y, z,
+ * intensity) with each scan's min/max, so the voxel build and the association stream 16 B per point and the map build needs no min/max
+ * pass.  The 32 B pcl::PointXYZI layout exists only at the boundary (import / export below). */
+/* ScanUndistortion::undistortScan / undistortScanInMap (same arguments as lvi_undistort_d), result kept as a batch */
+int lvi_scan_batch_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw_d, int32_t n_scans,
+                               int64_t pts_per_scan, const double* target_time, int correct_position, lvi_scan_batch** out,
+                               int32_t* n_bad_targets);
+/* pcl::transformPointCloud with one float 4x4 per scan (same as lvi_transform_scans_d), batch in -> new batch out */
+int lvi_scan_batch_transform(lvi_ctx* ctx, const lvi_scan_batch* in, const double* poses, lvi_scan_batch** out);
+/* import a device-resident PCL cloud (x,y,z float at offset 0, intensity at offset 16 when stride_bytes >= 20) as a batch */
+int lvi_scan_batch_from_xyzi_d(lvi_ctx* ctx, const void* xyzi_d, size_t stride_bytes, int32_t n_scans, int64_t pts_per_scan,
+                               lvi_scan_batch** out);
+/* write the batch as pcl::PointXYZI records (32 B: x,y,z,1,intensity,0,0,0) to a host (out_is_device = 0) or device buffer */
+int lvi_scan_batch_export_xyzi(lvi_ctx* ctx, const lvi_scan_batch* b, void* out_xyzi, int out_is_device);
+int lvi_scan_batch_destroy(lvi_scan_batch* b);
+int64_t lvi_scan_batch_num_points(const lvi_scan_batch* b);
+int32_t lvi_scan_batch_num_scans(const lvi_scan_batch* b);
+const void* lvi_scan_batch_points_d(const lvi_scan_batch* b); /* packed device buffer: float x,y,z,intensity per point */
+/* lvi_voxel_build over the scans of a batch.  scan_keep (host, [n_scans], may be NULL = all) selects the scans that make up the map
+ * cloud: LiDAROdometry::feedScan only adds KEY scans to it (L/src/core/lidar_odometry.cpp:89-128).  Point indices reported by
+ * lvi_voxel_export count the points of the selected scans in batch order (= the concatenated map_cloud_). */
+int lvi_voxel_build_batch(lvi_ctx* ctx, const lvi_scan_batch* batch, const uint8_t* scan_keep, float leaf_size, int min_points,
+                          double eig_mult, lvi_voxel_map** out);
+/* lvi_associate_d with the map-frame scans given as a batch (W x H must equal the batch's pts_per_scan) */
+int lvi_associate_batch(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s, const lvi_scan_batch* batch,
+                        const lvi_point_xyzit* scans_raw_d, int32_t W, int32_t H, double radius, int32_t k_per_ring,
+                        int32_t time_step, lvi_surfel_point* out_d, int64_t cap, int64_t* n_out, int64_t* n_all);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------------------- */
 /* Solves A x = rhs through the band+arrow tile Cholesky used by lvi_problem_solve (tests only). A_dense is

@@ -125,7 +125,7 @@ _lib = None
 # every symbol include/lvi_exc_b200.h declares (tests/test_abi.py checks the built library exports all of them)
 ABI_SYMBOLS = [
     "lvi_last_error", "lvi_abi_version", "lvi_abi_sizeof", "lvi_device_count", "lvi_ctx_create", "lvi_ctx_destroy", "lvi_ctx_synchronize",
-    "lvi_ctx_stream", "lvi_ctx_launch_count", "lvi_nccl_unique_id", "lvi_ctx_create_nccl",
+    "lvi_ctx_stream", "lvi_ctx_launch_count", "lvi_ctx_kernel_timing", "lvi_ctx_kernel_times", "lvi_nccl_unique_id", "lvi_ctx_create_nccl",
     "lvi_voxel_build", "lvi_voxel_build_d", "lvi_voxel_destroy", "lvi_voxel_num_leaves", "lvi_voxel_num_points",
     "lvi_voxel_grid", "lvi_voxel_export", "lvi_surfel_extract", "lvi_surfel_destroy", "lvi_surfel_count",
     "lvi_surfel_export", "lvi_associate", "lvi_associate_d", "lvi_solve_options_default", "lvi_problem_create",
@@ -133,6 +133,9 @@ ABI_SYMBOLS = [
     "lvi_problem_num_tangent", "lvi_problem_tangent_offset_knot", "lvi_problem_tangent_offset_block",
     "lvi_problem_jacobian_dense", "lvi_problem_bench_iterations", "lvi_problem_layout", "lvi_associate_landmarks", "lvi_undistort",
     "lvi_undistort_d", "lvi_transform_scans", "lvi_transform_scans_d", "lvi_trajectory_evaluate", "lvi_band_solve_dense",
+    "lvi_scan_batch_undistort_d", "lvi_scan_batch_transform", "lvi_scan_batch_from_xyzi_d", "lvi_scan_batch_export_xyzi",
+    "lvi_scan_batch_destroy", "lvi_scan_batch_num_points", "lvi_scan_batch_num_scans", "lvi_scan_batch_points_d",
+    "lvi_voxel_build_batch", "lvi_associate_batch",
 ]
 
 
@@ -157,6 +160,9 @@ def load() -> C.CDLL:
     lib.lvi_ctx_stream.restype = vp
     lib.lvi_ctx_launch_count.argtypes = [vp]
     lib.lvi_ctx_launch_count.restype = C.c_int64
+    lib.lvi_ctx_kernel_timing.argtypes = [vp, C.c_int]
+    lib.lvi_ctx_kernel_times.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.lvi_ctx_kernel_times.restype = C.c_int64
     for name in ("lvi_voxel_build", "lvi_voxel_build_d"):
         getattr(lib, name).argtypes = [vp, vp, C.c_size_t, C.c_int64, C.c_float, C.c_int, C.c_double, C.POINTER(vp)]
     lib.lvi_voxel_destroy.argtypes = [vp]
@@ -194,6 +200,19 @@ def load() -> C.CDLL:
     for name in ("lvi_transform_scans", "lvi_transform_scans_d"):
         getattr(lib, name).argtypes = [vp, vp, C.c_int32, C.c_int64, c_double_p, vp]
     lib.lvi_trajectory_evaluate.argtypes = [vp, C.POINTER(ProblemDesc), c_double_p, C.c_int64, c_double_p, c_double_p, c_uint8_p]
+    lib.lvi_scan_batch_undistort_d.argtypes = [vp, C.POINTER(ProblemDesc), vp, C.c_int32, C.c_int64, c_double_p, C.c_int, C.POINTER(vp), c_int32_p]
+    lib.lvi_scan_batch_transform.argtypes = [vp, vp, c_double_p, C.POINTER(vp)]
+    lib.lvi_scan_batch_from_xyzi_d.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int64, C.POINTER(vp)]
+    lib.lvi_scan_batch_export_xyzi.argtypes = [vp, vp, vp, C.c_int]
+    lib.lvi_scan_batch_destroy.argtypes = [vp]
+    lib.lvi_scan_batch_num_points.argtypes = [vp]
+    lib.lvi_scan_batch_num_points.restype = C.c_int64
+    lib.lvi_scan_batch_num_scans.argtypes = [vp]
+    lib.lvi_scan_batch_num_scans.restype = C.c_int32
+    lib.lvi_scan_batch_points_d.argtypes = [vp]
+    lib.lvi_scan_batch_points_d.restype = vp
+    lib.lvi_voxel_build_batch.argtypes = [vp, vp, c_uint8_p, C.c_float, C.c_int, C.c_double, C.POINTER(vp)]
+    lib.lvi_associate_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, vp, C.c_int64, c_int64_p, c_int64_p]
     lib.lvi_band_solve_dense.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     _lib = lib
     return lib

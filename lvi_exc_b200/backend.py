@@ -24,6 +24,40 @@ def _torch():
     return torch
 
 
+class CudaScanBatch:
+    """lvi_scan_batch: organised scans in one frame, packed in HBM (ScanUndistortion::scan_data_in_map_ on the device)."""
+
+    def __init__(self, backend: "CudaBackend", handle, S: int, H: int, W: int):
+        self.b, self.h, self.shape = backend, handle, (S, H, W)
+
+    def numpy(self) -> np.ndarray:
+        """the scans as pcl::PointXYZI records: [S, H, W, 8] float32 (x, y, z, 1, intensity, 0, 0, 0)"""
+        out = np.zeros(self.shape + (8,), dtype=np.float32)
+        check(self.b.lib.lvi_scan_batch_export_xyzi(self.b.ctx, self.h, C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def cpu(self):
+        return self
+
+    def close(self):
+        if self.h:
+            self.b.lib.lvi_scan_batch_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaMapCloud:
+    """the cloud a map is built from: the key scans of a batch (LiDAROdometry::updateKeyScan, L/src/core/lidar_odometry.cpp:89-104)"""
+
+    def __init__(self, batch: CudaScanBatch, keep: np.ndarray | None):
+        self.batch = batch
+        self.keep = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+
+
 class CudaSurfelMap:
     def __init__(self, backend: "CudaBackend", cloud, leaf: float, lam: float, min_points=6, eig_mult=0.01, min_leaf_points=10,
                  ransac_thr=0.05, min_inliers=20):
@@ -31,9 +65,14 @@ class CudaSurfelMap:
         lib = backend.lib
         self.vmap = C.c_void_p()
         self.surfels = C.c_void_p()
-        dev, n, stride, keep = backend._as_device_cloud(cloud)
-        self._keep = keep
-        check(lib.lvi_voxel_build_d(backend.ctx, dev, stride, n, leaf, min_points, eig_mult, C.byref(self.vmap)))
+        if isinstance(cloud, CudaScanBatch):
+            cloud = CudaMapCloud(cloud, None)
+        if isinstance(cloud, CudaMapCloud):
+            check(lib.lvi_voxel_build_batch(backend.ctx, cloud.batch.h, ptr(cloud.keep), leaf, min_points, eig_mult, C.byref(self.vmap)))
+        else:   # a PCL-shaped cloud (numpy / device tensor): the ABI's 32 B layout
+            dev, n, stride, keep = backend._as_device_cloud(cloud)
+            self._keep = keep
+            check(lib.lvi_voxel_build_d(backend.ctx, dev, stride, n, leaf, min_points, eig_mult, C.byref(self.vmap)))
         check(lib.lvi_surfel_extract(backend.ctx, self.vmap, lam, min_leaf_points, ransac_thr, min_inliers, C.byref(self.surfels)))
         self._keep = None  # the map keeps its own sorted copy of the points
         self.num_leaves = lib.lvi_voxel_num_leaves(self.vmap)
@@ -157,6 +196,19 @@ class CudaBackend:
     def synchronize(self):
         check(self.lib.lvi_ctx_synchronize(self.ctx))
 
+    def kernel_timing(self, enable: bool):
+        check(self.lib.lvi_ctx_kernel_timing(self.ctx, int(enable)))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (launches, total ms)} of the launches since timing was enabled / last drained (CUDA events on the launch stream)"""
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.lvi_ctx_kernel_times(self.ctx, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
     # ---- device-memory helpers (torch = allocator only) ------------------------------------------------------
     def to_device(self, a, cache: bool = False):
         """numpy -> device tensor; `cache=True` keeps the copy resident across calls (the raw scans are uploaded once)"""
@@ -196,20 +248,40 @@ class CudaBackend:
     def build_surfel_map(self, cloud, leaf, lam):
         return CudaSurfelMap(self, cloud, leaf, lam)
 
+    def batch_from_xyzi(self, scans_xyzi) -> CudaScanBatch:
+        """import PCL-shaped scans [S, H, W, >=3] float32 (numpy or device tensor) as a packed scan batch"""
+        t = self.to_device(scans_xyzi).contiguous()
+        S, H, W = t.shape[0], t.shape[1], t.shape[2]
+        h = C.c_void_p()
+        _torch().cuda.synchronize(self.device)
+        check(self.lib.lvi_scan_batch_from_xyzi_d(self.ctx, C.c_void_p(t.data_ptr()), t.shape[-1] * 4, S, H * W, C.byref(h)))
+        return CudaScanBatch(self, h, S, H, W)
+
+    def map_cloud(self, scans_in_map, keys=None):
+        """the cloud the map is built from: all scans, or the key scans only (first association)"""
+        if isinstance(scans_in_map, CudaScanBatch):
+            return CudaMapCloud(scans_in_map, keys)
+        a = scans_in_map if keys is None else scans_in_map[np.nonzero(keys)[0]]
+        return a.reshape(-1, a.shape[-1])
+
     def associate(self, smap: CudaSurfelMap, scans_in_map, scans_raw, radius, k, step):
         torch = _torch()
-        m = self.to_device(scans_in_map)
-        r = self.to_device(scans_raw, cache=True)
+        r = self.to_device(scans_raw, cache=True).contiguous()
         S, H, W = r.shape[0], r.shape[1], r.shape[2]
-        assert m.shape[:3] == (S, H, W)
-        m = m.contiguous(); r = r.contiguous()
-        torch.cuda.synchronize(self.device)
         n_out, n_all = C.c_int64(0), C.c_int64(0)
-        args = (self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H, radius, k, step)
         cap = (S * H * W) // step + 1      # every emitted point is a scan point: one pass with a worst-case buffer instead of a sizing pass
-        od = torch.empty(cap * 64, dtype=torch.uint8, device=m.device)
+        od = torch.empty(cap * 64, dtype=torch.uint8, device=r.device)
         torch.cuda.synchronize(self.device)
-        check(self.lib.lvi_associate_d(*args, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
+        if isinstance(scans_in_map, CudaScanBatch):
+            assert scans_in_map.shape == (S, H, W)
+            check(self.lib.lvi_associate_batch(self.ctx, smap.vmap, smap.surfels, scans_in_map.h, C.c_void_p(r.data_ptr()), W, H, radius, k, step,
+                                               C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
+        else:
+            m = self.to_device(scans_in_map).contiguous()
+            assert m.shape[:3] == (S, H, W)
+            torch.cuda.synchronize(self.device)
+            check(self.lib.lvi_associate_d(self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H,
+                                           radius, k, step, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
         n = n_out.value
         self.last_n_all = n_all.value
         out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
@@ -219,6 +291,12 @@ class CudaBackend:
 
     def transform(self, scans_xyzi, poses):
         torch = _torch()
+        if isinstance(scans_xyzi, CudaScanBatch):
+            S = scans_xyzi.shape[0]
+            poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(S, 16)
+            h = C.c_void_p()
+            check(self.lib.lvi_scan_batch_transform(self.ctx, scans_xyzi.h, ptr(poses), C.byref(h)))
+            return CudaScanBatch(self, h, *scans_xyzi.shape)
         t = self.to_device(scans_xyzi).contiguous()
         S = t.shape[0]
         pts = int(np.prod(t.shape[1:-1]))
@@ -237,6 +315,23 @@ class CudaBackend:
             tt = r[:, 0, 0, 6:8].contiguous().cpu().numpy().view(np.float64).reshape(S).copy()
         else:
             tt = np.full(S, float(target_time))
+        d = pd.desc()
+        bad = C.c_int32(0)
+        torch.cuda.synchronize(self.device)
+        h = C.c_void_p()
+        check(self.lib.lvi_scan_batch_undistort_d(self.ctx, C.byref(d), C.c_void_p(r.data_ptr()), S, H * W, ptr(tt), int(correct_position),
+                                                  C.byref(h), C.byref(bad)))
+        out = CudaScanBatch(self, h, S, H, W)
+        if bad.value:
+            raise IndexError(f"{bad.value} scan target time(s) outside the trajectory")
+        return out
+
+    def undistort_xyzi(self, pd, scans_raw, target_time, correct_position):
+        """same through the PCL-layout entry point lvi_undistort_d: -> device tensor [S, H, W, 8] float32"""
+        torch = _torch()
+        r = self.to_device(scans_raw, cache=True).contiguous()
+        S, H, W = r.shape[0], r.shape[1], r.shape[2]
+        tt = (r[:, 0, 0, 6:8].contiguous().cpu().numpy().view(np.float64).reshape(S).copy() if target_time is None else np.full(S, float(target_time)))
         out = torch.empty((S, H, W, 8), dtype=torch.float32, device=r.device)
         d = pd.desc()
         bad = C.c_int32(0)

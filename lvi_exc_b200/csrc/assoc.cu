@@ -14,6 +14,8 @@
 // Compiled with -fmad=false (bit-exact index selection).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "map.cuh"
 
 namespace lvi {
@@ -45,30 +47,69 @@ __device__ __forceinline__ int lookup_leaf(const GridParams& g, const int32_t* _
   return -1;
 }
 
+// Per point: voxel index -> leaf -> plane -> strict bbox test + |n.x + d| <= radius.  stride == 16 with a 16-byte aligned base is the
+// library's own packed scan batch: the kernel then moves 16 B in and 4 B out per point.  Every step is a dependent lookup (point ->
+// cell2leaf -> leaf2plane -> plane record), so each thread keeps FOUR points in flight and walks the chain stage by stage; the plane
+// record is one packed 48-byte row (PlaneRec) instead of 128 B spread over three fp64 arrays.  The box test compares floats (both sides
+// are floats widened to double in the reference, L/src/core/surfel_association.cpp:305-331, so the float comparison is the same
+// comparison); the plane distance is evaluated in fp64 in the reference's order (:296-303).
+struct __align__(16) PlaneRec { float mn[3], a; float mx[3], b; float c, d, pad0, pad1; };
+
+__global__ void __launch_bounds__(256) assoc_plane_rec_kernel(const double* __restrict__ p4, const double* __restrict__ bmin, const double* __restrict__ bmax,
+                                                              int n_planes, PlaneRec* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_planes) return;
+  PlaneRec r;
+  for (int k = 0; k < 3; ++k) { r.mn[k] = static_cast<float>(bmin[3 * i + k]); r.mx[k] = static_cast<float>(bmax[3 * i + k]); }   // exact: they ARE floats
+  r.a = static_cast<float>(p4[4 * i]); r.b = static_cast<float>(p4[4 * i + 1]); r.c = static_cast<float>(p4[4 * i + 2]); r.d = static_cast<float>(p4[4 * i + 3]);
+  r.pad0 = r.pad1 = 0.f;
+  rec[i] = r;
+}
+
+constexpr int kHitIlp = 4;
 __global__ void __launch_bounds__(256) assoc_hit_kernel(const char* __restrict__ scan_map, size_t stride, int64_t n, const GridParams* __restrict__ gp,
                                                         const int32_t* __restrict__ cell2leaf, const int32_t* __restrict__ leaf_key, int n_leaves,
-                                                        const int32_t* __restrict__ leaf2plane, const double* __restrict__ p4,
-                                                        const double* __restrict__ bmin, const double* __restrict__ bmax, double radius,
+                                                        const int32_t* __restrict__ leaf2plane, const PlaneRec* __restrict__ planes, double radius,
                                                         int32_t* __restrict__ cand) {
   __shared__ GridParams g;
   if (threadIdx.x == 0) g = *gp;
   __syncthreads();
   const bool vec = (stride % 16 == 0) && ((reinterpret_cast<size_t>(scan_map) & 15) == 0);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float x, y, z;
-    if (vec) { const float4 v = __ldg(reinterpret_cast<const float4*>(scan_map + i * stride)); x = v.x; y = v.y; z = v.z; }
-    else { const float* p = reinterpret_cast<const float*>(scan_map + i * stride); x = p[0]; y = p[1]; z = p[2]; }
-    int res = -1;
-    const int leaf = lookup_leaf(g, cell2leaf, leaf_key, n_leaves, x, y, z);
-    if (leaf >= 0) {
-      const int pl = leaf2plane[leaf];
-      if (pl >= 0) {
-        const double dx = x, dy = y, dz = z;
-        const double* mn = bmin + 3 * pl; const double* mx = bmax + 3 * pl;
-        if (dx > mn[0] && dx < mx[0] && dy > mn[1] && dy < mx[1] && dz > mn[2] && dz < mx[2] && p2plane(dx, dy, dz, p4 + 4 * pl) <= radius) res = pl;
+  const int64_t span = static_cast<int64_t>(blockDim.x) * kHitIlp;
+  for (int64_t c0 = blockIdx.x * span; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * span) {
+    float x[kHitIlp], y[kHitIlp], z[kHitIlp];
+    int leaf[kHitIlp], pl[kHitIlp];
+#pragma unroll
+    for (int u = 0; u < kHitIlp; ++u) {
+      const int64_t i = c0 + threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
+      x[u] = y[u] = z[u] = __int_as_float(0x7fc00000);
+      if (i < n) {
+        if (vec) { const float4 v = __ldcs(reinterpret_cast<const float4*>(scan_map + i * stride)); x[u] = v.x; y[u] = v.y; z[u] = v.z; }   // streamed: L2 stays with the tables
+        else { const float* p = reinterpret_cast<const float*>(scan_map + i * stride); x[u] = p[0]; y[u] = p[1]; z[u] = p[2]; }
       }
     }
-    cand[i] = res;
+#pragma unroll
+    for (int u = 0; u < kHitIlp; ++u) leaf[u] = lookup_leaf(g, cell2leaf, leaf_key, n_leaves, x[u], y[u], z[u]);
+#pragma unroll
+    for (int u = 0; u < kHitIlp; ++u) pl[u] = leaf[u] >= 0 ? __ldg(leaf2plane + leaf[u]) : -1;
+#pragma unroll
+    for (int u = 0; u < kHitIlp; ++u) {
+      const int64_t i = c0 + threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
+      if (i >= n) continue;
+      int res = -1;
+      if (pl[u] >= 0) {
+        const float4* r = reinterpret_cast<const float4*>(planes + pl[u]);
+        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+        if (x[u] > r0.x && x[u] < r1.x && y[u] > r0.y && y[u] < r1.y && z[u] > r0.z && z[u] < r1.z) {
+          double d = static_cast<double>(x[u]) * static_cast<double>(r0.w);   // point2PlaneDistance :296-303, in its order
+          d = d + static_cast<double>(y[u]) * static_cast<double>(r1.w);
+          d = d + static_cast<double>(z[u]) * static_cast<double>(r2.x);
+          d = d + static_cast<double>(r2.y);
+          if ((d > 0 ? d : -d) <= radius) res = pl[u];
+        }
+      }
+      __stcs(cand + i, res);
+    }
   }
 }
 
@@ -90,6 +131,25 @@ __device__ __forceinline__ int sel_hash_slot(int* hkey, int plane) {  // find-or
     if (k == -1) { hkey[sl] = plane; return sl; }
   }
   return -1;  // table full: cannot happen for W <= 4096 with 256 slots unless > 256 distinct planes hit one ring
+}
+
+// concurrent find-or-insert: the leaders of one 32-column step insert their (distinct) planes at the same time
+__device__ __forceinline__ int sel_hash_slot_atomic(int* hkey, int plane) {
+  unsigned h = (static_cast<unsigned>(plane) * 2654435761u) >> 24;
+  for (int probe = 0; probe < kSelHash; ++probe) {
+    const int sl = (h + probe) & (kSelHash - 1);
+    const int k = atomicCAS(hkey + sl, -1, plane);
+    if (k == -1 || k == plane) return sl;
+  }
+  return -1;
+}
+__device__ __forceinline__ int sel_hash_find(const int* hkey, int plane) {
+  unsigned h = (static_cast<unsigned>(plane) * 2654435761u) >> 24;
+  for (int probe = 0; probe < kSelHash; ++probe) {
+    const int sl = (h + probe) & (kSelHash - 1);
+    if (hkey[sl] == plane) return sl;
+  }
+  return 0;   // not reached: every plane of the ring was inserted by pass 1
 }
 
 __global__ void __launch_bounds__(kSelWarps * 32) assoc_select_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw, int n_rings,
@@ -236,6 +296,152 @@ __global__ void __launch_bounds__(256) assoc_emit_kernel(const int32_t* __restri
   }
 }
 
+// ---- per-scan selection: one CTA per scan ---------------------------------------------------------------------------------------
+// assoc_hit_kernel leaves the candidate plane of every point (cand[scan][h][w]).  For scans of up to kScanSelMaxPts points one CTA then
+// does the rest of a scan without another pass over HBM beyond reading those 4 B per point:
+//   B  one warp per ring: pass 1 counts the hits of every plane (match_any + warp hash table), pass 2 walks the ring again with running
+//      counts and marks hits[step*(s+1)-1] in a bitmap laid out in emission order [w][h] (surfel_association.cpp:127-158)
+//   C  ordered compaction of the bitmap -> (position, plane) list of the scan + its length
+// A tiny exclusive scan over the per-scan lengths then gives every selected point its global emission rank, and assoc_emit_list_kernel
+// writes every time_step-th of them as a SurfelPoint (:240-244).  (The first version ranked into a [scan][w][h] int array with strided
+// writes, flagged, scanned and re-read it: 4 passes of 4 B per point, 0.65 ms at C2.)
+constexpr int kScanSelThreads = 512;
+constexpr int kScanSelWarps = kScanSelThreads / 32;
+constexpr int kScanSelMaxPts = 1 << 17;   // bitmap of 16 KB in shared memory
+
+struct FusedSel { int32_t e; int32_t plane; };   // e = w * H + h: position inside the scan in emission order
+
+__global__ void __launch_bounds__(kScanSelThreads) assoc_scan_select_kernel(const int32_t* __restrict__ cand, const lvi_point_xyzit* __restrict__ raw,
+                                                                            int n_scans, int W, int H, int k_per_ring, FusedSel* __restrict__ lists,
+                                                                            int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  __shared__ int s_part[kScanSelWarps + 1];
+  const int HW = H * W;
+  const int n_words = (HW + 31) >> 5;
+  unsigned* bits = reinterpret_cast<unsigned*>(sel_smem);                   // [n_words] emission order
+  int* hkey = reinterpret_cast<int*>(bits + n_words);                       // [warps][kSelHash]
+  int* htot = hkey + kScanSelWarps * kSelHash;
+  int* hrun = htot + kScanSelWarps * kSelHash;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned FULL = 0xffffffffu;
+  for (int scan = blockIdx.x; scan < n_scans; scan += gridDim.x) {
+    __syncthreads();
+    const int64_t base = static_cast<int64_t>(scan) * HW;
+    for (int w = tid; w < n_words; w += kScanSelThreads) bits[w] = 0u;
+    __syncthreads();
+    // ---- B: per-ring selection, one warp per ring
+    int* hk = hkey + warp * kSelHash; int* ht = htot + warp * kSelHash; int* hr = hrun + warp * kSelHash;
+    for (int h = warp; h < H; h += kScanSelWarps) {
+      const int32_t* row = cand + base + static_cast<int64_t>(h) * W;
+      for (int i = lane; i < kSelHash; i += 32) { hk[i] = -1; ht[i] = 0; hr[i] = 0; }
+      __syncwarp();
+      bool full = false;
+      for (int w0 = 0; w0 < W; w0 += 32) {   // pass 1: hits per plane
+        const int w = w0 + lane;
+        const int c = w < W ? __ldg(row + w) : -1;
+        const unsigned hits = __ballot_sync(FULL, c >= 0);
+        if (c >= 0) {
+          const unsigned grp = __match_any_sync(hits, c);
+          if (lane == __ffs(grp) - 1) {   // group leaders hold distinct planes: their table slots are distinct too
+            const int sl = sel_hash_slot_atomic(hk, c);
+            if (sl < 0) full = true; else ht[sl] += __popc(grp);
+          }
+        }
+        __syncwarp();
+      }
+      full = __any_sync(FULL, full);
+      for (int w0 = 0; w0 < W; w0 += 32) {   // pass 2: rank of every hit inside its plane's hit list -> the k picked ones
+        const int w = w0 + lane;
+        const int c = w < W ? __ldg(row + w) : -1;
+        const unsigned hits = __ballot_sync(FULL, c >= 0);
+        if (c >= 0) {
+          int rank, total;
+          if (!full) {
+            const unsigned grp = __match_any_sync(hits, c);
+            const int leader = __ffs(grp) - 1;
+            int basev = 0, tot = 0;
+            if (lane == leader) {
+              const int sl = sel_hash_find(hk, c);
+              basev = hr[sl]; tot = ht[sl];
+              hr[sl] = basev + __popc(grp);
+            }
+            basev = __shfl_sync(grp, basev, leader); total = __shfl_sync(grp, tot, leader);
+            rank = basev + __popc(grp & ((1u << lane) - 1));
+          } else {   // more distinct planes than the table holds: count directly over the ring (rare; no limit in the reference)
+            rank = 0; total = 0;
+            for (int v = 0; v < W; ++v) { const int same = __ldg(row + v) == c; total += same; rank += same & (v < w); }
+          }
+          if (total >= k_per_ring * 2) {
+            int step = total / (k_per_ring + 1);
+            step = step > 1 ? step : 1;
+            const int r1 = rank + 1;
+            if (r1 % step == 0 && r1 / step >= 1 && r1 / step <= k_per_ring) {
+              const double ts = raw[base + static_cast<int64_t>(h) * W + w].timestamp;
+              if (ts != 0.0) { const int e = w * H + h; atomicOr(bits + (e >> 5), 1u << (e & 31)); }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- C: ordered compaction of the emission-order bitmap
+    FusedSel* list = lists + base;
+    int running = 0;
+    for (int w0 = 0; w0 < n_words; w0 += kScanSelThreads) {
+      const int wd = w0 + tid;
+      const unsigned word = wd < n_words ? bits[wd] : 0u;
+      const int cnt = __popc(word);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_part[warp] = inc;
+      __syncthreads();
+      if (tid == 0) { int a = 0; for (int q = 0; q < kScanSelWarps; ++q) { const int t = s_part[q]; s_part[q] = a; a += t; } s_part[kScanSelWarps] = a; }
+      __syncthreads();
+      int o = running + s_part[warp] + inc - cnt;
+      unsigned wbits = word;
+      while (wbits) {
+        const int b = __ffs(wbits) - 1;
+        wbits &= wbits - 1;
+        const int e = 32 * wd + b;
+        const int w = e / H, h = e - w * H;
+        list[o++] = FusedSel{e, __ldg(cand + base + static_cast<int64_t>(h) * W + w)};
+      }
+      running += s_part[kScanSelWarps];
+      __syncthreads();
+    }
+    if (tid == 0) counts[scan] = running;
+  }
+}
+
+__global__ void __launch_bounds__(256) assoc_emit_list_kernel(const FusedSel* __restrict__ lists, const int32_t* __restrict__ counts, const int32_t* __restrict__ bases,
+                                                              int n_scans, int W, int H, int time_step, const char* __restrict__ scan_map, size_t stride,
+                                                              const lvi_point_xyzit* __restrict__ raw, lvi_surfel_point* __restrict__ out, int64_t cap) {
+  const int HW = W * H;
+  for (int scan = blockIdx.x; scan < n_scans; scan += gridDim.x) {
+    const int cnt = counts[scan], b0 = bases[scan];
+    const FusedSel* list = lists + static_cast<int64_t>(scan) * HW;
+    // first j with (b0 + j) % time_step == 0
+    const int j0 = (time_step - b0 % time_step) % time_step;
+    for (int j = j0 + threadIdx.x * time_step; j < cnt; j += blockDim.x * time_step) {   // averageTimeDownSmaple :240-244
+      const int64_t o = (static_cast<int64_t>(b0) + j) / time_step;
+      if (o >= cap) continue;
+      const FusedSel fs = list[j];
+      const int w = fs.e / H, h = fs.e - w * H;
+      const int64_t idx = static_cast<int64_t>(scan) * HW + static_cast<int64_t>(h) * W + w;
+      const lvi_point_xyzit p = raw[idx];
+      const float* q = reinterpret_cast<const float*>(scan_map + idx * stride);
+      lvi_surfel_point sp;
+      sp.timestamp = p.timestamp;
+      sp.point[0] = p.x; sp.point[1] = p.y; sp.point[2] = p.z;
+      sp.point_in_map[0] = q[0]; sp.point_in_map[1] = q[1]; sp.point_in_map[2] = q[2];
+      sp.plane_id = fs.plane;
+      out[o] = sp;
+    }
+  }
+}
+
 // a-3'  associateVisualPointsWithPlanes inner test (L/src/core/surfel_association.cpp:196-210): thread per landmark sweeps the
 // plane list (<= 1e4 landmarks x <= 1e4 planes, all planes L2-resident); the LAST matching plane wins (:206).
 __global__ void __launch_bounds__(128) assoc_landmark_kernel(const double* __restrict__ pts, int64_t n, int n_planes, const double* __restrict__ p4,
@@ -263,11 +469,41 @@ static void associate_device(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_sur
   const int64_t n = static_cast<int64_t>(n_scans) * W * H;
   LVI_REQUIRE(n < 2147483647LL, LVI_ERR_INVALID, "lvi_associate: batch too large (split the scans)");
   cudaStream_t st = ctx->stream;
-  DBuf<int32_t> cand(n), sel(n), flag(n), rank(n);
   if (s->n_planes == 0) { if (n_out) *n_out = 0; if (n_all) *n_all = 0; return; }
-  LVI_LAUNCH(ctx, assoc_hit_kernel, grid_for(n, 256, ctx->sm_count, 8), 256, 0, static_cast<const char*>(map_d), stride, n, m->grid_d.p,
-             m->cell2leaf.n ? m->cell2leaf.p : nullptr, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p, s->p4.p, s->bmin.p, s->bmax.p,
-             radius, cand.p);
+  DBuf<int32_t> cand(n);
+  DBuf<PlaneRec> prec(static_cast<size_t>(s->n_planes));
+  LVI_LAUNCH(ctx, assoc_plane_rec_kernel, static_cast<int>((s->n_planes + 255) / 256), 256, 0, s->p4.p, s->bmin.p, s->bmax.p, static_cast<int>(s->n_planes), prec.p);
+  LVI_LAUNCH(ctx, assoc_hit_kernel, grid_for(n, 256 * kHitIlp, ctx->sm_count, 8), 256, 0, static_cast<const char*>(map_d), stride, n, m->grid_d.p,
+             m->cell2leaf.n ? m->cell2leaf.p : nullptr, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p, prec.p, radius, cand.p);
+  if (static_cast<int64_t>(W) * H <= kScanSelMaxPts && !std::getenv("LVI_ASSOC_UNFUSED")) {   // selection + emission order of a scan inside one CTA
+    const int HW = W * H;
+    const size_t smem = static_cast<size_t>((HW + 31) / 32) * 4 + static_cast<size_t>(kScanSelWarps) * kSelHash * 12;
+    if (smem > ctx->ks.assoc_attr) {
+      LVI_CUDA(cudaFuncSetAttribute(assoc_scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      ctx->ks.assoc_attr = smem;
+    }
+    DBuf<FusedSel> lists(static_cast<size_t>(n));
+    DBuf<int32_t> counts(n_scans), bases(n_scans);
+    LVI_LAUNCH(ctx, assoc_scan_select_kernel, std::min(n_scans, ctx->sm_count * 4), kScanSelThreads, smem, cand.p, raw_d, n_scans, W, H, k, lists.p, counts.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, bases.p, n_scans, st);
+    DBuf<char> tmp(tb + 16);
+    LVI_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, bases.p, n_scans, st));
+    ctx->launches += 1;
+    // the emission needs no host decision: it runs before the host learns the total
+    if (out_d && cap > 0)
+      LVI_LAUNCH(ctx, assoc_emit_list_kernel, std::min(n_scans, ctx->sm_count * 8), 256, 0, lists.p, counts.p, bases.p, n_scans, W, H, time_step,
+                 static_cast<const char*>(map_d), stride, raw_d, out_d, cap);
+    int last_base = 0, last_count = 0;
+    LVI_CUDA(cudaMemcpyAsync(&last_base, bases.p + n_scans - 1, 4, cudaMemcpyDeviceToHost, st));
+    LVI_CUDA(cudaMemcpyAsync(&last_count, counts.p + n_scans - 1, 4, cudaMemcpyDeviceToHost, st));
+    LVI_CUDA(cudaStreamSynchronize(st));
+    const int64_t total = static_cast<int64_t>(last_base) + last_count;
+    if (n_all) *n_all = total;
+    if (n_out) *n_out = (total + time_step - 1) / time_step;
+    return;
+  }
+  DBuf<int32_t> sel(n), flag(n), rank(n);
   const int n_rings = n_scans * H;
   DBuf<int> overflow(1);
   DBuf<int32_t> ring_overflow(n_rings);
@@ -309,6 +545,18 @@ int lvi_associate_d(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* 
     LVI_REQUIRE(ctx && m && s && scans_in_map_d && scans_raw_d, LVI_ERR_INVALID, "lvi_associate_d: null argument");
     activate(ctx);
     associate_device(ctx, m, s, scans_in_map_d, map_stride_bytes, scans_raw_d, n_scans, W, H, radius, k_per_ring, time_step, out_d, cap, n_out, n_all);
+  });
+}
+
+int lvi_associate_batch(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s, const lvi_scan_batch* batch, const lvi_point_xyzit* scans_raw_d,
+                        int32_t W, int32_t H, double radius, int32_t k_per_ring, int32_t time_step, lvi_surfel_point* out_d, int64_t cap, int64_t* n_out,
+                        int64_t* n_all) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && m && s && batch && scans_raw_d, LVI_ERR_INVALID, "lvi_associate_batch: null argument");
+    LVI_REQUIRE(static_cast<int64_t>(W) * H == batch->pts_per_scan && batch->n == static_cast<int64_t>(batch->n_scans) * batch->pts_per_scan, LVI_ERR_INVALID,
+                "lvi_associate_batch: W x H does not match the batch");
+    activate(ctx);
+    associate_device(ctx, m, s, batch->pts.p, sizeof(float4), scans_raw_d, batch->n_scans, W, H, radius, k_per_ring, time_step, out_d, cap, n_out, n_all);
   });
 }
 

@@ -1,6 +1,8 @@
 // capi.cu — context management and misc entry points of the C-ABI (include/lvi_exc_b200.h).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "common.cuh"
 #include "nccl_dyn.hpp"
@@ -56,9 +58,9 @@ static void ctx_init(lvi_ctx* c, int device) {
   tl_stream = c->stream;
   // Grow the pool ONCE, here, instead of inside the first solve: a C2 problem takes ~1.1 GB of solver buffers (tile stores + flagged
   // copies) and the first cudaMallocAsync of that size is a synchronous driver allocation of tens of milliseconds.  LVI_POOL_RESERVE_MB
-  // overrides the default (2 GB of the 180 GB); 0 disables it.
+  // overrides the default (4 GB of the 180 GB: two C2 problems side by side); 0 disables it.
   {
-    size_t mb = 2048;
+    size_t mb = 4096;
     if (const char* e = std::getenv("LVI_POOL_RESERVE_MB")) mb = static_cast<size_t>(std::strtoull(e, nullptr, 10));
     if (mb > 0) {
       void* p = nullptr;
@@ -122,6 +124,8 @@ int lvi_ctx_destroy(lvi_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    for (auto& sp : ctx->kt_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : ctx->kt_free) cudaEventDestroy(e);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     cudaStreamDestroy(ctx->stream);
     if (tl_stream == ctx->stream) tl_stream = nullptr;
@@ -138,6 +142,40 @@ int lvi_ctx_synchronize(lvi_ctx* ctx) {
     LVI_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
+// per-kernel timing: enable (1) / disable (0); lvi_ctx_kernel_times drains the spans recorded so far as text lines "name count total_ms"
+int lvi_ctx_kernel_timing(lvi_ctx* ctx, int enable) {
+  if (!ctx) return LVI_ERR_INVALID;
+  ctx->kt_enabled = enable != 0;
+  return LVI_OK;
+}
+int64_t lvi_ctx_kernel_times(lvi_ctx* ctx, char* out, int64_t cap) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 2; ++i) cudaStreamSynchronize(ctx->aux[i]);
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (auto& sp : ctx->kt_spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    std::string name = sp.name;
+    const size_t lt = name.find('<');   // template arguments stay: linearize_kernel<RT_CAM> etc.
+    (void)lt;
+    bool found = false;
+    for (auto& a : agg) if (a.first == name) { a.second.first += 1; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({name, {1, ms}});
+    ctx->kt_free.push_back(sp.a); ctx->kt_free.push_back(sp.b);
+  }
+  ctx->kt_spans.clear();
+  std::string txt;
+  for (auto& a : agg) {
+    std::string nm = a.first;
+    for (char& c : nm) if (c == ' ') c = '_';
+    txt += nm + " " + std::to_string(a.second.first) + " " + std::to_string(a.second.second) + "\n";
+  }
+  if (out && cap > 0) { const size_t n = std::min<size_t>(txt.size(), static_cast<size_t>(cap - 1)); std::memcpy(out, txt.data(), n); out[n] = 0; }
+  return static_cast<int64_t>(txt.size());
+}
+
 void* lvi_ctx_stream(lvi_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 int64_t lvi_ctx_launch_count(lvi_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

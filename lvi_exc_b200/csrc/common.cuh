@@ -70,12 +70,24 @@ struct lvi_ctx {
     int bs_resident = 0;              //            ... of band_backsolve_ll_kernel
     size_t corner_attr = 48 * 1024;   //            dynamic shared memory granted to corner_solve_kernel so far
     size_t schur_attr = 48 * 1024;    //            ... to schur_eliminate_kernel
+    size_t assoc_attr = 48 * 1024;    // assoc.cu: ... to assoc_scan_fused_kernel
     bool selftest_done = false;
   } ks;
   // host-side resources every solve needs, made once per context (cudaMallocHost / cudaEventCreate cost 0.1 - 1 ms each on a cold driver)
   double* h_scal = nullptr;           // pinned mirror of a problem's scalar block (64 doubles)
   std::vector<cudaEvent_t> timing_events;   // reused by the LM loop's phase timers
   size_t timing_used = 0;
+  // optional per-kernel timing (lvi_ctx_kernel_timing): every LVI_LAUNCH is bracketed by CUDA events on the stream it goes to
+  bool kt_enabled = false;
+  struct KtSpan { const char* name; cudaEvent_t a, b; };
+  std::vector<KtSpan> kt_spans;
+  std::vector<cudaEvent_t> kt_free;
+  cudaEvent_t kt_event() {
+    if (!kt_free.empty()) { cudaEvent_t e = kt_free.back(); kt_free.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
   cudaEvent_t timing_event() {
     if (timing_used == timing_events.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; timing_events.push_back(e); }
     return timing_events[timing_used++];
@@ -136,11 +148,24 @@ inline int grid_for(int64_t work_items, int block, int sm_count, int blocks_per_
   return static_cast<int>(g);
 }
 
-#define LVI_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+#define LVI_LAUNCH_AS(ctx, label, kernel, grid, block, smem, ...)            \
   do {                                                                       \
+    cudaEvent_t kt_a__ = nullptr, kt_b__ = nullptr;                          \
+    if ((ctx)->kt_enabled) { kt_a__ = (ctx)->kt_event(); kt_b__ = (ctx)->kt_event(); cudaEventRecord(kt_a__, (ctx)->stream); } \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+    if (kt_a__) { cudaEventRecord(kt_b__, (ctx)->stream); (ctx)->kt_spans.push_back({label, kt_a__, kt_b__}); } \
     ++(ctx)->launches;                                                       \
     LVI_CUDA(cudaGetLastError());                                            \
+  } while (0)
+#define LVI_LAUNCH(ctx, kernel, grid, block, smem, ...) LVI_LAUNCH_AS(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+
+// the same bracket around a library call that launches kernels itself (CUB sort / scan)
+#define LVI_TIMED(ctx, label, call)                                          \
+  do {                                                                       \
+    cudaEvent_t kt_a__ = nullptr, kt_b__ = nullptr;                          \
+    if ((ctx)->kt_enabled) { kt_a__ = (ctx)->kt_event(); kt_b__ = (ctx)->kt_event(); cudaEventRecord(kt_a__, (ctx)->stream); } \
+    LVI_CUDA(call);                                                          \
+    if (kt_a__) { cudaEventRecord(kt_b__, (ctx)->stream); (ctx)->kt_spans.push_back({label, kt_a__, kt_b__}); } \
   } while (0)
 
 }  // namespace lvi

@@ -215,7 +215,9 @@ static void launch_linearize(lvi_problem* p) {
   int grid = std::max(1, (T.hi - T.lo + per_cta - 1) / per_cta);
   const int cap = p->ctx->sm_count * 8;
   if (grid > cap) grid = cap;
-  LVI_LAUNCH(p->ctx, linearize_kernel<TYPE>, grid, per_cta, smem, p->view, p->H, p->schur, p->g.p, p->scal.p);
+  static const char* const names[RT_COUNT] = {"linearize_kernel<RT_GYRO>", "linearize_kernel<RT_ACCEL>", "linearize_kernel<RT_SURFEL>", "linearize_kernel<RT_CAM>",
+                                              "linearize_kernel<RT_CAMSURF>", "linearize_kernel<RT_ORIENT>"};
+  LVI_LAUNCH_AS(p->ctx, names[TYPE], linearize_kernel<TYPE>, grid, per_cta, smem, p->view, p->H, p->schur, p->g.p, p->scal.p);
 }
 
 template <int TYPE>

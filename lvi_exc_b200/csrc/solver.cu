@@ -1352,7 +1352,16 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   std::memset(&S, 0, sizeof(S));
   lvi_ctx* ctx = p->ctx;
   cudaStream_t st = ctx->stream;
+  const bool timing = std::getenv("LVI_TIME_SOLVE") != nullptr;   // diagnostics: host wall time between the loop's wait points, on stderr
+  auto Tl = T0;
+  auto lap = [&](const char* what, int it_no = -1) {
+    if (!timing) return;
+    const auto T1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lvi] solve: %-24s %3d %9.3f ms\n", what, it_no, std::chrono::duration<double, std::milli>(T1 - Tl).count());
+    Tl = T1;
+  };
   problem_ensure_solver_buffers(p);
+  lap("solver buffers");
   const int nt = p->nt;
   DBuf<double> dH(std::max(nt, 1));
   Scalars sc{};
@@ -1373,8 +1382,10 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   trial_cost(p, p->X.p, p->scal.p + 1, false, true);
   read_scalars(p, sc);
   const double fixed_cost = sc.cand_cost;
+  lap("fixed cost");
   tic(tj); linearize(p); toc();
   read_scalars(p, sc);
+  lap("first linearize");
   double x_cost = sc.cost;
   S.initial_cost = x_cost + fixed_cost; S.fixed_cost = fixed_cost;
   S.num_residual_blocks = p->L.n_res_blocks; S.num_residuals = p->L.n_res; S.num_effective_parameters = nt;
@@ -1422,6 +1433,7 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
     }
     diff_norms(p);
     read_scalars(p, sc);
+    lap("step + trial cost", it);
     reuse_diagonal = true;
     bool step_valid = !sc.failed && sc.nonfinite == 0.0;
     // model_cost_change = -(J y).(r + J y / 2) = -y.g_s - y^T H_s y / 2, with H_s y = -g_s - D^2 y
@@ -1470,6 +1482,7 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
       decrease_factor = 2.0; reuse_diagonal = false;
       ++S.num_successful_steps;
       gmax = grad_max_norm();
+      lap("accept: linearize", it);
       x_norm = std::sqrt(sc.xnorm_ss);
       log_iter(x_cost + fixed_cost, cost_change, gmax, step_norm, true);
       if (o.verbose) std::printf("[lvi] iter %3d cost %.9e change %.3e |g| %.3e |step| %.3e radius %.3e\n", it, x_cost, cost_change, gmax, step_norm, radius);
@@ -1484,6 +1497,7 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   }
   problem_download_params(p);
   LVI_CUDA(cudaStreamSynchronize(st));
+  lap("download");
   for (Span& sp : spans) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.accu += ms;

@@ -9,7 +9,9 @@
 //                             32 B coalesced store (PointXYZI).  HBM-bound: 64 B/point + cache-resident knots.
 //   transform_kernel        : float 4x4 per scan, evaluated left to right without FMA (bit-exact with Eigen's float path).
 // Compiled with -fmad=false.
-#include "common.cuh"
+#include <memory>
+
+#include "map.cuh"
 #include "spline_math.cuh"
 
 namespace lvi {
@@ -62,13 +64,23 @@ __global__ void undistort_target_kernel(TrajView T, const double* __restrict__ t
   out[s] = tp;
 }
 
+// PACKED = false: out is pcl::PointXYZI-shaped (2 x float4 per point, the ABI layout).  PACKED = true: out is the library's own scan batch
+// (one float4 per point: x y z intensity) and the finite points are folded into their scan's min/max slots on the way out.
+template <bool PACKED>
 __global__ void __launch_bounds__(256) undistort_kernel(TrajView T, const lvi_point_xyzit* __restrict__ raw, int64_t n, int64_t pts_per_scan,
-                                                        const TargetPose* __restrict__ target, int correct_position, float4* __restrict__ out) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+                                                        const TargetPose* __restrict__ target, int correct_position, float4* __restrict__ out,
+                                                        int* __restrict__ mm) {
+  ScanMinMax acc;
+  acc.reset(-1);
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kProducerChunk; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * kProducerChunk)
+  for (int j = 0; j < kProducerChunk / 256; ++j) {
+    const int64_t i = c0 + threadIdx.x + 256 * j;
+    if (i >= n) break;
     const float4 a = __ldg(reinterpret_cast<const float4*>(raw + i));       // x y z pad
     const float4 b = __ldg(reinterpret_cast<const float4*>(raw + i) + 1);   // intensity pad2 timestamp(lo,hi)
     const double ts = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));
-    const TargetPose tp = target[i / pts_per_scan];
+    const int64_t scan = i / pts_per_scan;
+    const TargetPose tp = target[scan];
     float4 o0 = make_float4(0.f, 0.f, 0.f, 1.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!tp.ok || isnan(a.x)) {
       const float nanv = __int_as_float(0x7fc00000);
@@ -84,9 +96,20 @@ __global__ void __launch_bounds__(256) undistort_kernel(TrajView T, const lvi_po
         o1.x = b.x;
       }  // else: the reference leaves the default-constructed point (zeros)
     }
-    out[2 * i] = o0;
-    out[2 * i + 1] = o1;
+    if (PACKED) {
+      out[i] = make_float4(o0.x, o0.y, o0.z, o1.x);
+      acc.add(mm, scan, o0.x, o0.y, o0.z);
+    } else {
+      out[2 * i] = o0;
+      out[2 * i + 1] = o1;
+    }
   }
+  if (PACKED) acc.flush(mm);
+}
+
+__global__ void scan_minmax_init_kernel(int* mm, int n_slots) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slots * 6) mm[i] = (i % 6) < 3 ? f2ord(3.402823466e38f) : f2ord(-3.402823466e38f);
 }
 
 // IMU pose of the trajectory at arbitrary times (SplitTrajectory::Evaluate, K/trajectories/split_trajectory.h:41-58), used by
@@ -106,24 +129,86 @@ __global__ void traj_eval_kernel(TrajView T, const double* __restrict__ t, int64
 
 struct Mat34f { float m[12]; };
 
+// pcl::transformPointCloud with a float 4x4 per scan.  The input is a PCL cloud (2 x float4 per point) or a packed batch; so is the output.
+template <bool IN_PACKED, bool OUT_PACKED>
 __global__ void __launch_bounds__(256) transform_kernel(const float4* __restrict__ in, int64_t n, int64_t pts_per_scan, const Mat34f* __restrict__ poses,
-                                                        float4* __restrict__ out) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float4 a = __ldg(in + 2 * i);
-    const float4 b = __ldg(in + 2 * i + 1);
-    const Mat34f& M = poses[i / pts_per_scan];
+                                                        float4* __restrict__ out, int* __restrict__ mm) {
+  ScanMinMax acc;
+  acc.reset(-1);
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kProducerChunk; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * kProducerChunk)
+  for (int j = 0; j < kProducerChunk / 256; ++j) {
+    const int64_t i = c0 + threadIdx.x + 256 * j;
+    if (i >= n) break;
+    float4 a; float inten;
+    if (IN_PACKED) { a = __ldg(in + i); inten = a.w; }
+    else { a = __ldg(in + 2 * i); inten = __ldg(in + 2 * i + 1).x; }
+    const int64_t scan = i / pts_per_scan;
+    const Mat34f& M = poses[scan];
     float4 o;
     o.x = M.m[0] * a.x + M.m[1] * a.y + M.m[2] * a.z + M.m[3];
     o.y = M.m[4] * a.x + M.m[5] * a.y + M.m[6] * a.z + M.m[7];
     o.z = M.m[8] * a.x + M.m[9] * a.y + M.m[10] * a.z + M.m[11];
     o.w = 1.f;
-    out[2 * i] = o;
-    out[2 * i + 1] = make_float4(b.x, 0.f, 0.f, 0.f);
+    if (OUT_PACKED) {
+      out[i] = make_float4(o.x, o.y, o.z, inten);
+      acc.add(mm, scan, o.x, o.y, o.z);
+    } else {
+      out[2 * i] = o;
+      out[2 * i + 1] = make_float4(inten, 0.f, 0.f, 0.f);
+    }
+  }
+  if (OUT_PACKED) acc.flush(mm);
+}
+
+// ABI cloud (x,y,z float at `stride` spacing, intensity at offset 16 when the record is the 32 B PCL one) -> packed batch + min/max slots
+__global__ void __launch_bounds__(256) batch_import_kernel(const char* __restrict__ in, size_t stride, int64_t n, int64_t pts_per_scan,
+                                                           float4* __restrict__ out, int* __restrict__ mm) {
+  const bool vec = (stride % 16 == 0) && ((reinterpret_cast<size_t>(in) & 15) == 0);
+  ScanMinMax acc;
+  acc.reset(-1);
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kProducerChunk; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * kProducerChunk)
+  for (int j = 0; j < kProducerChunk / 256; ++j) {
+    const int64_t i = c0 + threadIdx.x + 256 * j;
+    if (i >= n) break;
+    float x, y, z, w = 0.f;
+    if (vec) { const float4 v = __ldg(reinterpret_cast<const float4*>(in + i * stride)); x = v.x; y = v.y; z = v.z; }
+    else { const float* p = reinterpret_cast<const float*>(in + i * stride); x = p[0]; y = p[1]; z = p[2]; }
+    if (stride >= 20) w = *reinterpret_cast<const float*>(in + i * stride + 16);
+    out[i] = make_float4(x, y, z, w);
+    acc.add(mm, i / pts_per_scan, x, y, z);
+  }
+  acc.flush(mm);
+}
+// packed batch -> pcl::PointXYZI records (x, y, z, 1, intensity, 0, 0, 0)
+__global__ void __launch_bounds__(256) batch_export_kernel(const float4* __restrict__ in, int64_t n, float4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    out[2 * i] = make_float4(v.x, v.y, v.z, 1.f);
+    out[2 * i + 1] = make_float4(v.w, 0.f, 0.f, 0.f);
   }
 }
 
+lvi_scan_batch* batch_alloc(lvi_ctx* ctx, int32_t n_scans, int64_t pts_per_scan, int64_t n) {
+  auto b = std::unique_ptr<lvi_scan_batch>(new lvi_scan_batch());
+  b->ctx = ctx; b->n_scans = n_scans; b->pts_per_scan = pts_per_scan; b->n = n;
+  b->pts.alloc(static_cast<size_t>(n));
+  b->mm.alloc(static_cast<size_t>(n_scans) * 6);
+  LVI_LAUNCH(ctx, scan_minmax_init_kernel, (n_scans * 6 + 255) / 256, 256, 0, b->mm.p, n_scans);
+  return b.release();
+}
+lvi_scan_batch* batch_import_xyzi(lvi_ctx* ctx, const void* xyz_d, size_t stride, int64_t n, int64_t pts_per_scan) {
+  LVI_REQUIRE(n > 0 && n < 2147483647LL, LVI_ERR_INVALID, "point count must be in (0, 2^31)");
+  LVI_REQUIRE(stride >= 12 && stride % 4 == 0, LVI_ERR_INVALID, "stride must be a multiple of 4, >= 12");
+  LVI_REQUIRE(pts_per_scan > 0, LVI_ERR_INVALID, "pts_per_scan must be positive");
+  const int64_t slots = (n + pts_per_scan - 1) / pts_per_scan;
+  LVI_REQUIRE(slots < (1 << 24), LVI_ERR_INVALID, "too many scans in one batch");
+  auto b = std::unique_ptr<lvi_scan_batch>(batch_alloc(ctx, static_cast<int32_t>(slots), pts_per_scan, n));
+  LVI_LAUNCH(ctx, batch_import_kernel, grid_for(n, kProducerChunk, ctx->sm_count, 8), 256, 0, static_cast<const char*>(xyz_d), stride, n, pts_per_scan, b->pts.p, b->mm.p);
+  return b.release();
+}
+
 static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_point_xyzit* raw_d, int n_scans, int64_t pts_per_scan,
-                             const double* target_time_h, int correct_position, void* out_d, int* n_bad_targets) {
+                             const double* target_time_h, int correct_position, void* out_d, int* n_bad_targets, int* mm_packed = nullptr) {
   LVI_REQUIRE(d->r3_knots && d->so3_knots && d->n_knots >= 4, LVI_ERR_INVALID, "lvi_undistort: trajectory needs both splines and >= 4 knots");
   LVI_REQUIRE(n_scans > 0 && pts_per_scan > 0, LVI_ERR_INVALID, "lvi_undistort: empty batch");
   cudaStream_t st = ctx->stream;
@@ -141,8 +226,12 @@ static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_
   DBuf<TargetPose> tp(n_scans);
   LVI_LAUNCH(ctx, undistort_target_kernel, (n_scans + 127) / 128, 128, 0, T, tt.p, n_scans, tp.p);
   const int64_t np = static_cast<int64_t>(n_scans) * pts_per_scan;
-  LVI_LAUNCH(ctx, undistort_kernel, grid_for(np, 256, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
-             static_cast<float4*>(out_d));
+  if (mm_packed)
+    LVI_LAUNCH(ctx, undistort_kernel<true>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
+               static_cast<float4*>(out_d), mm_packed);
+  else
+    LVI_LAUNCH(ctx, undistort_kernel<false>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
+               static_cast<float4*>(out_d), static_cast<int*>(nullptr));
   std::vector<TargetPose> h(n_scans);
   tp.download(h.data(), n_scans, st);
   LVI_CUDA(cudaStreamSynchronize(st));
@@ -151,7 +240,8 @@ static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_
   if (n_bad_targets) *n_bad_targets = bad;
 }
 
-static void transform_device(lvi_ctx* ctx, const void* in_d, int n_scans, int64_t pts_per_scan, const double* poses_h, void* out_d) {
+static void transform_device(lvi_ctx* ctx, const void* in_d, int n_scans, int64_t pts_per_scan, const double* poses_h, void* out_d,
+                             bool packed = false, int* mm_packed = nullptr) {
   LVI_REQUIRE(n_scans > 0 && pts_per_scan > 0, LVI_ERR_INVALID, "lvi_transform_scans: empty batch");
   std::vector<Mat34f> hm(n_scans);
   for (int s = 0; s < n_scans; ++s)
@@ -159,8 +249,12 @@ static void transform_device(lvi_ctx* ctx, const void* in_d, int n_scans, int64_
   DBuf<Mat34f> pm(n_scans);
   pm.upload(hm.data(), n_scans, ctx->stream);
   const int64_t np = static_cast<int64_t>(n_scans) * pts_per_scan;
-  LVI_LAUNCH(ctx, transform_kernel, grid_for(np, 256, ctx->sm_count, 8), 256, 0, static_cast<const float4*>(in_d), np, pts_per_scan, pm.p,
-             static_cast<float4*>(out_d));
+  if (packed)
+    LVI_LAUNCH(ctx, (transform_kernel<true, true>), grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, static_cast<const float4*>(in_d), np, pts_per_scan, pm.p,
+               static_cast<float4*>(out_d), mm_packed);
+  else
+    LVI_LAUNCH(ctx, (transform_kernel<false, false>), grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, static_cast<const float4*>(in_d), np, pts_per_scan, pm.p,
+               static_cast<float4*>(out_d), static_cast<int*>(nullptr));
   LVI_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -193,6 +287,61 @@ int lvi_undistort(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xy
     LVI_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
+
+// ---- scan batches (packed, HBM-resident) --------------------------------------------------------------------------------------
+int lvi_scan_batch_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_xyzit* scans_raw_d, int32_t n_scans, int64_t pts_per_scan,
+                               const double* target_time, int correct_position, lvi_scan_batch** out, int32_t* n_bad_targets) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && traj && scans_raw_d && target_time && out, LVI_ERR_INVALID, "lvi_scan_batch_undistort_d: null argument");
+    activate(ctx);
+    LVI_REQUIRE(n_scans > 0 && pts_per_scan > 0, LVI_ERR_INVALID, "lvi_scan_batch_undistort_d: empty batch");
+    auto b = std::unique_ptr<lvi_scan_batch>(batch_alloc(ctx, n_scans, pts_per_scan, static_cast<int64_t>(n_scans) * pts_per_scan));
+    undistort_device(ctx, traj, scans_raw_d, n_scans, pts_per_scan, target_time, correct_position, b->pts.p, n_bad_targets, b->mm.p);
+    *out = b.release();
+  });
+}
+
+int lvi_scan_batch_transform(lvi_ctx* ctx, const lvi_scan_batch* in, const double* poses, lvi_scan_batch** out) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && in && poses && out, LVI_ERR_INVALID, "lvi_scan_batch_transform: null argument");
+    activate(ctx);
+    auto b = std::unique_ptr<lvi_scan_batch>(batch_alloc(ctx, in->n_scans, in->pts_per_scan, in->n));
+    transform_device(ctx, in->pts.p, in->n_scans, in->pts_per_scan, poses, b->pts.p, true, b->mm.p);
+    *out = b.release();
+  });
+}
+
+int lvi_scan_batch_from_xyzi_d(lvi_ctx* ctx, const void* xyzi_d, size_t stride_bytes, int32_t n_scans, int64_t pts_per_scan, lvi_scan_batch** out) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && xyzi_d && out && n_scans > 0, LVI_ERR_INVALID, "lvi_scan_batch_from_xyzi_d: bad argument");
+    activate(ctx);
+    *out = batch_import_xyzi(ctx, xyzi_d, stride_bytes, static_cast<int64_t>(n_scans) * pts_per_scan, pts_per_scan);
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int lvi_scan_batch_export_xyzi(lvi_ctx* ctx, const lvi_scan_batch* b, void* out_xyzi, int out_is_device) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && b && out_xyzi, LVI_ERR_INVALID, "lvi_scan_batch_export_xyzi: null argument");
+    activate(ctx);
+    const size_t bytes = static_cast<size_t>(b->n) * 32;
+    DBuf<char> tmp;
+    float4* dst = static_cast<float4*>(out_xyzi);
+    if (!out_is_device) { tmp.alloc(bytes); dst = reinterpret_cast<float4*>(tmp.p); }
+    LVI_LAUNCH(ctx, batch_export_kernel, grid_for(b->n, 256, ctx->sm_count, 8), 256, 0, b->pts.p, b->n, dst);
+    if (!out_is_device) LVI_CUDA(cudaMemcpyAsync(out_xyzi, tmp.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LVI_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int lvi_scan_batch_destroy(lvi_scan_batch* b) {
+  if (b) { cudaSetDevice(b->ctx->device); tl_stream = b->ctx->stream; delete b; }
+  return LVI_OK;
+}
+int64_t lvi_scan_batch_num_points(const lvi_scan_batch* b) { return b ? b->n : 0; }
+int32_t lvi_scan_batch_num_scans(const lvi_scan_batch* b) { return b ? b->n_scans : 0; }
+/* the packed device buffer (float4 x,y,z,intensity per point) for callers that keep working on the device */
+const void* lvi_scan_batch_points_d(const lvi_scan_batch* b) { return b ? b->pts.p : nullptr; }
 
 int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const double* t, int64_t n, double* pos, double* quat, uint8_t* valid) {
   return guarded([&] {

@@ -176,15 +176,6 @@ def extrinsic_errors(calib: CalibParams, gt: dict) -> dict:
                 rot_C=quat_angle(calib.q_CtoI, gt["q_CtoI"]), pos_C=float(np.linalg.norm(calib.p_CinI - gt["p_CinI"])))
 
 
-def _take_scans(scans, keys: np.ndarray):
-    """rows of a [S, ...] scan batch (numpy array or device tensor) selected by a boolean key-scan mask"""
-    idx = np.nonzero(keys)[0]
-    if isinstance(scans, np.ndarray):
-        return scans[idx]
-    import torch  # device tensors are only held, never computed on, by the product path
-    return scans[torch.as_tensor(idx, device=scans.device)]
-
-
 def check_key_scan(poses: np.ndarray) -> np.ndarray:
     """LiDAROdometry::checkKeyScan (L/src/core/lidar_odometry.cpp:107-128): first scan, or moved > 0.2 m, or any of
     yaw/pitch/roll changed by more than 5 (degrees; mathutils::R2ypr returns degrees)."""
@@ -209,7 +200,8 @@ def check_key_scan(poses: np.ndarray) -> np.ndarray:
 def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bool = False) -> dict:
     """LCIoptimize replay.  `backend` provides:
          solve(ProblemData, max_iterations) -> SolveSummary
-         build_surfel_map(cloud_xyzi[N,8] float32, leaf, lambda) -> surfel-map handle with .planes_Pi [P,3]
+         map_cloud(scans_in_map, key-scan mask or None) -> the cloud the map is built from (key scans concatenated)
+         build_surfel_map(cloud, leaf, lambda) -> surfel-map handle with .planes_Pi [P,3]
          associate(map, scans_in_map [S,H,W,8] f32, scans_raw, radius, k, step) -> SurfelPoint array
          undistort(ProblemData-like trajectory, scans_raw, target_time, correct_position) -> [S,H,W,8] f32
          transform(scans_xyzi, poses) -> [S,H,W,8] f32        (pcl::transformPointCloud, float 4x4)
@@ -244,7 +236,7 @@ def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bo
     scans_rot = backend.undistort(traj_pd(), seq.scans_raw, None, False)
     scans_in_map = backend.transform(scans_rot, seq.loam_poses)
     keys = check_key_scan(seq.loam_poses)
-    smap = backend.build_surfel_map(_take_scans(scans_in_map, keys).reshape(-1, 8), cfg.ndt_resolution, cfg.plane_lambda_first)
+    smap = backend.build_surfel_map(backend.map_cloud(scans_in_map, keys), cfg.ndt_resolution, cfg.plane_lambda_first)
     spoints = backend.associate(smap, scans_in_map, seq.scans_raw, cfg.associated_radius, cfg.k_per_ring, cfg.time_downsample)
     out["assoc_counts"] = [len(spoints)]
     # S1
@@ -255,7 +247,7 @@ def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bo
     # Refinement x n
     for r in range(cfg.n_refine):
         scans_in_map = backend.undistort(traj_pd(), seq.scans_raw, map_time, True)
-        smap = backend.build_surfel_map(scans_in_map.reshape(-1, 8), cfg.ndt_resolution, cfg.plane_lambda_refine)
+        smap = backend.build_surfel_map(backend.map_cloud(scans_in_map), cfg.ndt_resolution, cfg.plane_lambda_refine)
         spoints = backend.associate(smap, scans_in_map, seq.scans_raw, cfg.associated_radius, cfg.k_per_ring, cfg.time_downsample)
         out["assoc_counts"].append(len(spoints))
         pd = mgr.problem_surfel(smap.planes_Pi, spoints, map_time)

@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         L.synth_camera.restype = C.c_int64
         L.synth_gt_state.argtypes = [C.POINTER(SynthConfig), C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.synth_gt_extrinsics.argtypes = [C.c_void_p] * 6
+        L.synth_lattice_scans.argtypes = [C.POINTER(SynthConfig), C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -104,11 +105,32 @@ def make_scans(cfg: SynthConfig, first: int, n: int) -> np.ndarray:
     return out
 
 
-def make_sequence(cfg: SynthConfig, with_camera: bool = True) -> Sequence:
+def make_lattice_scans(cfg: SynthConfig, n_leaves: int, first: int, n: int, with_map: bool = False):
+    """C3: scans over a map synthesised in voxel space (`n_leaves` planar leaves on a sparse lattice) -> raw scans
+    [n, H, W] (and, optionally, the same points in the map frame [n, H, W, 8] float32)"""
+    raw = np.zeros((n, cfg.rings, cfg.az_steps), dtype=RAW_POINT_DTYPE)
+    m = np.zeros((n, cfg.rings, cfg.az_steps, 8), dtype=np.float32) if with_map else None
+    lib().synth_lattice_scans(C.byref(cfg), n_leaves, SEED_LATTICE, first, n, raw.ctypes.data, m.ctypes.data if with_map else None)
+    return raw, m
+
+
+def make_imu(cfg: SynthConfig):
+    n_imu = lib().synth_num_imu(C.byref(cfg))
+    imu_t, gyro, accel = np.zeros(n_imu), np.zeros((n_imu, 3)), np.zeros((n_imu, 3))
+    lib().synth_imu(C.byref(cfg), SEED_IMU, imu_t.ctypes.data, gyro.ctypes.data, accel.ctypes.data)
+    return imu_t, gyro, accel
+
+
+def scan_times(cfg: SynthConfig) -> np.ndarray:
+    L = lib()
+    return np.array([L.synth_scan_time(C.byref(cfg), i) for i in range(L.synth_num_scans(C.byref(cfg)))])
+
+
+def make_sequence(cfg: SynthConfig, with_camera: bool = True, lattice_leaves: int = 0) -> Sequence:
     L = lib()
     S = L.synth_num_scans(C.byref(cfg))
     scan_times = np.array([L.synth_scan_time(C.byref(cfg), i) for i in range(S)])
-    scans = make_scans(cfg, 0, S)
+    scans = make_lattice_scans(cfg, lattice_leaves, 0, S)[0] if lattice_leaves else make_scans(cfg, 0, S)
     poses = np.zeros((S, 4, 4))
     L.synth_loam_poses(C.byref(cfg), S, SEED_LOAM, poses.ctypes.data)
     n_imu = L.synth_num_imu(C.byref(cfg))

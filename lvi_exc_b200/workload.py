@@ -52,7 +52,7 @@ def lvi_stage_problem(seq, backend, cfg: pipeline.PipelineConfig | None = None, 
     scans_in_map = backend.undistort(mgr_map._base(), seq.scans_raw, seq.map_time, True)
     info["undistort_s"] = time.perf_counter() - t
     t = time.perf_counter()
-    smap = backend.build_surfel_map(scans_in_map.reshape(-1, 8), cfg.ndt_resolution, cfg.plane_lambda_refine)
+    smap = backend.build_surfel_map(backend.map_cloud(scans_in_map), cfg.ndt_resolution, cfg.plane_lambda_refine)
     info["map_build_s"] = time.perf_counter() - t
     t = time.perf_counter()
     spoints = backend.associate(smap, scans_in_map, seq.scans_raw, cfg.associated_radius, cfg.k_per_ring, cfg.time_downsample)

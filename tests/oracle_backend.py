@@ -32,6 +32,10 @@ class OracleBackend:
     def build_surfel_map(self, cloud, leaf, lam):
         return OracleSurfelMap(cloud, leaf, lam)
 
+    def map_cloud(self, scans_in_map, keys=None):
+        a = scans_in_map if keys is None else scans_in_map[np.nonzero(keys)[0]]
+        return a.reshape(-1, a.shape[-1])
+
     def associate(self, smap, scans_in_map, scans_raw, radius, k, step):
         pts, _ = smap.surfels.associate(scans_in_map, scans_raw, radius, k, step, self.assoc_mode)
         return pts

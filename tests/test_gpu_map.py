@@ -112,6 +112,36 @@ def test_association_bit_exact(cuda_backend, k, step):
     gmap.close()
 
 
+def test_scan_batch_path_matches_oracle(cuda_backend, monkeypatch):
+    """the packed scan-batch path (what the pipeline uses): map from the KEY scans only, association of all scans; fused and unfused
+    association kernels; export round trip"""
+    seq, scans_map = _cloud_synth()
+    keys = np.zeros(len(scans_map), bool); keys[::3] = True; keys[1] = True
+    batch = cuda_backend.batch_from_xyzi(scans_map)
+    back = batch.numpy()
+    fin = np.isfinite(scans_map[..., 0])
+    assert np.array_equal(np.isfinite(back[..., 0]), fin) and np.array_equal(back[fin][:, :3], scans_map[fin][:, :3])
+    assert np.array_equal(back[..., 4], scans_map[..., 4])
+    cloud_o = scans_map[np.nonzero(keys)[0]].reshape(-1, 8)
+    for lam in (0.6, 0.7):
+        gmap = cuda_backend.build_surfel_map(cuda_backend.map_cloud(batch, keys), 0.5, lam)
+        ov = ob.OracleVoxelMap(cloud_o, 0.5); osf = ob.OracleSurfels(ov, lam)
+        _compare_maps(gmap, ov, osf)
+        for unfused in ("", "1"):
+            if unfused:
+                monkeypatch.setenv("LVI_ASSOC_UNFUSED", "1")
+            else:
+                monkeypatch.delenv("LVI_ASSOC_UNFUSED", raising=False)
+            for k, step in ((2, 10), (1, 1), (3, 7)):
+                sp_g = cuda_backend.associate(gmap, batch, seq.scans_raw, 0.05, k, step)
+                sp_o, n_all = osf.associate(scans_map, seq.scans_raw, 0.05, k, step, mode=0)
+                assert cuda_backend.last_n_all == n_all and len(sp_g) == len(sp_o) and len(sp_g) > 50
+                for f in ("timestamp", "point", "point_in_map", "plane_id"):
+                    assert np.array_equal(sp_g[f], sp_o[f]), (f, unfused, k, step)
+        gmap.close()
+    batch.close()
+
+
 def test_association_ragged_scan(cuda_backend):
     """rings with fewer than 2k hits, timestamp == 0 points and all-NaN scans"""
     seq, scans_map = _cloud_synth()
@@ -145,7 +175,7 @@ def _cylinder_scans(S=8, H=16, W=1800, radius=30.0):
     return sm, raw
 
 
-def test_association_more_than_256_planes_on_one_ring(cuda_backend):
+def test_association_more_than_256_planes_on_one_ring(cuda_backend, monkeypatch):
     """the reference has no limit on the planes one ring may hit (L/src/core/surfel_association.cpp:111-159); the warp-table fast path
     holds 256 and hands fuller rings to the dense fallback kernel"""
     sm, raw = _cylinder_scans()
@@ -153,12 +183,15 @@ def test_association_more_than_256_planes_on_one_ring(cuda_backend):
     gmap = cuda_backend.build_surfel_map(cloud, 0.5, 0.6)
     ov = ob.OracleVoxelMap(cloud, 0.5); osf = ob.OracleSurfels(ov, 0.6)
     assert gmap.num_planes == osf.count and gmap.num_planes > 300
-    for k, step in ((2, 1), (2, 10)):
-        sp_g = cuda_backend.associate(gmap, sm, raw, 0.05, k, step)
-        sp_o, n_all = osf.associate(sm, raw, 0.05, k, step, mode=0)
-        assert cuda_backend.last_n_all == n_all and len(sp_g) == len(sp_o)
-        for f in ("timestamp", "point", "point_in_map", "plane_id"):
-            assert np.array_equal(sp_g[f], sp_o[f]), f
+    for unfused in ("", "1"):   # the fused per-scan kernel counts directly over the ring; the per-ring kernel hands over to the dense one
+        if unfused:
+            monkeypatch.setenv("LVI_ASSOC_UNFUSED", "1")
+        for k, step in ((2, 1), (2, 10)):
+            sp_g = cuda_backend.associate(gmap, sm, raw, 0.05, k, step)
+            sp_o, n_all = osf.associate(sm, raw, 0.05, k, step, mode=0)
+            assert cuda_backend.last_n_all == n_all and len(sp_g) == len(sp_o)
+            for f in ("timestamp", "point", "point_in_map", "plane_id"):
+                assert np.array_equal(sp_g[f], sp_o[f]), f
     sp_all, _ = osf.associate(sm[:1], raw[:1], 0.05, 2, 1, mode=1)
     per_ring = [len(np.unique(sp_all["plane_id"][np.abs(sp_all["point"][:, 2] - (0.03 + 0.027 * h)) < 1e-3])) for h in range(16)]
     assert max(per_ring) > 256, per_ring   # the case really exercises the fallback

@@ -239,6 +239,61 @@ void synth_scans(const synth_config* c, int32_t first_scan, int32_t n_scans, uin
     }
 }
 
+// C3: a room scene holds ~1.5 k occupied 0.5 m leaves, so the large NDT map of the 300 s configuration is synthesised
+// directly in voxel space: `n_leaves` occupied leaves on a sparse lattice (every second cell of a cube, in the map frame = LiDAR frame
+// at the first scan), each holding one planar patch (normal along a random axis, tilted by up to ~6 deg, offset by up to 0.1 m from the
+// leaf centre, range noise sigma 0.01 m along the normal).  The scan stream re-draws the patches in time order: point g of the stream
+// (scan-major, ring, azimuth; 16 x 1800 per scan) lies on leaf floor(g * n_leaves / n_points), so consecutive firings of a ring sweep
+// one surface as on a real sensor.  Every raw point is the map point seen from the sensor's ground-truth pose at its own firing time,
+// i.e. the stream is motion-distorted exactly like synth_scans' and the de-skew has real work to do.
+//   raw_out [n_scans][rings][az_steps] PointXYZIT ; map_out (may be NULL) the same points in the map frame, PointXYZI-shaped 8 floats
+void synth_lattice_scans(const synth_config* c, int64_t n_leaves, uint64_t seed, int32_t first_scan, int32_t n_scans, synth_raw_point* raw_out,
+                         float* map_out) {
+  const int H = c->rings, W = c->az_steps;
+  const int total_scans = synth_num_scans(c);
+  const int64_t n_points = static_cast<int64_t>(total_scans) * H * W;
+  int side = 1;
+  while (static_cast<int64_t>(side) * side * side < n_leaves) ++side;
+  const double leaf = 0.5;
+  const double org = -std::floor(side / 2.0) - 0.25 + 0.5;   // leaf centres at org + i (metres): cell centres of the absolute 0.5 m grid, never closer than 0.25 m to 0
+  const double az_dt = (1.0 / c->scan_rate) / W * (H == 16 ? 0.99533 : 1.0);
+  const double ring_dt = 2.304e-6;
+  const Pose L0 = lidar_pose_world(*c, synth_scan_time(c, 0));
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int s = 0; s < n_scans; ++s)
+    for (int h = 0; h < H; ++h) {
+      const int scan = first_scan + s;
+      const double t_scan = synth_scan_time(c, scan);
+      for (int wi = 0; wi < W; ++wi) {
+        const int64_t g = (static_cast<int64_t>(scan) * H + h) * W + wi;
+        const int64_t l = static_cast<int64_t>((static_cast<__int128>(g) * n_leaves) / n_points);
+        const int ix = static_cast<int>(l % side), iy = static_cast<int>((l / side) % side), iz = static_cast<int>(l / (static_cast<int64_t>(side) * side));
+        const double ctr[3] = {org + ix, org + iy, org + iz};
+        const int k = static_cast<int>(mix64(seed ^ (0x51ull << 40) ^ static_cast<uint64_t>(l)) % 3);   // dominant axis of the normal
+        const double tu = 0.1 * (2 * uni(seed, 7, 4 * l) - 1), tv = 0.1 * (2 * uni(seed, 7, 4 * l + 1) - 1);   // slopes of the patch
+        const double off = 0.1 * (2 * uni(seed, 7, 4 * l + 2) - 1);
+        const double a = 0.22 * (2 * uni(seed, 8, 2 * g) - 1), b = 0.22 * (2 * uni(seed, 8, 2 * g + 1) - 1);
+        const double hgt = off + tu * a + tv * b + c->range_noise * gauss(seed, 9, g) / std::sqrt(1.0 + tu * tu + tv * tv);
+        double pm[3];
+        pm[k] = ctr[k] + hgt; pm[(k + 1) % 3] = ctr[(k + 1) % 3] + a; pm[(k + 2) % 3] = ctr[(k + 2) % 3] + b;
+        (void)leaf;
+        const double t = t_scan + (wi + 0.5) * az_dt + h * ring_dt;
+        const Pose Lk = lidar_pose_world(*c, t);
+        const V3 pw = mul(L0.R, V3{pm[0], pm[1], pm[2]}) + L0.p;
+        const V3 pr = mulT(Lk.R, pw - Lk.p);
+        const size_t o = (static_cast<size_t>(s) * H + h) * W + wi;
+        synth_raw_point& r = raw_out[o];
+        r.x = static_cast<float>(pr.x); r.y = static_cast<float>(pr.y); r.z = static_cast<float>(pr.z);
+        r.pad = 1.0f; r.pad2 = 0; r.intensity = static_cast<float>(10 + (h * 7 + wi) % 90); r.timestamp = t;
+        if (map_out) {
+          float* m = map_out + 8 * o;
+          m[0] = static_cast<float>(pm[0]); m[1] = static_cast<float>(pm[1]); m[2] = static_cast<float>(pm[2]); m[3] = 1.0f;
+          m[4] = r.intensity; m[5] = m[6] = m[7] = 0.0f;
+        }
+      }
+    }
+}
+
 // LOAM-style poses: lidar pose at scan i expressed in the lidar frame of scan 0, row-major 4x4, with noise
 void synth_loam_poses(const synth_config* c, int32_t n_scans, uint64_t seed, double* T44) {
   Pose L0 = lidar_pose_world(*c, synth_scan_time(c, 0));
