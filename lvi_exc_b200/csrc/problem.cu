@@ -10,6 +10,7 @@
 // J_run^T J_run contribution, so HBM sees one fp64 atomic per (run, column pair) instead of one per (residual, pair).
 // The Huber corrector (ceres Corrector, rho'' <= 0 branch) and the EigenQuaternionParameterization tangent are folded in.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "problem.cuh"
@@ -259,9 +260,10 @@ void problem_linearize(lvi_problem* p, double* cost_d) {
   launch_linearize<RT_CAM>(p);
   {
     struct Restore { lvi_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, st};   // LVI_LAUNCH goes to ctx->stream
-    ctx->stream = ctx->aux[0];
+    const bool serial = std::getenv("LVI_LIN_SERIAL") != nullptr;   // diagnostics: every table on the main stream (per-kernel times mean something)
+    ctx->stream = serial ? st : ctx->aux[0];
     launch_linearize<RT_SURFEL>(p);
-    ctx->stream = ctx->aux[1];
+    ctx->stream = serial ? st : ctx->aux[1];
     launch_linearize<RT_ACCEL>(p); launch_linearize<RT_GYRO>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
   }
   for (int i = 0; i < 2; ++i) {

@@ -278,7 +278,21 @@ __global__ void __launch_bounds__(kGatherThreads) voxel_gather_kernel(const floa
       for (int w = 0; w < kGatherThreads / 32; ++w) t += s_red[w][tid];
       partial[static_cast<size_t>(l0 + tile) * kRunSums + tid] = t;
     }
-  } else {          // several leaves in the tile: one warp per leaf adds up the tile's share of it from shared memory
+  } else if (l1 - l0 >= 32) {   // many small leaves in the tile (millions of leaves of a few points): one THREAD per leaf, in point order
+    __syncthreads();
+    for (int l = l0 + tid; l <= l1; l += kGatherThreads) {
+      const int a = max(__ldg(leaf_start + l), o0) - o0, e = min(__ldg(leaf_start + l + 1), o1) - o0;
+      double t[kRunSums];
+#pragma unroll
+      for (int k = 0; k < kRunSums; ++k) t[k] = 0.0;
+      for (int i = a; i < e; ++i) {
+        const double x = s_x[i], y = s_y[i], z = s_z[i];
+        t[0] += x; t[1] += y; t[2] += z; t[3] += x * x; t[4] += x * y; t[5] += x * z; t[6] += y * y; t[7] += y * z; t[8] += z * z;
+      }
+#pragma unroll
+      for (int k = 0; k < kRunSums; ++k) partial[static_cast<size_t>(l + tile) * kRunSums + k] = t[k];
+    }
+  } else {          // a few leaves in the tile: one warp per leaf adds up the tile's share of it from shared memory
     __syncthreads();
     for (int l = l0 + warp; l <= l1; l += kGatherThreads / 32) {
       const int a = max(__ldg(leaf_start + l), o0) - o0, e = min(__ldg(leaf_start + l + 1), o1) - o0;
