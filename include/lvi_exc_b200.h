@@ -207,7 +207,7 @@ typedef struct lvi_solve_options {
 } lvi_solve_options;
 void lvi_solve_options_default(lvi_solve_options* o);
 
-enum { LVI_CONVERGENCE = 0, LVI_NO_CONVERGENCE = 1, LVI_FAILURE = 2 };
+enum { LVI_CONVERGENCE = 0, LVI_NO_CONVERGENCE = 1, LVI_FAILURE = 2, LVI_USER_SUCCESS = 3, LVI_USER_FAILURE = 4 };
 #define LVI_MAX_ITER_LOG 256
 /* ceres::Solver::Summary subset (BriefReport fields) + per-iteration log (IterationSummary) */
 typedef struct lvi_solve_summary {
@@ -236,6 +236,17 @@ int lvi_problem_destroy(lvi_problem* p);
  * every rank passes the SAME full problem; the library evaluates a contiguous time chunk of every residual table
  * per rank and all-reduces the normal equations (NCCL), so every rank returns identical parameters. */
 int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary);
+/* ceres::IterationCallback (K/trajectory_estimator.h:88-94 AddCallback; L/include/utils/ceres_callbacks.h:31-66): called after the
+ * evaluation of iteration 0 and after every LM iteration with ceres::IterationSummary's fields.  Return 0 = SOLVER_CONTINUE,
+ * 1 = SOLVER_ABORT, 2 = SOLVER_TERMINATE_SUCCESSFULLY.  With update_state != 0 (Solver::Options::update_state_every_iteration, the
+ * needs_state flag of AddCallback) the caller's in/out parameter arrays hold the current iterate when the callback runs. */
+typedef struct lvi_iteration_summary {
+  int32_t iteration; int32_t step_is_successful;
+  double cost, cost_change, gradient_max_norm, step_norm, trust_region_radius;
+} lvi_iteration_summary;
+typedef int (*lvi_iteration_callback)(const lvi_iteration_summary* it, void* user);
+int lvi_problem_solve_cb(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary, lvi_iteration_callback cb, void* user,
+                         int update_state);
 /* One evaluation at the current parameters (ceres::Problem::Evaluate analogue, used for parity tests):
  *   cost (with loss, excluding fixed cost) ; residuals[num_residuals] after loss correction, in table order
  *   gyro,accel,surfel,cam,camsurf,orient ; gradient[num_effective_parameters] in the library's tangent order
@@ -285,6 +296,11 @@ int lvi_undistort_d(lvi_ctx* ctx, const lvi_problem_desc* traj, const lvi_point_
  * at n times: pos[n*3], quat[n*4] (x,y,z,w), valid[n] = 0 where t is outside [MinTime, MaxTime). */
 int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* traj, const double* t, int64_t n, double* pos,
                             double* quat, uint8_t* valid);
+/* every quantity of kontiki::trajectories::TrajectoryEvaluation (K/trajectories/trajectory.h:27-37; Trajectory::Position / Velocity /
+ * Acceleration / Orientation / AngularVelocity, :95-133) at n times: pos/vel/acc[n*3] of the R3 spline, quat[n*4] (x,y,z,w) and the
+ * WORLD-frame angular velocity[n*3] of the SO3 spline.  Any output may be NULL; r3_knots may be NULL (SO3-only trajectory). */
+int lvi_trajectory_evaluate_full(lvi_ctx* ctx, const lvi_problem_desc* traj, const double* t, int64_t n, double* pos, double* vel,
+                                 double* acc, double* quat, double* angvel, uint8_t* valid);
 /* pcl::transformPointCloud(scan, out, pose) with the pose cast to a float 4x4 (L/include/core/scan_undistortion.h:111,
  * L/src/core/lidar_odometry.cpp:98), one pose per scan: poses[n_scans*16] row-major double. In/out PointXYZI (32 B). */
 int lvi_transform_scans(lvi_ctx* ctx, const void* scans_xyzi, int32_t n_scans, int64_t pts_per_scan,

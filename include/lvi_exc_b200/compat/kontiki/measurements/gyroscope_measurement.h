@@ -1,0 +1,1 @@
+#include "../kontiki_b200.h"

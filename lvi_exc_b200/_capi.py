@@ -129,10 +129,10 @@ ABI_SYMBOLS = [
     "lvi_voxel_build", "lvi_voxel_build_d", "lvi_voxel_destroy", "lvi_voxel_num_leaves", "lvi_voxel_num_points",
     "lvi_voxel_grid", "lvi_voxel_export", "lvi_surfel_extract", "lvi_surfel_destroy", "lvi_surfel_count",
     "lvi_surfel_export", "lvi_associate", "lvi_associate_d", "lvi_solve_options_default", "lvi_problem_create",
-    "lvi_problem_destroy", "lvi_problem_solve", "lvi_problem_evaluate", "lvi_problem_num_residuals",
+    "lvi_problem_destroy", "lvi_problem_solve", "lvi_problem_solve_cb", "lvi_problem_evaluate", "lvi_problem_num_residuals",
     "lvi_problem_num_tangent", "lvi_problem_tangent_offset_knot", "lvi_problem_tangent_offset_block",
     "lvi_problem_jacobian_dense", "lvi_problem_bench_iterations", "lvi_problem_layout", "lvi_associate_landmarks", "lvi_undistort",
-    "lvi_undistort_d", "lvi_transform_scans", "lvi_transform_scans_d", "lvi_trajectory_evaluate", "lvi_band_solve_dense",
+    "lvi_undistort_d", "lvi_transform_scans", "lvi_transform_scans_d", "lvi_trajectory_evaluate", "lvi_trajectory_evaluate_full", "lvi_band_solve_dense",
     "lvi_scan_batch_undistort_d", "lvi_scan_batch_transform", "lvi_scan_batch_from_xyzi_d", "lvi_scan_batch_export_xyzi",
     "lvi_scan_batch_destroy", "lvi_scan_batch_num_points", "lvi_scan_batch_num_scans", "lvi_scan_batch_points_d",
     "lvi_voxel_build_batch", "lvi_associate_batch",
@@ -200,6 +200,7 @@ def load() -> C.CDLL:
     for name in ("lvi_transform_scans", "lvi_transform_scans_d"):
         getattr(lib, name).argtypes = [vp, vp, C.c_int32, C.c_int64, c_double_p, vp]
     lib.lvi_trajectory_evaluate.argtypes = [vp, C.POINTER(ProblemDesc), c_double_p, C.c_int64, c_double_p, c_double_p, c_uint8_p]
+    lib.lvi_trajectory_evaluate_full.argtypes = [vp, C.POINTER(ProblemDesc), c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p]
     lib.lvi_scan_batch_undistort_d.argtypes = [vp, C.POINTER(ProblemDesc), vp, C.c_int32, C.c_int64, c_double_p, C.c_int, C.POINTER(vp), c_int32_p]
     lib.lvi_scan_batch_transform.argtypes = [vp, vp, c_double_p, C.POINTER(vp)]
     lib.lvi_scan_batch_from_xyzi_d.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int64, C.POINTER(vp)]

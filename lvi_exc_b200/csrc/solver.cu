@@ -1347,7 +1347,8 @@ static void refresh_diag(lvi_problem* p, DBuf<double>& dH, const lvi_solve_optio
   LVI_LAUNCH(p->ctx, lm_diag_kernel, blocks_for(p->nt), 256, 0, dH.p, p->scale.p, p->nt, o.min_lm_diagonal, o.max_lm_diagonal, p->diag.p);
 }
 
-static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summary& S) {
+static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summary& S, lvi_iteration_callback cb = nullptr, void* cb_user = nullptr,
+                     int cb_update_state = 0) {
   const auto T0 = std::chrono::steady_clock::now();
   std::memset(&S, 0, sizeof(S));
   lvi_ctx* ctx = p->ctx;
@@ -1404,10 +1405,18 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
   bool reuse_diagonal = false;
   int it = 0, invalid = 0;
+  int cb_verdict = 0;   // what the last iteration callback returned
   auto log_iter = [&](double cost, double change, double gm, double step, bool ok) {
     if (S.n_log < LVI_MAX_ITER_LOG) {
       const int k = S.n_log++;
       S.log_cost[k] = cost; S.log_cost_change[k] = change; S.log_gradient_max_norm[k] = gm; S.log_step_norm[k] = step; S.log_radius[k] = radius; S.log_successful[k] = ok;
+    }
+    if (cb) {   // ceres::IterationCallback (TrajectoryEstimator::AddCallback, K/trajectory_estimator.h:88-94)
+      if (cb_update_state) problem_download_params(p);   // update_state_every_iteration: the caller's arrays hold the current iterate
+      lvi_iteration_summary its{};
+      its.iteration = it; its.step_is_successful = ok ? 1 : 0; its.cost = cost; its.cost_change = change; its.gradient_max_norm = gm; its.step_norm = step;
+      its.trust_region_radius = radius;
+      cb_verdict = cb(&its, cb_user);
     }
   };
   log_iter(x_cost + fixed_cost, 0, gmax, 0, true);
@@ -1416,6 +1425,8 @@ static void solve_lm(lvi_problem* p, const lvi_solve_options& o, lvi_solve_summa
   bool done = gmax <= o.gradient_tolerance;
   if (done) S.termination_type = LVI_CONVERGENCE;
   while (!done) {
+    if (cb_verdict == 1) { S.termination_type = LVI_USER_FAILURE; break; }
+    if (cb_verdict == 2) { S.termination_type = LVI_USER_SUCCESS; break; }
     if (it >= o.max_num_iterations) break;
     ++it;
     if (!reuse_diagonal) refresh_diag(p, dH, o);
@@ -1520,6 +1531,14 @@ int lvi_problem_solve(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_su
     LVI_REQUIRE(p && opt && summary, LVI_ERR_INVALID, "lvi_problem_solve: null argument");
     activate(p->ctx);
     solve_lm(p, *opt, *summary);
+  });
+}
+
+int lvi_problem_solve_cb(lvi_problem* p, const lvi_solve_options* opt, lvi_solve_summary* summary, lvi_iteration_callback cb, void* user, int update_state) {
+  return guarded([&] {
+    LVI_REQUIRE(p && opt && summary, LVI_ERR_INVALID, "lvi_problem_solve_cb: null argument");
+    activate(p->ctx);
+    solve_lm(p, *opt, *summary, cb, user, update_state);
   });
 }
 

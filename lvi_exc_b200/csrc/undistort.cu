@@ -127,6 +127,45 @@ __global__ void traj_eval_kernel(TrajView T, const double* __restrict__ t, int64
   valid[i] = ok ? 1 : 0;
 }
 
+// all five quantities of kontiki::trajectories::TrajectoryEvaluation (K/trajectories/trajectory.h:27-37) at arbitrary times:
+// position / velocity / acceleration of the R3 spline (uniform_r3_spline_trajectory.h:36-103), orientation and WORLD-frame angular
+// velocity of the SO3 spline (uniform_so3_spline_trajectory.h:46-125)
+__global__ void traj_eval_full_kernel(TrajView T, const double* __restrict__ t, int64_t n, double* __restrict__ pos, double* __restrict__ vel,
+                                      double* __restrict__ acc, double* __restrict__ quat, double* __restrict__ angvel, unsigned char* __restrict__ valid) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double tt = t[i];
+  bool ok = !(T.t0 > tt || T.t_max <= tt || !(tt == tt));
+  int i0 = 0; double u = 0;
+  if (ok) {
+    const double s = (tt - T.t0) / T.dt;
+    i0 = static_cast<int>(floor(s));
+    u = s - i0;
+    ok = i0 >= 0 && i0 <= T.n_knots - 4;
+  }
+  V3 p = v3(0, 0, 0), v = p, a = p, w = p;
+  Q4 q = q4(0, 0, 0, 1);
+  if (ok) {
+    double B[4], Bv[4], Ba[4];
+    basis_pos(u, B);
+    const double u2 = u * u;   // (0,1,2u,3u^2) M / dt
+    Bv[0] = T.dt_inv * (-3.0 + 6.0 * u - 3.0 * u2) / 6.0; Bv[1] = T.dt_inv * (-12.0 * u + 9.0 * u2) / 6.0;
+    Bv[2] = T.dt_inv * (3.0 + 6.0 * u - 9.0 * u2) / 6.0; Bv[3] = T.dt_inv * (3.0 * u2) / 6.0;
+    basis_acc(u, T.dt_inv, Ba);
+    if (T.r3) { p = r3_spline(T.r3 + 3 * i0, B); v = r3_spline(T.r3 + 3 * i0, Bv); a = r3_spline(T.r3 + 3 * i0, Ba); }
+    So3Eval e;
+    so3_spline_eval(T.so3 + 4 * i0, u, T.dt_inv, true, false, e);
+    q = e.q;
+    w = e.R * e.w_body;
+  }
+  if (pos) { pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
+  if (vel) { vel[3 * i] = v.x; vel[3 * i + 1] = v.y; vel[3 * i + 2] = v.z; }
+  if (acc) { acc[3 * i] = a.x; acc[3 * i + 1] = a.y; acc[3 * i + 2] = a.z; }
+  if (quat) { quat[4 * i] = q.x; quat[4 * i + 1] = q.y; quat[4 * i + 2] = q.z; quat[4 * i + 3] = q.w; }
+  if (angvel) { angvel[3 * i] = w.x; angvel[3 * i + 1] = w.y; angvel[3 * i + 2] = w.z; }
+  valid[i] = ok ? 1 : 0;
+}
+
 struct Mat34f { float m[12]; };
 
 // pcl::transformPointCloud with a float 4x4 per scan.  The input is a PCL cloud (2 x float4 per point) or a packed batch; so is the output.
@@ -360,6 +399,33 @@ int lvi_trajectory_evaluate(lvi_ctx* ctx, const lvi_problem_desc* d, const doubl
     T.r3 = r3.p; T.so3 = so3.p; T.hlog = hlog.p; T.qL = q4(0, 0, 0, 1); T.pL = v3(0, 0, 0);
     LVI_LAUNCH(ctx, traj_eval_kernel, static_cast<int>((n + 127) / 128), 128, 0, T, td.p, n, pd.p, qd.p, vd.p);
     pd.download(pos, pd.n, st); qd.download(quat, qd.n, st); vd.download(valid, n, st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int lvi_trajectory_evaluate_full(lvi_ctx* ctx, const lvi_problem_desc* d, const double* t, int64_t n, double* pos, double* vel, double* acc, double* quat,
+                                 double* angvel, uint8_t* valid) {
+  return guarded([&] {
+    LVI_REQUIRE(ctx && d && t && valid && n > 0, LVI_ERR_INVALID, "lvi_trajectory_evaluate_full: bad argument");
+    LVI_REQUIRE(d->so3_knots && d->n_knots >= 4, LVI_ERR_INVALID, "lvi_trajectory_evaluate_full: trajectory needs the SO3 spline and >= 4 knots");
+    activate(ctx);
+    cudaStream_t st = ctx->stream;
+    const int nk = d->n_knots;
+    DBuf<double> r3(d->r3_knots ? 3 * static_cast<size_t>(nk) : 0), so3(4 * static_cast<size_t>(nk)), td(n);
+    DBuf<double> pd(3 * static_cast<size_t>(n)), vd(3 * static_cast<size_t>(n)), ad(3 * static_cast<size_t>(n)), qd(4 * static_cast<size_t>(n)), wd(3 * static_cast<size_t>(n));
+    DBuf<unsigned char> okd(n);
+    if (d->r3_knots) r3.upload(d->r3_knots, r3.n, st);
+    so3.upload(d->so3_knots, so3.n, st); td.upload(t, n, st);
+    TrajView T;
+    T.t0 = d->t0; T.dt = d->dt; T.dt_inv = 1.0 / d->dt; T.t_max = d->t0 + (nk - 3) * d->dt; T.toff = 0.0; T.n_knots = nk;
+    T.r3 = d->r3_knots ? r3.p : nullptr; T.so3 = so3.p; T.hlog = nullptr; T.qL = q4(0, 0, 0, 1); T.pL = v3(0, 0, 0);
+    LVI_LAUNCH(ctx, traj_eval_full_kernel, static_cast<int>((n + 127) / 128), 128, 0, T, td.p, n, pd.p, vd.p, ad.p, qd.p, wd.p, okd.p);
+    if (pos) pd.download(pos, pd.n, st);
+    if (vel) vd.download(vel, vd.n, st);
+    if (acc) ad.download(acc, ad.n, st);
+    if (quat) qd.download(quat, qd.n, st);
+    if (angvel) wd.download(angvel, wd.n, st);
+    okd.download(valid, n, st);
     LVI_CUDA(cudaStreamSynchronize(st));
   });
 }
