@@ -148,6 +148,101 @@ __global__ void __launch_bounds__(kLinWarps * 32) linearize_kernel(ProblemView P
   if (lane == 0 && cost_acc != 0.0) atomicAdd(cost, cost_acc);
 }
 
+// ---- loss-corrected Jacobian rows for the tile gather (assemble.cu) ---------------------------------------------------------------------
+// One lane per residual evaluates r and J (fp64, analytic) and stages them in shared memory; the warp then
+//   * (camera table) adds the inverse-depth couplings J_rho^T [J, r] to the landmark's Schur row, lanes across columns,
+//   * folds every second-window column whose knot the first window already holds into the first window's column (pos_kernel marks it -1), so
+//     the positions of one residual's columns are distinct and the gather can scatter them without collisions,
+//   * copies the rows out with coalesced stores: J [residual][row][column], r [residual][row] in table order.
+template <int TYPE>
+__global__ void __launch_bounds__(kLinWarps * 32) jacobian_kernel(ProblemView P, SchurView SV, double* __restrict__ Jg, double* __restrict__ g,
+                                                                  double* __restrict__ cost) {
+  constexpr int ROWS = RTr<TYPE>::rows, COLS = RTr<TYPE>::cols, RC = ROWS * COLS, SC = RTr<TYPE>::shared_cols;
+  constexpr int RS = (RC + ROWS + 1) & ~1;   // asm_block_doubles(TYPE): [J rows | r | pad]
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Jw = smem + warp * RTr<TYPE>::warp_doubles;
+  double* rw = Jw + 32 * RC;
+  const ResTable& T = P.tab[TYPE];
+  double cost_acc = 0.0;
+  const int stride = gridDim.x * kLinWarps * 32;
+  for (int base = T.lo + (blockIdx.x * kLinWarps + warp) * 32; base < T.hi; base += stride) {
+    const bool valid = base + lane < T.hi;
+    const int i = base + lane;
+    if (valid) {
+      ResOut o;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k)
+        for (int c = 0; c < COLS; ++c) o.J[k][c] = 0.0;
+      eval_residual<TYPE>(P, i, true, o);
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) s += o.r[k] * o.r[k];
+      double sc;
+      const double rho = huber(s, T.huber ? T.huber[i] : -1.0, sc);
+      cost_acc += 0.5 * rho;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        rw[lane * ROWS + k] = o.r[k] * sc;
+        for (int c = 0; c < COLS; ++c) Jw[lane * RC + k * COLS + c] = o.J[k][c] * sc;
+      }
+    }
+    __syncwarp();
+    const int nvalid = min(32, T.hi - base);
+    if (TYPE == RT_CAM) {  // inverse-depth column: one parameter per landmark, kept out of the band (eliminated by Schur complement)
+      for (int r = 0; r < nvalid; ++r) {
+        const int ir = base + r;
+        const int lm = T.ia[ir];
+        const int pr = P.pos_rho[lm];
+        if (pr < 0) continue;
+        const double* Jr = Jw + r * RC;
+        const int rs = SV.row_start[lm], obs_base = T.ib[ir];
+        for (int c = lane; c <= SC; c += 32) {   // slots with a constant parameter are skipped by their row_pos when the row is used
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + SC] * Jr[k * COLS + c];
+          if (acc == 0.0) continue;
+          if (c == SC) atomicAdd(SV.Hrr + (pr - SV.base), acc);
+          else atomicAdd(SV.Hrx + rs + (c < 24 ? c : c < 48 ? obs_base + (c - 24) : 24 + (c - 48)), acc);
+        }
+        if (lane == 0) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < ROWS; ++k) acc += Jr[k * COLS + SC] * rw[r * ROWS + k];
+          atomicAdd(g + pr, acc);
+        }
+      }
+      __syncwarp();
+    }
+    if (RTr<TYPE>::two_eval && valid) {   // overlapping windows: same knot, same parameter
+      const int shift = T.i0b[i] - T.i0a[i];
+      if (shift > -4 && shift < 4) {
+        double* Jr = Jw + lane * RC;
+        for (int jp = 0; jp < 4; ++jp) {
+          const int j = shift + jp;
+          if (j < 0 || j > 3) continue;
+          for (int k = 0; k < ROWS; ++k)
+            for (int c = 0; c < 3; ++c) {
+              Jr[k * COLS + 3 * j + c] += Jr[k * COLS + 24 + 3 * jp + c];           Jr[k * COLS + 24 + 3 * jp + c] = 0.0;
+              Jr[k * COLS + 12 + 3 * j + c] += Jr[k * COLS + 36 + 3 * jp + c];      Jr[k * COLS + 36 + 3 * jp + c] = 0.0;
+            }
+        }
+      }
+    }
+    __syncwarp();
+    double* Jo = Jg + static_cast<size_t>(base) * RS;
+    for (int e = lane; e < nvalid * RS; e += 32) {
+      const int l = e / RS, o = e - l * RS;
+      Jo[e] = o < RC ? Jw[l * RC + o] : (o < RC + ROWS ? rw[l * ROWS + (o - RC)] : 0.0);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(FULL, cost_acc, o);
+  if (lane == 0 && cost_acc != 0.0) atomicAdd(cost, cost_acc);
+}
+
 // cost only (trial steps, fixed cost): one thread per residual
 template <int TYPE>
 __global__ void __launch_bounds__(128) cost_kernel(ProblemView P, double* __restrict__ cost) {
@@ -222,6 +317,25 @@ static void launch_linearize(lvi_problem* p) {
 }
 
 template <int TYPE>
+static void launch_jacobian(lvi_problem* p) {
+  const ResTable& T = p->view.tab[TYPE];
+  if (T.n == 0 || !T.active || T.hi <= T.lo) return;
+  bool& attr_set = p->ctx->ks.jac_attr[TYPE];
+  const size_t smem = static_cast<size_t>(kLinWarps) * RTr<TYPE>::warp_doubles * sizeof(double);
+  if (!attr_set) {
+    LVI_CUDA(cudaFuncSetAttribute(jacobian_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const int per_cta = kLinWarps * 32;
+  int grid = std::max(1, (T.hi - T.lo + per_cta - 1) / per_cta);
+  const int cap = p->ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  static const char* const names[RT_COUNT] = {"jacobian_kernel<RT_GYRO>", "jacobian_kernel<RT_ACCEL>", "jacobian_kernel<RT_SURFEL>", "jacobian_kernel<RT_CAM>",
+                                              "jacobian_kernel<RT_CAMSURF>", "jacobian_kernel<RT_ORIENT>"};
+  LVI_LAUNCH_AS(p->ctx, names[TYPE], jacobian_kernel<TYPE>, grid, per_cta, smem, p->view, p->schur, p->asmp.J[TYPE].p, p->g.p, p->scal.p);
+}
+
+template <int TYPE>
 static void launch_cost(lvi_problem* p, double* cost_d, bool want_active, bool want_inactive) {
   const ResTable& T = p->view.tab[TYPE];
   if (T.n == 0) return;
@@ -257,18 +371,56 @@ void problem_linearize(lvi_problem* p, double* cost_d) {
   lvi_ctx* ctx = p->ctx;
   LVI_CUDA(cudaEventRecord(ctx->ev_fork, st));
   for (int i = 0; i < 2; ++i) LVI_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
-  launch_linearize<RT_CAM>(p);
+  static const bool scatter = std::getenv("LVI_ASM_SCATTER") != nullptr;   // diagnostics: the first version (atomic scatter per run of residuals)
+  if (scatter) launch_linearize<RT_CAM>(p); else launch_jacobian<RT_CAM>(p);
   {
     struct Restore { lvi_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, st};   // LVI_LAUNCH goes to ctx->stream
     const bool serial = std::getenv("LVI_LIN_SERIAL") != nullptr;   // diagnostics: every table on the main stream (per-kernel times mean something)
     ctx->stream = serial ? st : ctx->aux[0];
-    launch_linearize<RT_SURFEL>(p);
+    if (scatter) launch_linearize<RT_SURFEL>(p); else launch_jacobian<RT_SURFEL>(p);
     ctx->stream = serial ? st : ctx->aux[1];
-    launch_linearize<RT_ACCEL>(p); launch_linearize<RT_GYRO>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
+    if (scatter) { launch_linearize<RT_ACCEL>(p); launch_linearize<RT_GYRO>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p); }
+    else { launch_jacobian<RT_ACCEL>(p); launch_jacobian<RT_GYRO>(p); launch_jacobian<RT_CAMSURF>(p); launch_jacobian<RT_ORIENT>(p); }
   }
   for (int i = 0; i < 2; ++i) {
     LVI_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
     LVI_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+  }
+  if (!scatter) assemble_gather(p);   // H tiles, corner and g from the Jacobian rows (owner-computes tile gather, fp64 tensor pipe)
+  if (!scatter && std::getenv("LVI_ASM_CHECK")) {   // diagnostics: the atomic-scatter kernels on the same point, compared element by element
+    const BandSys& H = p->H;
+    std::vector<double> t1(p->H_tiles.n), c1(p->H_C.n), g1(p->g.n), t2(p->H_tiles.n), c2(p->H_C.n), g2(p->g.n);
+    p->H_tiles.download(t1.data(), t1.size(), st); p->H_C.download(c1.data(), c1.size(), st); p->g.download(g1.data(), g1.size(), st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+    p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st); p->Hrx.zero(st); p->Hrr.zero(st);
+    LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
+    launch_linearize<RT_CAM>(p); launch_linearize<RT_SURFEL>(p); launch_linearize<RT_ACCEL>(p); launch_linearize<RT_GYRO>(p); launch_linearize<RT_CAMSURF>(p); launch_linearize<RT_ORIENT>(p);
+    p->H_tiles.download(t2.data(), t2.size(), st); p->H_C.download(c2.data(), c2.size(), st); p->g.download(g2.data(), g2.size(), st);
+    LVI_CUDA(cudaStreamSynchronize(st));
+    int shown = 0;
+    double worst = 0, scale_ = 0;
+    for (size_t e = 0; e < t1.size(); ++e) {
+      const size_t tile = e >> 10; const int J = static_cast<int>(tile / H.TPC), s = static_cast<int>(tile % H.TPC), b = (e >> 5) & 31, a = e & 31;
+      if (s == 0 && a < b) continue;   // upper triangle of a diagonal tile: not part of the store
+      const double d = std::fabs(t1[e] - t2[e]);
+      scale_ = std::max(scale_, std::fabs(t2[e]));
+      if (d > worst) worst = d;
+      if (d > 1e-9 * (1.0 + std::fabs(t2[e])) && shown < 12) { std::fprintf(stderr, "[asm check] tile J=%d s=%d (a=%d,b=%d): gather %.12g scatter %.12g\n", J, s, a, b, t1[e], t2[e]); ++shown; }
+    }
+    double worst_c = 0, worst_g = 0;
+    for (int bj = 0; bj < H.ldc; ++bj) for (int bi = bj; bi < H.ldc; ++bi) {
+      const size_t e = bi + static_cast<size_t>(H.ldc) * bj;
+      const double d = std::fabs(c1[e] - c2[e]);
+      worst_c = std::max(worst_c, d);
+      if (d > 1e-9 * (1.0 + std::fabs(c2[e])) && shown < 24) { std::fprintf(stderr, "[asm check] corner (%d,%d): gather %.12g scatter %.12g\n", bi, bj, c1[e], c2[e]); ++shown; }
+    }
+    for (size_t e = 0; e < g1.size(); ++e) {
+      const double d = std::fabs(g1[e] - g2[e]);
+      worst_g = std::max(worst_g, d);
+      if (d > 1e-9 * (1.0 + std::fabs(g2[e])) && shown < 36) { std::fprintf(stderr, "[asm check] g[%zu]: gather %.12g scatter %.12g\n", e, g1[e], g2[e]); ++shown; }
+    }
+    std::fprintf(stderr, "[asm check] nb %d nbo %d NT %d T %d RB %d | items %d entries %d | max |dH| %.3g (max |H| %.3g), corner %.3g, g %.3g\n", H.nb, H.nbo, H.NT, H.T, H.RB,
+                 p->asmp.n_items, p->asmp.n_entries, worst, scale_, worst_c, worst_g);
   }
   if (cost_d && cost_d != p->scal.p) LVI_CUDA(cudaMemcpyAsync(cost_d, p->scal.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
 }
@@ -371,6 +523,7 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
     LVI_CUDA(cudaStreamSynchronize(p->ctx->stream));
   }
   p->has_solver_buffers = true;
+  assemble_build_plan(p);
 }
 
 void problem_download_params(lvi_problem* p) {

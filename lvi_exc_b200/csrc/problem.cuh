@@ -70,6 +70,24 @@ struct SchurView {
   double* yrho;             // [n_rho] back-substituted step
 };
 
+// ---- normal-equation assembly by tile gather (assemble.cu)
+// one residual table's loss-corrected Jacobian in HBM: one block of `rstride` doubles per residual = [row][column] | r[row] | padding to a
+// 16-byte multiple (so a block moves with one bulk async copy); pos [residual][column] = position in the linear system (-1: constant block,
+// or a column merged into an earlier one)
+struct RowSetView { const double* J; const int* pos; int ncols, rows, rstride, lo, hi; };
+LVI_HD int asm_block_doubles(int t) { return (rt_rows(t) * rt_cols(t) + rt_rows(t) + 1) & ~1; }
+struct AsmSets { RowSetView s[RT_COUNT]; };
+struct AsmPlan {
+  DBuf<double> J[RT_COUNT];
+  DBuf<int> pos[RT_COUNT];
+  DBuf<unsigned long long> keys;   // (tile << 32 | table << 29 | residual), sorted
+  DBuf<int> item_start;            // [n_items + 1] offsets into keys: one work item = <= kChunk residuals of one tile
+  DBuf<unsigned char> desc;        // [n_entries][64] Jacobian column behind each panel column (row range | column range), 255 = none
+  AsmSets sets{};
+  int n_items = 0, n_entries = 0;
+  bool built = false;
+};
+
 // free parameter block (for Plus / norms): kind 0 Euclidean, 1 quaternion (x,y,z,w), 2 Euclidean with lower bound 0
 struct FreeBlock { int off; int pos; int size; int kind; };
 
@@ -98,6 +116,7 @@ struct lvi_problem {
   lvi::DBuf<int> pack_map;       // multi-GPU: indices of the structurally non-zero tiles of H (what the all-reduce has to move)
   lvi::DBuf<double> pack_buf;    // ... and their contiguous staging copy
   int n_pack = 0;
+  lvi::AsmPlan asmp;
   lvi::SchurView schur{};
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;
@@ -115,6 +134,9 @@ void problem_linearize(lvi_problem* p, double* cost_d);                         
 void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active_only, bool inactive_only);
 void problem_ensure_solver_buffers(lvi_problem* p);
 void problem_download_params(lvi_problem* p);
+// assemble.cu
+void assemble_build_plan(lvi_problem* p);   // once per problem, after problem_ensure_solver_buffers
+void assemble_gather(lvi_problem* p);       // H tiles, corner and g from the Jacobian rows jacobian_kernel<TYPE> left in the plan's buffers
 // solver.cu
 void band_factor_solve(lvi_ctx* ctx, BandSys& A, BandSys& A2);
 void init_second_level(const BandSys& A, BandSys& A2);   // sizes of the separator system (no allocation)

