@@ -116,7 +116,7 @@ def workload_config(args, pd, world: int, num_residuals: int, tangent_dims: int)
     return {"workload": WORKLOAD, "seconds": args.duration, "residual_blocks": pd_sizes(pd), "num_residuals": int(num_residuals),
             "tangent_dims": int(tangent_dims),
             "l2_policy": "inputs larger than L2: the normal-equation tile stores H + A (416 MB at C2) exceed the 126 MB L2, no flush needed",
-            "parallelism": f"dp{world}: residual tables sharded by time chunk, one NCCL all-reduce of the packed normal equations"}
+            "parallelism": f"dp{world}: residual tables sharded by time chunk, normal equations summed by one kernel over NVLink peer memory (ncclAllReduce of the packed tiles where IPC mapping is unavailable)"}
 
 
 def run_reference(args, rank: int):

@@ -360,6 +360,18 @@ void assemble_build_plan(lvi_problem* p) {
   LVI_LAUNCH(ctx, desc_kernel, (n_entries + 127) / 128, 128, 0, A.sets, p->H, A.keys.p, n_entries, A.desc.p);
 }
 
+__global__ void mark_tiles_kernel(const unsigned long long* __restrict__ keys, int n, long long n_band_tiles, unsigned char* __restrict__ flags) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long long tile = static_cast<long long>(keys[e] >> 32);
+  if (tile < n_band_tiles) flags[tile] = 1;
+}
+void assemble_mark_tiles(lvi_problem* p, unsigned char* flags_d) {
+  AsmPlan& A = p->asmp;
+  if (A.n_entries == 0) return;
+  LVI_LAUNCH(p->ctx, mark_tiles_kernel, (A.n_entries + 255) / 256, 256, 0, A.keys.p, A.n_entries, static_cast<long long>(p->H.NT) * p->H.TPC, flags_d);
+}
+
 // tile += gathered J^T J, g += J^T r  (H, g zeroed by the caller; the Jacobian rows are in the plan's buffers)
 void assemble_gather(lvi_problem* p) {
   AsmPlan& A = p->asmp;
@@ -370,7 +382,7 @@ void assemble_gather(lvi_problem* p) {
     p->ctx->ks.gather_attr = true;
   }
   const int grid = std::min((A.n_items + kGatherWarps - 1) / kGatherWarps, p->ctx->sm_count * 3);
-  LVI_LAUNCH(p->ctx, gather_kernel, grid, kGatherWarps * 32, smem, A.sets, p->H, A.keys.p, A.desc.p, A.item_start.p, A.n_items, A.n_entries, p->g.p);
+  LVI_LAUNCH(p->ctx, gather_kernel, grid, kGatherWarps * 32, smem, A.sets, p->H_lin, A.keys.p, A.desc.p, A.item_start.p, A.n_items, A.n_entries, p->g_lin);
 }
 
 }  // namespace lvi

@@ -116,6 +116,7 @@ int lvi_ctx_create_nccl(int device, const void* id128, int rank, int world, lvi_
 int lvi_ctx_destroy(lvi_ctx* ctx) {
   if (!ctx) return LVI_OK;
   cudaSetDevice(ctx->device);
+  p2p_ctx_release(ctx);
   if (ctx->owns_nccl && ctx->nccl) nccl().CommDestroy(static_cast<ncclComm_t>(ctx->nccl));
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);

@@ -75,6 +75,17 @@ struct lvi_ctx {
     size_t assoc_attr = 48 * 1024;    // assoc.cu: ... to assoc_scan_fused_kernel
     bool selftest_done = false;
   } ks;
+  // Peer-memory region for the fused normal-equation reduction (p2p.cu): one cudaMalloc'd block per rank, exported with CUDA IPC and mapped
+  // by every other rank of the node, so the reduction kernel reads its peers' tiles directly over NVLink.  state: 0 not tried, 1 mapped,
+  // -1 unavailable on this node (the NCCL all-reduce is used instead).
+  struct PeerRegion {
+    void* base = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> peer;   // [world] base pointers (own = base)
+    void** peer_d = nullptr;   // device copy of the table
+    unsigned epoch = 0;
+    int state = 0;
+  } p2p;
   // host-side resources every solve needs, made once per context (cudaMallocHost / cudaEventCreate cost 0.1 - 1 ms each on a cold driver)
   double* h_scal = nullptr;           // pinned mirror of a problem's scalar block (64 doubles)
   std::vector<cudaEvent_t> timing_events;   // reused by the LM loop's phase timers
@@ -97,6 +108,8 @@ struct lvi_ctx {
 };
 
 namespace lvi {
+
+void p2p_ctx_release(lvi_ctx* ctx);   // p2p.cu: unmap / free the peer-memory region
 
 // The stream the calling thread's current entry point works on.  Device buffers are taken from and returned to the device's
 // stream-ordered memory pool on it (cudaMallocAsync / cudaFreeAsync; the pool keeps freed blocks, release threshold = never), so

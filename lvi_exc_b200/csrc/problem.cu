@@ -332,7 +332,7 @@ static void launch_jacobian(lvi_problem* p) {
   if (grid > cap) grid = cap;
   static const char* const names[RT_COUNT] = {"jacobian_kernel<RT_GYRO>", "jacobian_kernel<RT_ACCEL>", "jacobian_kernel<RT_SURFEL>", "jacobian_kernel<RT_CAM>",
                                               "jacobian_kernel<RT_CAMSURF>", "jacobian_kernel<RT_ORIENT>"};
-  LVI_LAUNCH_AS(p->ctx, names[TYPE], jacobian_kernel<TYPE>, grid, per_cta, smem, p->view, p->schur, p->asmp.J[TYPE].p, p->g.p, p->scal.p);
+  LVI_LAUNCH_AS(p->ctx, names[TYPE], jacobian_kernel<TYPE>, grid, per_cta, smem, p->view, p->schur_lin, p->asmp.J[TYPE].p, p->g_lin, p->cost_lin);
 }
 
 template <int TYPE>
@@ -363,8 +363,12 @@ void problem_set_param_source(lvi_problem* p, const double* x) {
 void problem_linearize(lvi_problem* p, double* cost_d) {
   cudaStream_t st = p->ctx->stream;
   problem_ensure_solver_buffers(p);
-  p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st); p->Hrx.zero(st); p->Hrr.zero(st);
-  LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
+  if (p->p2p.active) {
+    p2p_begin_linearize(p);   // clears this rank's units in the peer-memory region (after the peers have finished reading the previous ones)
+  } else {
+    p->H_tiles.zero(st); p->H_C.zero(st); p->g.zero(st); p->Hrx.zero(st); p->Hrr.zero(st);
+    LVI_CUDA(cudaMemsetAsync(p->scal.p, 0, sizeof(double), st));
+  }
   problem_set_param_source(p, p->X.p);
   // The per-type kernels only meet in fp64 atomics, and each of them leaves most of the machine idle (the camera kernel is 502 CTAs of
   // 64 threads at 255 registers): they run side by side on three streams -- camera | surfel | IMU and the rest -- and join again.
@@ -422,7 +426,7 @@ void problem_linearize(lvi_problem* p, double* cost_d) {
     std::fprintf(stderr, "[asm check] nb %d nbo %d NT %d T %d RB %d | items %d entries %d | max |dH| %.3g (max |H| %.3g), corner %.3g, g %.3g\n", H.nb, H.nbo, H.NT, H.T, H.RB,
                  p->asmp.n_items, p->asmp.n_entries, worst, scale_, worst_c, worst_g);
   }
-  if (cost_d && cost_d != p->scal.p) LVI_CUDA(cudaMemcpyAsync(cost_d, p->scal.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (cost_d && cost_d != p->cost_lin) LVI_CUDA(cudaMemcpyAsync(cost_d, p->cost_lin, sizeof(double), cudaMemcpyDeviceToDevice, st));
 }
 
 void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active, bool inactive) {
@@ -518,12 +522,17 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
     }
     p->pack_map.alloc(std::max<size_t>(map.size(), 1));
     p->pack_map.upload(map.data(), map.size(), p->ctx->stream);
-    p->pack_buf.alloc(std::max<size_t>(map.size() * kTileElems, 1));
+    // one staging buffer for ONE collective per iteration: [packed tiles | corner | g | Schur rows | Schur diagonal | cost]
+    p->pack_buf.alloc(map.size() * kTileElems + p->H_C.n + p->g.n + p->Hrx.n + p->Hrr.n + 1);
     p->n_pack = static_cast<int>(map.size());
     LVI_CUDA(cudaStreamSynchronize(p->ctx->stream));
   }
   p->has_solver_buffers = true;
+  p->H_lin = p->H; p->schur_lin = p->schur; p->g_lin = p->g.p; p->cost_lin = p->scal.p;
   assemble_build_plan(p);
+  if (p->ctx->world > 1 && p2p_prepare(p)) {   // the peers' contributions are read straight out of their HBM: the private store is only ever written
+    p->H_tiles.zero(p->ctx->stream);
+  }
 }
 
 void problem_download_params(lvi_problem* p) {

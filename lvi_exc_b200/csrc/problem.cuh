@@ -88,6 +88,17 @@ struct AsmPlan {
   bool built = false;
 };
 
+// multi-GPU reduction of the normal equations over peer memory (p2p.cu)
+struct P2PPlan {
+  bool active = false;
+  int n_tile_units = 0, n_units = 0, n_list = 0;
+  size_t small_elems = 0, off_flags = 0, off_data = 0;
+  DBuf<unsigned char> tile_flags;   // [n_tile_units] 1 = this rank's assembly plan writes the tile
+  DBuf<int> unit_list;              // units the reduction visits
+  DBuf<double> small_sum;           // reduced {corner, g, Schur rows, Schur diagonal, cost}, copied out to the private buffers
+  DBuf<int> counter;
+};
+
 // free parameter block (for Plus / norms): kind 0 Euclidean, 1 quaternion (x,y,z,w), 2 Euclidean with lower bound 0
 struct FreeBlock { int off; int pos; int size; int kind; };
 
@@ -117,7 +128,13 @@ struct lvi_problem {
   lvi::DBuf<double> pack_buf;    // ... and their contiguous staging copy
   int n_pack = 0;
   lvi::AsmPlan asmp;
+  lvi::P2PPlan p2p;
   lvi::SchurView schur{};
+  // where a linearisation writes: the private buffers (H, schur, g, scal), or this rank's peer-memory region (multi-GPU, p2p.cu)
+  lvi::BandSys H_lin{};
+  lvi::SchurView schur_lin{};
+  double* g_lin = nullptr;
+  double* cost_lin = nullptr;
   lvi::DBuf<int> row_start, row_pos, lm_of_rho;
   lvi::DBuf<double> Hrx, Hrr, yrho;
   lvi::DBuf<int> fail;
@@ -137,6 +154,12 @@ void problem_download_params(lvi_problem* p);
 // assemble.cu
 void assemble_build_plan(lvi_problem* p);   // once per problem, after problem_ensure_solver_buffers
 void assemble_gather(lvi_problem* p);       // H tiles, corner and g from the Jacobian rows jacobian_kernel<TYPE> left in the plan's buffers
+void assemble_mark_tiles(lvi_problem* p, unsigned char* flags_d);   // flags[tile] = 1 for every band / border tile this rank's plan writes
+// p2p.cu
+bool p2p_prepare(lvi_problem* p);           // collective; true: the linearisation targets point into the peer-memory region
+void p2p_begin_linearize(lvi_problem* p);
+void p2p_reduce(lvi_problem* p);
+void p2p_ctx_release(lvi_ctx* ctx);
 // solver.cu
 void band_factor_solve(lvi_ctx* ctx, BandSys& A, BandSys& A2);
 void init_second_level(const BandSys& A, BandSys& A2);   // sizes of the separator system (no allocation)

@@ -1280,19 +1280,20 @@ static void read_scalars(lvi_problem* p, Scalars& s) {
 static void linearize(lvi_problem* p) {
   problem_linearize(p, nullptr);
   lvi_ctx* ctx = p->ctx;
-  if (ctx->world > 1) {
-    if (p->n_pack > 0) {
-      LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, p->pack_buf.p, 0);
-      allreduce_sum(ctx, p->pack_buf.p, static_cast<size_t>(p->n_pack) * kTileElems);
-      LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, p->pack_buf.p, 1);
-    } else {
-      allreduce_sum(ctx, p->H_tiles.p, p->H_tiles.n);
-    }
-    allreduce_sum(ctx, p->H_C.p, p->H_C.n);
-    allreduce_sum(ctx, p->g.p, p->g.n);
-    allreduce_sum(ctx, p->Hrx.p, p->Hrx.n);
-    allreduce_sum(ctx, p->Hrr.p, p->Hrr.n);
-    allreduce_sum(ctx, p->scal.p, 1);
+  if (ctx->world > 1 && p->p2p.active) {   // fused reduction over NVLink peer memory (p2p.cu): no pack / unpack, peers' tiles read in place
+    p2p_reduce(p);
+  } else if (ctx->world > 1) {   // ONE all-reduce per iteration over [non-zero tiles | corner | g | Schur rows | Schur diagonal | cost]
+    cudaStream_t st = ctx->stream;
+    double* buf = p->pack_buf.p;
+    if (p->n_pack > 0) LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, buf, 0);
+    struct Seg { double* ptr; size_t n; };
+    const Seg segs[5] = {{p->H_C.p, p->H_C.n}, {p->g.p, p->g.n}, {p->Hrx.p, p->Hrx.n}, {p->Hrr.p, p->Hrr.n}, {p->scal.p, 1}};
+    size_t off = static_cast<size_t>(p->n_pack) * kTileElems;
+    for (const Seg& s : segs) { if (s.n) LVI_CUDA(cudaMemcpyAsync(buf + off, s.ptr, s.n * sizeof(double), cudaMemcpyDeviceToDevice, st)); off += s.n; }
+    allreduce_sum(ctx, buf, off);
+    if (p->n_pack > 0) LVI_LAUNCH(ctx, pack_tiles_kernel, p->n_pack, 256, 0, p->H_tiles.p, p->pack_map.p, buf, 1);
+    off = static_cast<size_t>(p->n_pack) * kTileElems;
+    for (const Seg& s : segs) { if (s.n) LVI_CUDA(cudaMemcpyAsync(s.ptr, buf + off, s.n * sizeof(double), cudaMemcpyDeviceToDevice, st)); off += s.n; }
   }
 }
 static void trial_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active, bool inactive) {
