@@ -339,6 +339,25 @@ int lvi_associate_batch(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_s
                         const lvi_point_xyzit* scans_raw_d, int32_t W, int32_t H, double radius, int32_t k_per_ring,
                         int32_t time_step, lvi_surfel_point* out_d, int64_t cap, int64_t* n_out, int64_t* n_all);
 
+/* ---- (e) the map path sharded over the GPUs of a node --------------------------------------------------------------------- */
+/* SURVEY §8e collectives 1-2.  Every rank passes the map-frame scans of ITS time chunk (ranks = consecutive time chunks).  The voxel grid
+ * (min_b_ / div_b_) is that of the whole cloud (ncclAllReduce min / max), every leaf is built by the rank that owns its voxel-index range
+ * from ALL its points in cloud order (all-to-all of points), and the surfel planes of all ranks are gathered on every rank in ascending
+ * voxel-index order, so plane ids, planes and boxes equal those of lvi_voxel_build_batch + lvi_surfel_extract over the concatenated scans.
+ *   *out_map     : look-up map over the surfel leaves (what lvi_associate_* needs); lvi_voxel_export is not available on it
+ *   *out_surfels : all planes (lvi_surfel_count / lvi_surfel_export / lvi_associate_landmarks work as usual)
+ *   stats[4]     : (may be NULL) points sent to other ranks, points received, leaves and planes built by this rank
+ * With world == 1: lvi_voxel_build_batch + lvi_surfel_extract. */
+int lvi_map_build_sharded(lvi_ctx* ctx, const lvi_scan_batch* local_scans, const uint8_t* scan_keep, float leaf_size, int min_points,
+                          double eig_mult, double lambda, int min_leaf_points, float ransac_threshold, int min_inliers,
+                          lvi_voxel_map** out_map, lvi_surfel_set** out_surfels, int64_t* stats);
+/* lvi_associate_batch over every rank's own scans.  The every-`time_step`-th decimation runs over the associated points of ALL ranks in
+ * time order (ncclAllGather of the hit counts); the selected points of all ranks are gathered into out_d on every rank (capacity cap;
+ * out_d == NULL sizes: *n_out = selected points of all ranks, *n_all = associated points of all ranks). */
+int lvi_associate_sharded(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_surfel_set* s, const lvi_scan_batch* local_scans,
+                          const lvi_point_xyzit* scans_raw_d, int32_t W, int32_t H, double radius, int32_t k_per_ring, int32_t time_step,
+                          lvi_surfel_point* out_d, int64_t cap, int64_t* n_out, int64_t* n_all);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------------- */
 /* Solves A x = rhs through the band+arrow tile Cholesky used by lvi_problem_solve (tests only). A_dense is
  * [n x n] row-major symmetric positive definite, n = nb + nbo; within the first nb rows/cols entries with

@@ -135,7 +135,7 @@ ABI_SYMBOLS = [
     "lvi_undistort_d", "lvi_transform_scans", "lvi_transform_scans_d", "lvi_trajectory_evaluate", "lvi_trajectory_evaluate_full", "lvi_band_solve_dense",
     "lvi_scan_batch_undistort_d", "lvi_scan_batch_transform", "lvi_scan_batch_from_xyzi_d", "lvi_scan_batch_export_xyzi",
     "lvi_scan_batch_destroy", "lvi_scan_batch_num_points", "lvi_scan_batch_num_scans", "lvi_scan_batch_points_d",
-    "lvi_voxel_build_batch", "lvi_associate_batch",
+    "lvi_voxel_build_batch", "lvi_associate_batch", "lvi_map_build_sharded", "lvi_associate_sharded",
 ]
 
 
@@ -214,6 +214,8 @@ def load() -> C.CDLL:
     lib.lvi_scan_batch_points_d.restype = vp
     lib.lvi_voxel_build_batch.argtypes = [vp, vp, c_uint8_p, C.c_float, C.c_int, C.c_double, C.POINTER(vp)]
     lib.lvi_associate_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, vp, C.c_int64, c_int64_p, c_int64_p]
+    lib.lvi_associate_sharded.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, vp, C.c_int64, c_int64_p, c_int64_p]
+    lib.lvi_map_build_sharded.argtypes = [vp, vp, c_uint8_p, C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp), c_int64_p]
     lib.lvi_band_solve_dense.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     _lib = lib
     return lib

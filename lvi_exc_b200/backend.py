@@ -60,13 +60,25 @@ class CudaMapCloud:
 
 class CudaSurfelMap:
     def __init__(self, backend: "CudaBackend", cloud, leaf: float, lam: float, min_points=6, eig_mult=0.01, min_leaf_points=10,
-                 ransac_thr=0.05, min_inliers=20):
+                 ransac_thr=0.05, min_inliers=20, sharded=False):
         self.b = backend
         lib = backend.lib
         self.vmap = C.c_void_p()
         self.surfels = C.c_void_p()
+        self.shard_stats = None
         if isinstance(cloud, CudaScanBatch):
             cloud = CudaMapCloud(cloud, None)
+        if sharded:   # every rank passes the scans of its own time chunk: grid, leaves and planes are those of the whole cloud
+            assert isinstance(cloud, CudaMapCloud)
+            st = np.zeros(4, np.int64)
+            check(lib.lvi_map_build_sharded(backend.ctx, cloud.batch.h, ptr(cloud.keep), leaf, min_points, eig_mult, lam, min_leaf_points, ransac_thr,
+                                            min_inliers, C.byref(self.vmap), C.byref(self.surfels), ptr(st)))
+            self.shard_stats = dict(points_sent=int(st[0]), points_received=int(st[1]), leaves_built=int(st[2]), planes_built=int(st[3]))
+            self.num_leaves = lib.lvi_voxel_num_leaves(self.vmap)
+            self.num_planes = lib.lvi_surfel_count(self.surfels)
+            self.planes = self.export_planes()
+            self.planes_Pi = self.planes["Pi"]
+            return
         if isinstance(cloud, CudaMapCloud):
             check(lib.lvi_voxel_build_batch(backend.ctx, cloud.batch.h, ptr(cloud.keep), leaf, min_points, eig_mult, C.byref(self.vmap)))
         else:   # a PCL-shaped cloud (numpy / device tensor): the ABI's 32 B layout
@@ -283,6 +295,29 @@ class CudaBackend:
             check(self.lib.lvi_associate_d(self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H,
                                            radius, k, step, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
         n = n_out.value
+        self.last_n_all = n_all.value
+        out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
+        if n:
+            out[:] = od[:n * 64].cpu().numpy().view(SURFEL_POINT_DTYPE)
+        return out
+
+    def build_surfel_map_sharded(self, local_cloud, leaf, lam):
+        return CudaSurfelMap(self, local_cloud, leaf, lam, sharded=True)
+
+    def associate_sharded(self, smap: CudaSurfelMap, local_scans_in_map: CudaScanBatch, local_scans_raw, radius, k, step):
+        """association of every rank's own scans against the gathered planes; returns the decimated points of ALL ranks (time order) on every rank"""
+        torch = _torch()
+        r = self.to_device(local_scans_raw, cache=True).contiguous()
+        S, H, W = r.shape[0], r.shape[1], r.shape[2]
+        assert local_scans_in_map.shape == (S, H, W)
+        n_out, n_all = C.c_int64(0), C.c_int64(0)
+        torch.cuda.synchronize(self.device)
+        args = (self.ctx, smap.vmap, smap.surfels, local_scans_in_map.h, C.c_void_p(r.data_ptr()), W, H, radius, k, step)
+        check(self.lib.lvi_associate_sharded(*args, None, 0, C.byref(n_out), C.byref(n_all)))
+        n = n_out.value
+        od = torch.empty(max(n, 1) * 64, dtype=torch.uint8, device=r.device)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.lvi_associate_sharded(*args, C.c_void_p(od.data_ptr()), n, C.byref(n_out), C.byref(n_all)))
         self.last_n_all = n_all.value
         out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
         if n:

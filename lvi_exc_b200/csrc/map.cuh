@@ -64,6 +64,11 @@ constexpr int kProducerChunk = 256 * 8;   // points one 256-thread CTA produces 
 lvi_scan_batch* batch_alloc(lvi_ctx* ctx, int32_t n_scans, int64_t pts_per_scan, int64_t n);
 lvi_scan_batch* batch_import_xyzi(lvi_ctx* ctx, const void* xyz_d, size_t stride, int64_t n, int64_t pts_per_scan);
 // voxel.cu
+struct VoxelBuildOptions { const GridParams* forced_grid_d = nullptr; bool idx_from_w = false; };
+lvi_voxel_map* voxel_build_core(lvi_ctx* ctx, const lvi_scan_batch* b, const uint8_t* scan_keep, float leaf, int min_points, double eig_mult, const VoxelBuildOptions& opt);
+// grid of the cloud selected by scan_base from the per-scan min / max slots of a batch (device): mm[6] ordered ints, then the grid
+void voxel_local_minmax(lvi_ctx* ctx, const lvi_scan_batch* b, const int* scan_base_d, int* mm_d);
+void voxel_grid_from_minmax(lvi_ctx* ctx, const int* mm_d, float leaf, GridParams* grid_d);
 lvi_voxel_map* voxel_build_from_batch(lvi_ctx* ctx, const lvi_scan_batch* b, const uint8_t* scan_keep, float leaf, int min_points, double eig_mult);
 
 }  // namespace lvi
@@ -102,6 +107,7 @@ struct lvi_voxel_map {
   lvi::DBuf<double> leaf_evecs;     // [L*9]
   lvi::DBuf<double> leaf_icov;      // [L*9]
   lvi::DBuf<int32_t> cell2leaf;     // dense lookup or empty
+  bool lookup_only = false;         // sharded build: keys of the surfel leaves of ALL ranks (leaf l = plane l), no statistics / point lists
 };
 
 struct lvi_surfel_set {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kGatherThreads) voxel_gather_kernel(const floa
                                                                       const unsigned long long* __restrict__ run_key, const int32_t* __restrict__ run_off,
                                                                       const int32_t* __restrict__ leaf_of_run, const int32_t* __restrict__ tile_run0,
                                                                       const int32_t* __restrict__ leaf_start, int n_runs, int n_out,
-                                                                      float4* __restrict__ out, double* __restrict__ partial) {
+                                                                      float4* __restrict__ out, double* __restrict__ partial, int idx_from_w) {
   __shared__ int s_off[kGatherTile + 1];
   __shared__ uint32_t s_src[kGatherTile];
   __shared__ float s_x[kGatherTile], s_y[kGatherTile], s_z[kGatherTile];
@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kGatherThreads) voxel_gather_kernel(const floa
     const uint32_t sp = s_src[lo] + static_cast<uint32_t>(o - s_off[lo]);
     const float4 p = __ldcs(pts + sp);
     int cidx = static_cast<int>(sp);   // index in the cloud the map is built from (Leaf::pointList_ consumers index by it)
-    if (scan_base) { const uint32_t sc = sp / static_cast<uint32_t>(pts_per_scan); cidx = scan_base[sc] + static_cast<int>(sp - sc * static_cast<uint32_t>(pts_per_scan)); }
+    if (idx_from_w) cidx = __float_as_int(p.w);   // sharded build: the point carries its index in the global map cloud
+    else if (scan_base) { const uint32_t sc = sp / static_cast<uint32_t>(pts_per_scan); cidx = scan_base[sc] + static_cast<int>(sp - sc * static_cast<uint32_t>(pts_per_scan)); }
     __stcs(out + o, make_float4(p.x, p.y, p.z, __int_as_float(cidx)));
     s_x[q] = p.x; s_y[q] = p.y; s_z[q] = p.z;
     const double x = p.x, y = p.y, z = p.z;
@@ -399,6 +400,13 @@ __global__ void __launch_bounds__(256) voxel_cell2leaf_kernel(const int32_t* __r
 // ------------------------------------------------------------------------------------------------------------------
 // scan_keep (host, optional): which scans of the batch make up the map cloud
 lvi_voxel_map* voxel_build_from_batch(lvi_ctx* ctx, const lvi_scan_batch* b, const uint8_t* scan_keep, float leaf, int min_points, double eig_mult) {
+  return voxel_build_core(ctx, b, scan_keep, leaf, min_points, eig_mult, VoxelBuildOptions{});
+}
+
+// opt.forced_grid_d: grid of a map this cloud is a PART of (sharded build: min_b_ / div_b_ must be those of the whole cloud);
+// opt.idx_from_w: the w component of every point is its index in the whole map cloud
+lvi_voxel_map* voxel_build_core(lvi_ctx* ctx, const lvi_scan_batch* b, const uint8_t* scan_keep, float leaf, int min_points, double eig_mult,
+                                const VoxelBuildOptions& opt) {
   const int64_t n = b->n;
   LVI_REQUIRE(n > 0 && n < 2147483647LL, LVI_ERR_INVALID, "lvi_voxel_build: n_points must be in (0, 2^31)");
   LVI_REQUIRE(leaf > 0, LVI_ERR_INVALID, "lvi_voxel_build: leaf_size must be positive");
@@ -423,8 +431,12 @@ lvi_voxel_map* voxel_build_from_batch(lvi_ctx* ctx, const lvi_scan_batch* b, con
   m->n_points = n_cloud;
   DBuf<int> mm(8);
   m->grid_d.alloc(1);
-  LVI_LAUNCH(ctx, voxel_reduce_minmax_kernel, 1, 256, 0, b->mm.p, scan_base.p, b->n_scans, mm.p);
-  LVI_LAUNCH(ctx, voxel_grid_params_kernel, 1, 1, 0, mm.p, leaf, m->grid_d.p);
+  if (opt.forced_grid_d) {
+    LVI_CUDA(cudaMemcpyAsync(m->grid_d.p, opt.forced_grid_d, sizeof(GridParams), cudaMemcpyDeviceToDevice, st));
+  } else {
+    LVI_LAUNCH(ctx, voxel_reduce_minmax_kernel, 1, 256, 0, b->mm.p, scan_base.p, b->n_scans, mm.p);
+    LVI_LAUNCH(ctx, voxel_grid_params_kernel, 1, 1, 0, mm.p, leaf, m->grid_d.p);
+  }
   // run records: at most one per finite point (+ one per tile cut); 12 B each, twice (sort double buffer)
   const size_t cap = static_cast<size_t>(n) + static_cast<size_t>((n + kRunTile - 1) / kRunTile) + 1;
   DBuf<unsigned long long> rk(cap), rk2(cap);
@@ -476,7 +488,7 @@ lvi_voxel_map* voxel_build_from_batch(lvi_ctx* ctx, const lvi_scan_batch* b, con
   m->pts_sorted.alloc(static_cast<size_t>(std::max(n_out, 1)));
   LVI_LAUNCH(ctx, voxel_tile_run0_kernel, (R + 255) / 256, 256, 0, run_off.p, rl2.p, R, tile_run0.p);
   LVI_LAUNCH(ctx, voxel_gather_kernel, n_gt, kGatherThreads, 0, b->pts.p, b->pts_per_scan, scan_base.p, rk2.p, run_off.p, leaf_of_run.p, tile_run0.p,
-             m->leaf_start.p, R, n_out, m->pts_sorted.p, partial.p);
+             m->leaf_start.p, R, n_out, m->pts_sorted.p, partial.p, opt.idx_from_w ? 1 : 0);
   m->leaf_npts.alloc(L); m->leaf_mean.alloc(3 * L); m->leaf_cov.alloc(9 * L); m->leaf_evals.alloc(3 * L); m->leaf_evecs.alloc(9 * L); m->leaf_icov.alloc(9 * L);
   if (L) {
     DBuf<double> leaf_sums(static_cast<size_t>(L) * kRunSums);
@@ -491,6 +503,13 @@ lvi_voxel_map* voxel_build_from_batch(lvi_ctx* ctx, const lvi_scan_batch* b, con
     LVI_CUDA(cudaStreamSynchronize(st));  // leaf_sums is freed on return
   }
   return m.release();
+}
+
+void voxel_local_minmax(lvi_ctx* ctx, const lvi_scan_batch* b, const int* scan_base_d, int* mm_d) {
+  LVI_LAUNCH(ctx, voxel_reduce_minmax_kernel, 1, 256, 0, b->mm.p, scan_base_d, b->n_scans, mm_d);
+}
+void voxel_grid_from_minmax(lvi_ctx* ctx, const int* mm_d, float leaf, GridParams* grid_d) {
+  LVI_LAUNCH(ctx, voxel_grid_params_kernel, 1, 1, 0, mm_d, leaf, grid_d);
 }
 
 static lvi_voxel_map* build_from_device(lvi_ctx* ctx, const void* xyz_d, size_t stride, int64_t n, float leaf, int min_points, double eig_mult) {
@@ -551,6 +570,7 @@ int lvi_voxel_export(lvi_ctx* ctx, const lvi_voxel_map* m, int64_t* keys, int32_
                      double* evecs, double* icov, int64_t* leaf_start, int32_t* point_index) {
   return guarded([&] {
     LVI_REQUIRE(ctx && m, LVI_ERR_INVALID, "lvi_voxel_export: null argument");
+    LVI_REQUIRE(!m->lookup_only, LVI_ERR_INVALID, "lvi_voxel_export: the look-up map of a sharded build holds no leaf statistics");
     activate(ctx);
     cudaStream_t st = ctx->stream;
     const size_t L = static_cast<size_t>(m->n_leaves);

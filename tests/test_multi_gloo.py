@@ -72,3 +72,71 @@ def test_shard_ranges_partition_every_table():
             edges = [(n * r // world, n * (r + 1) // world) for r in range(world)]
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+
+
+# ---- the sharded map path (csrc/shard.cu): its bookkeeping, restated in lvi_exc_b200/shardplan.py, at world size 2 over gloo ----------------
+def _map_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lvi_exc_b200 import shardplan
+        rng = np.random.default_rng(7)
+        n = 20000
+        pts_all = (rng.random((n, 3)) * np.array([12.0, 9.0, 3.5]) - np.array([6.0, 4.5, 1.0])).astype(np.float32)   # the same cloud on every rank
+        lo, hi = n * rank // world, n * (rank + 1) // world     # ranks = consecutive time chunks
+        pts = pts_all[lo:hi]
+        inv = np.float32(1.0) / np.float32(0.5)
+        # collective 1: grid of the WHOLE cloud from all-reduced min / max
+        mn, mx = torch.from_numpy(pts.min(0).copy()), torch.from_numpy(pts.max(0).copy())
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        min_b = np.floor(mn.numpy() * inv).astype(np.int64)
+        div_b = np.floor(mx.numpy() * inv).astype(np.int64) - min_b + 1
+        ijk = (np.floor(pts * inv) - min_b.astype(np.float32)).astype(np.int64)
+        keys = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+        ncell = int(div_b.prod())
+        # ownership ranges from the all-reduced histogram
+        hist = torch.from_numpy(shardplan.key_histogram(keys, ncell).astype(np.int64))
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        split = shardplan.balanced_splitters(hist.numpy().astype(np.uint64), ncell, world)
+        owner = shardplan.owner_of(keys, split)
+        order = np.argsort(owner, kind="stable")
+        send = [dict(xyz=pts[order][owner[order] == q], idx=(lo + order[owner[order] == q])) for q in range(world)]
+        got = [None] * world
+        dist.all_gather_object(got, send)                       # the all-to-all of points
+        mine_xyz = np.concatenate([got[q][rank]["xyz"] for q in range(world)])   # rank order = time order
+        mine_idx = np.concatenate([got[q][rank]["idx"] for q in range(world)])
+        # decimation bookkeeping: random hit counts per rank
+        tots = [137 + 59 * q for q in range(world)]
+        first, count = shardplan.decimation_plan(tots, 10)
+        off = sum(tots[:rank])
+        kept = [off + first[rank] + 10 * j for j in range(count[rank])]
+        np.savez(os.path.join(out_dir, f"m{rank}.npz"), xyz=mine_xyz, idx=mine_idx, split=split, min_b=min_b, div_b=div_b, kept=np.array(kept), tots=np.array(tots))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_map_bookkeeping_world2(tmp_path):
+    world = 2
+    mp.spawn(_map_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    n = 20000
+    pts = (rng.random((n, 3)) * np.array([12.0, 9.0, 3.5]) - np.array([6.0, 4.5, 1.0])).astype(np.float32)
+    inv = np.float32(2.0)
+    min_b = np.floor(pts.min(0) * inv).astype(np.int64)
+    div_b = np.floor(pts.max(0) * inv).astype(np.int64) - min_b + 1
+    ijk = (np.floor(pts * inv) - min_b.astype(np.float32)).astype(np.int64)
+    keys = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+    r = [np.load(tmp_path / f"m{q}.npz") for q in range(world)]
+    assert all(np.array_equal(x["min_b"], min_b) and np.array_equal(x["div_b"], div_b) for x in r)      # the grid of the whole cloud on every rank
+    assert np.array_equal(r[0]["split"], r[1]["split"])
+    split = r[0]["split"]
+    seen = 0
+    for q in range(world):
+        own = np.nonzero((keys >= split[q]) & (keys < split[q + 1]))[0]                                 # single-process: the owner's points in cloud order
+        assert np.array_equal(r[q]["idx"], own) and np.array_equal(r[q]["xyz"], pts[own])               # ... arrive in exactly that order
+        assert 0.35 * n < len(own) < 0.65 * n                                                           # balanced ranges
+        seen += len(own)
+    assert seen == n
+    tots = r[0]["tots"]
+    kept = np.concatenate([x["kept"] for x in r])
+    assert np.array_equal(kept, np.arange(0, tots.sum(), 10))                                           # the global every-10th decimation
