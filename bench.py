@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--duration", type=float, default=60.0, help="seconds of synthetic data (60 = BASELINE configs[1])")
     ap.add_argument("--cpu-steps", type=int, default=3, help="LM iterations of the CPU oracle in the cpu_baseline leg (full problem, N=1 only)")
-    ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 = the headline workload; C3 = 300 s / large-map roofline run of the map path + one J^T J build")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"], help="C2 = the headline workload; C3 = 300 s / large-map roofline run of the map path + one J^T J build; "
+                    "C4 = 64-beam 20 Hz sequence, map path sharded over the GPUs + one sharded J^T J build; C5 = C2 with the degenerate (planar, low excitation) trajectory")
     ap.add_argument("--leaves", type=int, default=150000, help="C3: occupied 0.5 m leaves of the synthetic map (150000 x 576 points are all surfels; 5000000 x 17 = "
                     "the ~5 M-leaf variant, which the reference's planarity test rejects as surfels, DESIGN.md)")
     ap.add_argument("--no-calibration", action="store_true", help="skip the full S0-S5 stage sequence (extrinsic error report)")
@@ -113,7 +114,8 @@ def host_threads() -> int:
 
 def workload_config(args, pd, world: int, num_residuals: int, tangent_dims: int) -> dict:
     """`config` of the JSON line: identical for both arms (it describes the workload and how the GPU arm treats it)"""
-    return {"workload": WORKLOAD, "seconds": args.duration, "residual_blocks": pd_sizes(pd), "num_residuals": int(num_residuals),
+    wl = WORKLOAD if args.config != "C5" else WORKLOAD.replace("C2:", "C5: degenerate motion (planar, low excitation),")
+    return {"workload": wl, "seconds": args.duration, "residual_blocks": pd_sizes(pd), "num_residuals": int(num_residuals),
             "tangent_dims": int(tangent_dims),
             "l2_policy": "inputs larger than L2: the normal-equation tile stores H + A (416 MB at C2) exceed the 126 MB L2, no flush needed",
             "parallelism": f"dp{world}: residual tables sharded by time chunk, normal equations summed by one kernel over NVLink peer memory (ncclAllReduce of the packed tiles where IPC mapping is unavailable)"}
@@ -129,7 +131,7 @@ def run_reference(args, rank: int):
     from tests import oracle_binding as ob           # bench.py's reference arm is one of the places allowed to run oracle/
     from tests.oracle_backend import OracleBackend
     cores = ob.set_num_threads(host_threads())
-    seq = synth.make_sequence(synth.default_config(duration=args.duration))
+    seq = synth.make_sequence(synth.default_config(duration=args.duration, degenerate=1 if args.config == "C5" else 0))
     pd, info = workload.lvi_stage_problem(seq, OracleBackend())
     tol0 = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
     saved = pd.clone_params()
@@ -159,7 +161,7 @@ def oracle_comparison(args, res) -> dict:
     """extrinsics of the GPU stage sequence against the CPU oracle's on the same sequence.  The oracle needs minutes at C2, so its result
     is a committed fixture (tests/golden/oracle_calibration_c2.json, written by tools/oracle_calibration.py); the north star's tolerance
     is 1e-4 rad / 1e-3 m."""
-    f = ROOT / "tests" / "golden" / "oracle_calibration_c2.json"
+    f = ROOT / "tests" / "golden" / ("oracle_calibration_c5.json" if args.config == "C5" else "oracle_calibration_c2.json")
     if args.duration != 60.0 or not f.exists():
         return {"extrinsic_err_vs_oracle": None}
     from lvi_exc_b200.problem import quat_angle
@@ -196,6 +198,10 @@ def kernel_rooflines(times: dict, peaks: dict, peak_kind: str, n_points: int, n_
         ("voxel_gather_kernel", ("voxel_gather_kernel",), 24 * n_points, "12 B read + 12 B written per point"),
         ("assoc_hit_kernel", ("assoc_hit_kernel",), 16 * n_points, "12 B read + 4 B written per point"),
         ("association (all kernels)", ("assoc_",), 12 * n_points + 84 * n_selected, "12 B read per point + 20 B read / 64 B written per selected point"),
+        ("jacobian_kernel<RT_SURFEL>", ("jacobian_kernel<RT_SURFEL>",), 8 * 56 * n_res.get("surfel", 0) + JAC_BYTES["surfel"] * n_res.get("surfel", 0) // 4, "record + plane read, fp64 J block (54 + r, padded) written per residual"),
+        ("jacobian_kernel<RT_CAM>", ("jacobian_kernel<RT_CAM>",), 8 * 112 * n_res.get("cam", 0) + 64 * n_res.get("cam", 0), "record read, fp64 J block (2 x 55 + r, padded) written per residual"),
+        ("jacobian_kernel<RT_ACCEL>", ("jacobian_kernel<RT_ACCEL>",), 8 * 90 * n_res.get("accel", 0) + 40 * n_res.get("accel", 0), "record read, fp64 J block (3 x 29 + r) written per residual"),
+        ("jacobian_kernel<RT_GYRO>", ("jacobian_kernel<RT_GYRO>",), 8 * 48 * n_res.get("gyro", 0) + 40 * n_res.get("gyro", 0), "record read, fp64 J block (3 x 15 + r) written per residual"),
         ("linearize_kernel<RT_SURFEL>", ("linearize_kernel<RT_SURFEL>",), JAC_BYTES["surfel"] * n_res.get("surfel", 0), "record + plane + 4 r p J bytes + 4 r per residual"),
         ("linearize_kernel<RT_CAM>", ("linearize_kernel<RT_CAM>",), JAC_BYTES["cam"] * n_res.get("cam", 0), "record + 4 r p J bytes + 4 r per residual"),
         ("linearize_kernel<RT_ACCEL>", ("linearize_kernel<RT_ACCEL>",), JAC_BYTES["accel"] * n_res.get("accel", 0), "record + 4 r p J bytes + 4 r per residual"),
@@ -306,12 +312,126 @@ def run_c3(args, rank: int, local_rank: int, world: int):
                       "knots": mgr.n_knots, "residual_blocks": n_res, "l2_policy": "inputs larger than L2 (2.8 GB of raw scans, 1.4 GB packed batch)"},
            "kernel_ms_per_step": map_kernel_ms, "host_wall_ms_per_step": 1e3 * wall / args.steps, "generator_s": gen_s,
            "kernels_ms": {k: v[1] / args.steps for k, v in sorted(map_times.items(), key=lambda kv: -kv[1][1])},
-           "linearize_ms": {k: v[1] / args.steps for k, v in sorted(lin_times.items(), key=lambda kv: -kv[1][1]) if k.startswith("linearize")},
+           "linearize_ms": {k: v[1] / args.steps for k, v in sorted(lin_times.items(), key=lambda kv: -kv[1][1]) if k.startswith(("linearize", "jacobian", "gather"))},
            "phases_ms": {n: float(ms[i]) for i, n in enumerate(["linearize", "build_system", "band_factor", "corner_backsolve", "trial_cost"])},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": {**top, "kernels": roof},
            "e2e": {"value": n_points * args.steps / wall, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(len(sp) * 64),
                    "note": "raw scans resident in HBM (uploaded once); every pass downloads the associated points"}}
     print(json.dumps(out), flush=True)
+
+
+def run_c4(args, rank: int, local_rank: int, world: int):
+    """BASELINE configs[3]: 64-beam LiDAR at 20 Hz (2.56 M points/s), the map path sharded over the GPUs of the node -- rank r holds the scans of the
+    r-th time chunk -- plus ONE sharded J^T J build of the S1-type problem (normal equations reduced over NVLink peer memory).  Total work is
+    fixed (120 s by default): strong scaling."""
+    import torch
+    from lvi_exc_b200 import pipeline, synth, workload
+    from lvi_exc_b200.backend import CudaProblem
+    from lvi_exc_b200.dist import make_backend, shard_range
+    backend, dist, rank, world = make_backend()
+    dev = f"cuda:{local_rank}"
+    duration = 120.0 if args.duration == 60.0 else args.duration
+    cfg = synth.default_config(duration=duration, rings=64, az_steps=2000, scan_rate=20.0)
+    times = synth.scan_times(cfg)
+    S, H, W = len(times), cfg.rings, cfg.az_steps
+    lo, hi = shard_range(S, rank, world)
+    Sl = hi - lo
+    t0 = time.perf_counter()
+    raw_d = torch.empty((Sl, H, W, 8), dtype=torch.float32, device=dev)
+    chunk = 100
+    for c0 in range(0, Sl, chunk):     # this rank's time chunk only: generated on the host in pieces, uploaded once, resident from here on
+        n = min(chunk, Sl - c0)
+        raw = synth.make_scans(cfg, lo + c0, n)
+        raw_d[c0:c0 + n] = torch.from_numpy(raw.view(np.float32).reshape(n, H, W, 8)).to(dev)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+
+    class Seq:
+        pass
+    seq = Seq()
+    seq.cfg, seq.scan_times, seq.gt = cfg, times, synth.gt_extrinsics()
+    seq.map_time, seq.end_time = float(times[0]), float(times[-1] + 1.0 / cfg.scan_rate)
+    seq.imu_t, seq.gyro, seq.accel = synth.make_imu(cfg)
+    pc = pipeline.PipelineConfig()
+    mgr = workload.make_manager(seq, pc)
+    mgr.calib.q_LtoI, mgr.calib.p_LinI = seq.gt["q_LtoI"], seq.gt["p_LinI"]
+
+    def barrier():
+        torch.cuda.synchronize(); backend.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def one_pass():
+        batch = backend.undistort(mgr._base(), raw_d, seq.map_time, True)
+        smap = backend.build_surfel_map_sharded(backend.map_cloud(batch), pc.ndt_resolution, pc.plane_lambda_refine)
+        sp = backend.associate_sharded(smap, batch, raw_d, pc.associated_radius, pc.k_per_ring, pc.time_downsample, total_points=S * H * W)
+        return batch, smap, sp
+
+    for _ in range(max(args.warmup, 3)):
+        batch, smap, sp = one_pass()
+        n_planes, n_all, stats = smap.num_planes, backend.last_n_all, smap.shard_stats
+        smap.close(); batch.close()
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.7)
+    backend.kernel_timing(True); backend.kernel_times()
+    l0 = backend.launches
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch, smap, sp = one_pass()
+        if _ + 1 < args.steps:
+            smap.close(); batch.close()
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    map_times = backend.kernel_times()
+    launches = backend.launches - l0
+    clocks = sampler.stop()
+    # ---- one sharded Jacobian / J^T J build of the S1-type problem (gyro + accel + surfel), identical on every rank
+    pd = workload.make_manager(seq, pc).problem_surfel(smap.planes_Pi, sp.copy(), seq.map_time)
+    prob = CudaProblem(backend, pd)
+    prob.bench_iterations(3)
+    backend.kernel_times()
+    barrier()
+    ms = prob.bench_iterations(args.steps)
+    ms = np.array([max_over_ranks(float(v)) for v in ms])
+    lin_times = backend.kernel_times()
+    backend.kernel_timing(False)
+    n_res = {k: len(pd.tables[k][0]) for k in ("gyro", "accel", "surfel") if k in pd.tables}
+    prob.close(); smap.close(); batch.close()
+    n_points = S * H * W
+    n_local = Sl * H * W
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        roof = finish_rooflines(kernel_rooflines(map_times, peaks, peak_kind, n_local, stats["leaves_built"] if stats else 0, n_all // world, {}), args.steps)
+        top = max(roof, key=lambda e: e["ms_per_pass"] if "all kernels" not in e["kernel"] else 0.0) if roof else {}
+        out = {"metric": "map path points/s (de-skew + sharded NDT voxel build + surfel extraction + association) on a 64-beam 20 Hz synthetic sequence",
+               "value": n_points * args.steps / wall, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 coordinates / f64 statistics",
+               "data": "synthetic",
+               "config": {"workload": f"C4: {duration:g} s of a 64-beam LiDAR at 20 Hz + 200 Hz IMU, map path sharded over {world} GPU(s) by time chunk, one sharded J^T J build",
+                          "points": n_points, "scans": S, "points_per_rank": n_local, "surfels": int(n_planes), "associated_points": int(n_all), "knots": mgr.n_knots,
+                          "residual_blocks": n_res, "parallelism": f"dp{world}: scans by time chunk; grid by ncclAllReduce(min/max), leaves owned by voxel-index range "
+                          "(all-to-all of points), planes gathered by ncclBroadcast, decimation by ncclAllGather of hit counts; J^T J reduced over NVLink peer memory",
+                          "l2_policy": f"inputs larger than L2 ({n_local * 32 / 1e9:.1f} GB of raw scans per rank)"},
+               "rank0_shard": stats, "host_wall_ms_per_step": 1e3 * wall / args.steps, "generator_s": gen_s,
+               "kernels_ms": {k: v[1] / args.steps for k, v in sorted(map_times.items(), key=lambda kv: -kv[1][1])},
+               "linearize_ms": {k: v[1] / args.steps for k, v in sorted(lin_times.items(), key=lambda kv: -kv[1][1]) if k.startswith(("jacobian", "gather", "p2p"))},
+               "phases_ms": {n: float(ms[i]) for i, n in enumerate(["linearize", "build_system", "band_factor", "corner_backsolve", "trial_cost"])},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": {**top, "kernels": roof},
+               "e2e": {"value": n_points * args.steps / wall, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(len(sp) * 64),
+                       "note": "raw scans resident in HBM (uploaded once per rank); every pass downloads the associated points of all ranks on every rank"}}
+        print(json.dumps(out), flush=True)
+    barrier()
+    backend.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -324,6 +444,9 @@ def main():
         return
     if args.config == "C3":
         run_c3(args, rank, local_rank, world)
+        return
+    if args.config == "C4":
+        run_c4(args, rank, local_rank, world)
         return
 
     import torch
@@ -362,7 +485,7 @@ def main():
         return float(t.item())
 
     # ---- workload: identical on every rank (deterministic generator); the library shards the residual tables by time chunk
-    seq = synth.make_sequence(synth.default_config(duration=args.duration))
+    seq = synth.make_sequence(synth.default_config(duration=args.duration, degenerate=1 if args.config == "C5" else 0))
     pd, info = workload.lvi_stage_problem(seq, backend)
     saved = pd.clone_params()
     tol0 = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)

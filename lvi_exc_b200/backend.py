@@ -221,6 +221,21 @@ class CudaBackend:
             out[name] = (int(cnt), float(ms))
         return out
 
+    def _download_records(self, dev_bytes, n: int, dtype) -> np.ndarray:
+        """n records of `dtype` from a device byte tensor through a pinned staging buffer that is kept (and grown) across calls; the
+        returned array is a view of that buffer, valid until the next download"""
+        torch = _torch()
+        nbytes = n * dtype.itemsize
+        if nbytes == 0:
+            return np.zeros(0, dtype=dtype)
+        pin = getattr(self, "_pinned", None)
+        if pin is None or pin.numel() < nbytes:
+            pin = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self._pinned = pin
+        pin[:nbytes].copy_(dev_bytes[:nbytes], non_blocking=True)
+        torch.cuda.synchronize(self.device)
+        return pin[:nbytes].numpy().view(dtype)
+
     # ---- device-memory helpers (torch = allocator only) ------------------------------------------------------
     def to_device(self, a, cache: bool = False):
         """numpy -> device tensor; `cache=True` keeps the copy resident across calls (the raw scans are uploaded once)"""
@@ -294,18 +309,15 @@ class CudaBackend:
             torch.cuda.synchronize(self.device)
             check(self.lib.lvi_associate_d(self.ctx, smap.vmap, smap.surfels, C.c_void_p(m.data_ptr()), m.shape[-1] * 4, C.c_void_p(r.data_ptr()), S, W, H,
                                            radius, k, step, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
-        n = n_out.value
         self.last_n_all = n_all.value
-        out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
-        if n:
-            out[:] = od[:n * 64].cpu().numpy().view(SURFEL_POINT_DTYPE)
-        return out
+        return self._download_records(od, n_out.value, SURFEL_POINT_DTYPE).copy()   # callers keep the points across associations
 
     def build_surfel_map_sharded(self, local_cloud, leaf, lam):
         return CudaSurfelMap(self, local_cloud, leaf, lam, sharded=True)
 
-    def associate_sharded(self, smap: CudaSurfelMap, local_scans_in_map: CudaScanBatch, local_scans_raw, radius, k, step):
-        """association of every rank's own scans against the gathered planes; returns the decimated points of ALL ranks (time order) on every rank"""
+    def associate_sharded(self, smap: CudaSurfelMap, local_scans_in_map: CudaScanBatch, local_scans_raw, radius, k, step, total_points=None):
+        """association of every rank's own scans against the gathered planes; returns the decimated points of ALL ranks (time order) on every
+        rank.  total_points (points of all ranks) bounds the output so that one call suffices; without it a sizing call runs first."""
         torch = _torch()
         r = self.to_device(local_scans_raw, cache=True).contiguous()
         S, H, W = r.shape[0], r.shape[1], r.shape[2]
@@ -313,16 +325,16 @@ class CudaBackend:
         n_out, n_all = C.c_int64(0), C.c_int64(0)
         torch.cuda.synchronize(self.device)
         args = (self.ctx, smap.vmap, smap.surfels, local_scans_in_map.h, C.c_void_p(r.data_ptr()), W, H, radius, k, step)
-        check(self.lib.lvi_associate_sharded(*args, None, 0, C.byref(n_out), C.byref(n_all)))
-        n = n_out.value
-        od = torch.empty(max(n, 1) * 64, dtype=torch.uint8, device=r.device)
+        if total_points is None:
+            check(self.lib.lvi_associate_sharded(*args, None, 0, C.byref(n_out), C.byref(n_all)))
+            cap = max(n_out.value, 1)
+        else:
+            cap = total_points // step + self.world + 1
+        od = torch.empty(cap * 64, dtype=torch.uint8, device=r.device)
         torch.cuda.synchronize(self.device)
-        check(self.lib.lvi_associate_sharded(*args, C.c_void_p(od.data_ptr()), n, C.byref(n_out), C.byref(n_all)))
+        check(self.lib.lvi_associate_sharded(*args, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
         self.last_n_all = n_all.value
-        out = np.zeros(n, dtype=SURFEL_POINT_DTYPE)
-        if n:
-            out[:] = od[:n * 64].cpu().numpy().view(SURFEL_POINT_DTYPE)
-        return out
+        return self._download_records(od, n_out.value, SURFEL_POINT_DTYPE)
 
     def transform(self, scans_xyzi, poses):
         torch = _torch()
