@@ -315,7 +315,7 @@ class CudaBackend:
     def build_surfel_map_sharded(self, local_cloud, leaf, lam):
         return CudaSurfelMap(self, local_cloud, leaf, lam, sharded=True)
 
-    def associate_sharded(self, smap: CudaSurfelMap, local_scans_in_map: CudaScanBatch, local_scans_raw, radius, k, step, total_points=None):
+    def associate_sharded(self, smap: CudaSurfelMap, local_scans_in_map: CudaScanBatch, local_scans_raw, radius, k, step, total_points=None, download=True):
         """association of every rank's own scans against the gathered planes; returns the decimated points of ALL ranks (time order) on every
         rank.  total_points (points of all ranks) bounds the output so that one call suffices; without it a sizing call runs first."""
         torch = _torch()
@@ -334,6 +334,8 @@ class CudaBackend:
         torch.cuda.synchronize(self.device)
         check(self.lib.lvi_associate_sharded(*args, C.c_void_p(od.data_ptr()), cap, C.byref(n_out), C.byref(n_all)))
         self.last_n_all = n_all.value
+        if not download:   # the points stay in HBM (device tensor of 64-byte records, all ranks' points on every rank)
+            return od[:n_out.value * 64]
         return self._download_records(od, n_out.value, SURFEL_POINT_DTYPE)
 
     def transform(self, scans_xyzi, poses):

@@ -52,13 +52,9 @@ __global__ void p2p_wait_kernel(const void* base, int world, int slot, unsigned 
 }
 
 // flagged tile units are cleared (split tiles accumulate with atomics), the small part is cleared whole, the static tile flags are re-installed
-__global__ void __launch_bounds__(256) p2p_clear_kernel(unsigned char* __restrict__ flags, const unsigned char* __restrict__ tile_flags, double* __restrict__ data,
-                                                        int n_tile_units, int n_units) {
-  const int u = blockIdx.x;
-  const bool tile = u < n_tile_units;
-  const unsigned char f = tile ? tile_flags[u] : 0;
-  if (threadIdx.x == 0) flags[u] = f;
-  if (tile && !f) return;
+__global__ void __launch_bounds__(256) p2p_clear_kernel(unsigned char* __restrict__ flags, const int* __restrict__ own_list, int n_tile_units, double* __restrict__ data) {
+  const int u = own_list[blockIdx.x];   // the tile units this rank writes, then every small unit
+  if (threadIdx.x == 0) flags[u] = u < n_tile_units ? 1 : 0;
   double2* d = reinterpret_cast<double2*>(data + static_cast<size_t>(u) * kUnit);
   for (int e = threadIdx.x; e < kUnit / 2; e += 256) d[e] = make_double2(0.0, 0.0);
 }
@@ -76,8 +72,9 @@ struct P2PView {
   int world, rank;
   size_t off_flags, off_data;
   int n_tile_units, n_units;
-  const int* unit_list;      // units this kernel visits (structurally non-zero tiles + every small unit)
+  const int* unit_list;      // units this kernel visits (tiles some rank writes + every small unit)
   int n_list;
+  const unsigned char* tile_flags_all;   // [world][n_tile_units] every rank's static tile flags (local copy, gathered once per problem)
   double* tiles_out;         // private tile store
   double* small_out;         // private contiguous copy of the small part
   unsigned epoch;
@@ -97,7 +94,9 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(P2PView V) {
   if (s_ok) {
     for (int it = blockIdx.x; it < V.n_list; it += gridDim.x) {
       const int u = V.unit_list[it];
-      if (tid < V.world) s_flag[tid] = static_cast<const unsigned char*>(V.peer[tid])[V.off_flags + u];
+      if (tid < V.world)   // tile units: the local copy of everybody's static flags; small units: the flag the peer computed after its gather
+        s_flag[tid] = u < V.n_tile_units ? V.tile_flags_all[static_cast<size_t>(tid) * V.n_tile_units + u]
+                                         : static_cast<const unsigned char*>(V.peer[tid])[V.off_flags + u];
       __syncthreads();
       double2 a0 = make_double2(0.0, 0.0), a1 = a0;
       for (int q = 0; q < V.world; ++q) {   // rank order on every rank: bitwise identical sums
@@ -218,20 +217,31 @@ bool p2p_prepare(lvi_problem* p) {
   const size_t bytes = Q.off_data + static_cast<size_t>(Q.n_units) * kUnit * sizeof(double);
   if (!p2p_ensure_region(ctx, bytes)) return false;
   cudaStream_t st = ctx->stream;
-  // static tile flags of this rank from its assembly plan, and the units the reduction visits (the structurally non-zero tiles + the small units)
+  // static tile flags of this rank from its assembly plan, gathered from every rank: the reduction then knows without a remote read which
+  // peers hold something for a tile, and visits only tiles that some rank writes
+  const int W = ctx->world;
   Q.tile_flags.alloc(std::max(Q.n_tile_units, 1));
   Q.tile_flags.zero(st);
   assemble_mark_tiles(p, Q.tile_flags.p);
-  std::vector<int> list;
+  Q.tile_flags_all.alloc(static_cast<size_t>(W) * std::max(Q.n_tile_units, 1));
   {
-    std::vector<int> map(p->n_pack);
-    p->pack_map.download(map.data(), map.size(), st);
-    LVI_CUDA(cudaStreamSynchronize(st));
-    list = map;
+    ncclResult_t r = nccl().AllGather(Q.tile_flags.p, Q.tile_flags_all.p, std::max(Q.n_tile_units, 1), ncclChar, static_cast<ncclComm_t>(ctx->nccl), st);
+    LVI_REQUIRE(r == ncclSuccess, LVI_ERR_NCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(r));
   }
-  for (int k = 0; k < n_small; ++k) list.push_back(Q.n_tile_units + k);
+  std::vector<unsigned char> fl(Q.tile_flags_all.n);
+  Q.tile_flags_all.download(fl.data(), fl.size(), st);
+  LVI_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> list, own;
+  for (int u = 0; u < Q.n_tile_units; ++u) {
+    bool any = false;
+    for (int q = 0; q < W; ++q) any = any || fl[static_cast<size_t>(q) * Q.n_tile_units + u];
+    if (any) list.push_back(u);
+    if (fl[static_cast<size_t>(ctx->rank) * Q.n_tile_units + u]) own.push_back(u);
+  }
+  for (int k = 0; k < n_small; ++k) { list.push_back(Q.n_tile_units + k); own.push_back(Q.n_tile_units + k); }
   Q.unit_list.alloc(std::max<size_t>(list.size(), 1)); Q.unit_list.upload(list.data(), list.size(), st);
-  Q.n_list = static_cast<int>(list.size());
+  Q.own_list.alloc(std::max<size_t>(own.size(), 1)); Q.own_list.upload(own.data(), own.size(), st);
+  Q.n_list = static_cast<int>(list.size()); Q.n_own = static_cast<int>(own.size());
   Q.small_sum.alloc(static_cast<size_t>(n_small) * kUnit);
   Q.counter.alloc(1); Q.counter.zero(st);
   LVI_CUDA(cudaStreamSynchronize(st));
@@ -259,8 +269,8 @@ void p2p_begin_linearize(lvi_problem* p) {
   p2p_bind(p);
   char* base = static_cast<char*>(R.base);
   if (R.epoch > 0) LVI_LAUNCH(ctx, p2p_wait_kernel, 1, 32, 0, R.base, ctx->world, 1, R.epoch, p->fail.p);   // the peers are done with the previous epoch
-  LVI_LAUNCH(ctx, p2p_clear_kernel, Q.n_units, 256, 0, reinterpret_cast<unsigned char*>(base + Q.off_flags), Q.tile_flags.p,
-             reinterpret_cast<double*>(base + Q.off_data), Q.n_tile_units, Q.n_units);
+  LVI_LAUNCH(ctx, p2p_clear_kernel, Q.n_own, 256, 0, reinterpret_cast<unsigned char*>(base + Q.off_flags), Q.own_list.p, Q.n_tile_units,
+             reinterpret_cast<double*>(base + Q.off_data));
 }
 
 void p2p_reduce(lvi_problem* p) {
@@ -274,7 +284,7 @@ void p2p_reduce(lvi_problem* p) {
              Q.n_tile_units);
   const unsigned epoch = ++R.epoch;
   LVI_LAUNCH(ctx, p2p_signal_kernel, 1, 32, 0, R.peer_d, ctx->world, ctx->rank, 0, epoch);
-  P2PView V{R.peer_d, ctx->world, ctx->rank, Q.off_flags, Q.off_data, Q.n_tile_units, Q.n_units, Q.unit_list.p, Q.n_list, p->H_tiles.p, Q.small_sum.p,
+  P2PView V{R.peer_d, ctx->world, ctx->rank, Q.off_flags, Q.off_data, Q.n_tile_units, Q.n_units, Q.unit_list.p, Q.n_list, Q.tile_flags_all.p, p->H_tiles.p, Q.small_sum.p,
             epoch, p->fail.p, reinterpret_cast<unsigned*>(Q.counter.p)};
   LVI_LAUNCH(ctx, p2p_reduce_kernel, std::min(Q.n_list, ctx->sm_count * 8), 256, 0, V);
   struct Seg { double* ptr; size_t n; };

@@ -94,7 +94,10 @@ struct P2PPlan {
   int n_tile_units = 0, n_units = 0, n_list = 0;
   size_t small_elems = 0, off_flags = 0, off_data = 0;
   DBuf<unsigned char> tile_flags;   // [n_tile_units] 1 = this rank's assembly plan writes the tile
-  DBuf<int> unit_list;              // units the reduction visits
+  DBuf<unsigned char> tile_flags_all;   // [world][n_tile_units] the same of every rank
+  DBuf<int> unit_list;              // units the reduction visits (tiles some rank writes + the small units)
+  DBuf<int> own_list;               // units this rank clears before it linearises (its own tiles + the small units)
+  int n_own = 0;
   DBuf<double> small_sum;           // reduced {corner, g, Schur rows, Schur diagonal, cost}, copied out to the private buffers
   DBuf<int> counter;
 };
