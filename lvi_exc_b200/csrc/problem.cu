@@ -454,6 +454,66 @@ void problem_cost(lvi_problem* p, const double* x_d, double* cost_d, bool active
   problem_set_param_source(p, p->X.p);
 }
 
+// Distinct positions of every landmark's Schur row (static per problem): the windows of consecutive observations overlap, so ~294 slots
+// hold ~195 distinct parameters; eliminating over the merged row needs 2.3x fewer updates.  One CTA per landmark: bitonic sort of
+// (position, slot) keys in shared memory, heads of equal-position runs numbered by a scan.
+__global__ void __launch_bounds__(256) schur_merge_plan_kernel(const int* __restrict__ row_start, const int* __restrict__ row_pos, int n_landmarks,
+                                                               int* __restrict__ slot2u, int* __restrict__ urow_pos, int* __restrict__ ulen, int* __restrict__ fail) {
+  __shared__ long long key[1024];
+  __shared__ int rank[1024];
+  const int l = blockIdx.x;
+  const int rs = row_start[l], len = row_start[l + 1] - rs;
+  if (len == 0) { if (threadIdx.x == 0) ulen[l] = 0; return; }
+  if (len > 1024) { if (threadIdx.x == 0) { *fail = 6; ulen[l] = 0; } return; }
+  int n2 = 1;
+  while (n2 < len) n2 <<= 1;
+  for (int e = threadIdx.x; e < n2; e += 256) {
+    long long k = 0x7fffffffffffffffll;
+    if (e < len) { const int p = row_pos[rs + e]; if (p >= 0) k = (static_cast<long long>(p) << 16) | e; else slot2u[rs + e] = -1; }
+    key[e] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int e = threadIdx.x; e < n2; e += 256) {
+        const int x = e ^ j;
+        if (x > e) {
+          const bool up = (e & k) == 0;
+          const long long a = key[e], b = key[x];
+          if ((a > b) == up) { key[e] = b; key[x] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int e = threadIdx.x; e < n2; e += 256) {
+    const long long k = key[e];
+    const bool valid = k != 0x7fffffffffffffffll;
+    rank[e] = (valid && (e == 0 || (key[e - 1] >> 16) != (k >> 16))) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int o = 1; o < n2; o <<= 1) {   // inclusive scan
+    int v[4];
+    int c = 0;
+    for (int e = threadIdx.x; e < n2; e += 256) v[c++] = e >= o ? rank[e - o] : 0;
+    __syncthreads();
+    c = 0;
+    for (int e = threadIdx.x; e < n2; e += 256) rank[e] += v[c++];
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < n2; e += 256) {
+    const long long k = key[e];
+    if (k == 0x7fffffffffffffffll) continue;
+    const int m = rank[e] - 1, slot = static_cast<int>(k & 0xffff), p = static_cast<int>(k >> 16);
+    slot2u[rs + slot] = m;
+    if (e == 0 || (key[e - 1] >> 16) != (k >> 16)) urow_pos[rs + m] = p;
+  }
+  if (threadIdx.x == 0) {
+    int last = 0;
+    for (int e = n2 - 1; e >= 0; --e) if (key[e] != 0x7fffffffffffffffll) { last = rank[e]; break; }
+    ulen[l] = last;
+  }
+}
+
 static void alloc_bandsys(BandSys& S, const Lowered& L, DBuf<double>& tiles, DBuf<double>& C, double* Linv, double* x, int* fail) {
   S.nb = L.nb; S.nbo = L.nbo;
   S.NT = (L.nb + kTile - 1) / kTile;
@@ -502,8 +562,18 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
     p->row_pos.alloc(L.row_pos.size()); p->row_pos.upload(L.row_pos.data(), L.row_pos.size(), st);
     p->lm_of_rho.alloc(std::max<size_t>(lm.size(), 1)); p->lm_of_rho.upload(lm.data(), lm.size(), st);
     p->Hrx.alloc(L.row_pos.size()); p->Hrr.alloc(std::max(L.n_rho, 1)); p->yrho.alloc(std::max(L.n_rho, 1));
+    p->slot2u.alloc(L.row_pos.size()); p->urow_pos.alloc(L.row_pos.size()); p->ulen.alloc(std::max<size_t>(L.row_start.size() - 1, 1));
+    if (L.row_start.size() > 1) {
+      LVI_CUDA(cudaMemsetAsync(p->fail.p + 3, 0, sizeof(int), st));
+      LVI_LAUNCH(p->ctx, schur_merge_plan_kernel, static_cast<int>(L.row_start.size() - 1), 256, 0, p->row_start.p, p->row_pos.p, static_cast<int>(L.row_start.size() - 1),
+                 p->slot2u.p, p->urow_pos.p, p->ulen.p, p->fail.p + 3);
+      int fail = 0;
+      LVI_CUDA(cudaMemcpyAsync(&fail, p->fail.p + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LVI_CUDA(cudaStreamSynchronize(st));
+      LVI_REQUIRE(fail == 0, LVI_ERR_INVALID, "a landmark couples to more than 1024 parameter slots");
+    }
     LVI_CUDA(cudaStreamSynchronize(st));
-    p->schur = SchurView{L.n_rho, L.nb + L.nbo, p->row_start.p, p->row_pos.p, p->lm_of_rho.p, p->Hrx.p, p->Hrr.p, p->yrho.p};
+    p->schur = SchurView{L.n_rho, L.nb + L.nbo, p->row_start.p, p->row_pos.p, p->lm_of_rho.p, p->slot2u.p, p->urow_pos.p, p->ulen.p, p->Hrx.p, p->Hrr.p, p->yrho.p};
   }
   p->g.alloc(nt); p->scale.alloc(nt); p->diag.alloc(nt); p->y.alloc(nt); p->delta.alloc(nt);
   if (p->ctx->world > 1) {  // the all-reduce of H moves only the tiles that can be non-zero (about half of the store at C2)

@@ -65,6 +65,9 @@ struct SchurView {
   const int* row_start;     // [n_landmarks + 1] by landmark id
   const int* row_pos;       // [slots] band/border position of each slot (-1: constant)
   const int* lm_of_rho;     // [n_rho] landmark id of the k-th free inverse depth
+  const int* slot2u;        // [slots] index of the slot's position in the landmark's list of DISTINCT positions (-1: constant)
+  const int* urow_pos;      // [slots] the distinct positions of landmark l, ascending, at row_start[l] .. row_start[l] + ulen[l]
+  const int* ulen;          // [n_landmarks]
   double* Hrx;              // [slots]
   double* Hrr;              // [n_rho]
   double* yrho;             // [n_rho] back-substituted step
@@ -138,7 +141,7 @@ struct lvi_problem {
   lvi::SchurView schur_lin{};
   double* g_lin = nullptr;
   double* cost_lin = nullptr;
-  lvi::DBuf<int> row_start, row_pos, lm_of_rho;
+  lvi::DBuf<int> row_start, row_pos, lm_of_rho, slot2u, urow_pos, ulen;
   lvi::DBuf<double> Hrx, Hrr, yrho;
   lvi::DBuf<int> fail;
   lvi::DBuf<double> g, scale, diag, y, delta, scal;  // scal: small scalar scratch (cost etc.)

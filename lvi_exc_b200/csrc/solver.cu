@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(BandSys A, SchurVi
   const int lm = SV.lm_of_rho[k];
   const int rs = SV.row_start[lm], len = SV.row_start[lm + 1] - rs;
   if (len == 0) return;
+  const int lu = SV.ulen[lm];   // distinct positions of the row (the windows of consecutive observations overlap), ascending
   double* hv = sm;
   int* hp = reinterpret_cast<int*>(sm + len);
   const int t = SV.base + k;
@@ -119,30 +120,30 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(BandSys A, SchurVi
   const double d = SV.Hrr[k] * sr * sr + diag[t] * inv_radius;
   const double dinv = 1.0 / d;
   const double br = -g[t] * sr;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+  for (int i = threadIdx.x; i < lu; i += blockDim.x) { hv[i] = 0.0; hp[i] = SV.urow_pos[rs + i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {   // slots of one parameter add up: h is the coupling to the PARAMETER
     const int p = SV.row_pos[rs + i];
-    hp[i] = p;
-    hv[i] = p >= 0 ? SV.Hrx[rs + i] * scale[p] * sr : 0.0;
+    if (p < 0) continue;
+    const double v = SV.Hrx[rs + i] * scale[p] * sr;
+    if (v != 0.0) atomicAdd(&hv[SV.slot2u[rs + i]], v);
   }
   __syncthreads();
   const int rhs_row = A.nb + A.nbo;
-  for (int i = threadIdx.x; i < len; i += blockDim.x)
-    if (hp[i] >= 0 && hv[i] != 0.0) atomicAdd(band_addr(A, rhs_row, hp[i]), -hv[i] * br * dinv);
-  // rows i and len-1-i together hold len+1 pairs: every thread gets the same amount of work and no index decoding is needed
-  for (int r = threadIdx.x; 2 * r < len; r += blockDim.x) {
+  for (int i = threadIdx.x; i < lu; i += blockDim.x)
+    if (hv[i] != 0.0) atomicAdd(band_addr(A, rhs_row, hp[i]), -hv[i] * br * dinv);
+  // rows i and lu-1-i together hold lu+1 pairs: every thread gets the same amount of work and no index decoding is needed
+  for (int r = threadIdx.x; 2 * r < lu; r += blockDim.x) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      const int i = half == 0 ? r : len - 1 - r;
+      const int i = half == 0 ? r : lu - 1 - r;
       if (half == 1 && i == r) break;
       const int pi = hp[i];
       const double hi = hv[i] * dinv;
-      if (pi < 0 || hi == 0.0) continue;
+      if (hi == 0.0) continue;
       for (int j = 0; j <= i; ++j) {
-        const int pj = hp[j];
-        double v = hi * hv[j];
-        if (pj < 0 || v == 0.0) continue;
-        if (i != j && pi == pj) v += v;
-        atomicAdd(band_addr(A, max(pi, pj), min(pi, pj)), -v);
+        const double v = hi * hv[j];
+        if (v != 0.0) atomicAdd(band_addr(A, pi, hp[j]), -v);   // positions ascend: pi >= hp[j]
       }
     }
   }
