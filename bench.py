@@ -522,6 +522,12 @@ def main():
     # stop the sampler before the host-synchronous e2e leg: every nvidia-smi query takes driver locks, and lvi_problem_solve has
     # half a dozen stream synchronisations per iteration (measured: 59 ms/iteration with the poller running, 12 ms without)
     clocks = sampler.stop() if sampler else None
+    # per-kernel CUDA-event times of a few more iterations (every rank: the iterations contain the multi-GPU reduction)
+    backend.kernel_timing(True); backend.kernel_times()
+    kt_iters = 5
+    prob.bench_iterations(kt_iters)
+    kt = {k: v[1] / kt_iters for k, v in backend.kernel_times().items()}
+    backend.kernel_timing(False)
     # ---- end to end through the C-ABI with host buffers (H2D of tables/parameters and D2H of the optimum inside the timed region)
     pw = CudaProblem(backend, pd)       # untimed warm-up of the host-buffer path (first-use costs of the solve loop's small kernels)
     pw.solve(2, **tol0)
@@ -567,6 +573,19 @@ def main():
                 "note": "latency-bound: two serial chains of ~273 block columns at ~6.5 us each (profiles/r1c_factor_trace_c2.txt); "
                         "~9.5 GFLOP of fp64 per launch, neither HBM nor FLOP limited",
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fac_ms, "share_of_step": fac_ms / ms_total}
+    # ---- the other kernels of an iteration, timed live with CUDA events around every launch (outside the timed region above): the
+    # normal-equation build against the fp64 tensor pipe, the rest as time only
+    n_of = lambda k: len(pd.tables[k][0]) if k in pd.tables else 0
+    jtj_flops = 2.0 * (3 * 15 * 16 * n_of("gyro") + 3 * 29 * 30 * n_of("accel") + 54 * 55 * n_of("surfel") + 2 * 55 * 56 * n_of("cam") + 60 * 61 * n_of("camsurf"))
+    gather_ms = kt.get("gather_kernel", 0.0)
+    ncu = json.loads(tf.read_text()).get("gather_kernel", {}) if tf.exists() and args.duration == 60.0 else {}
+    roofline["kernels_ms"] = {k: round(v, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:12]}
+    roofline["tensor_pipe"] = {"kernel": "gather_kernel", "instruction": "mma.sync.aligned.m8n8k4.f64 (fp64 tensor pipe; tcgen05 has no fp64 kind)",
+                               "avg_launch_ms": gather_ms, "algorithmic_flops": jtj_flops, "bytes_per_unit": "2 r p (p + 1) flops per residual of r rows and p columns (J^T J and J^T r)",
+                               "achieved_tflops_algorithmic": jtj_flops / (gather_ms * 1e-3) / 1e12 if gather_ms > 0 else None,
+                               "dmma_pipe_active_pct": ncu.get("dmma_pipe_pct_of_peak_sustained_active"), "traffic": ncu.get("dram_bytes_per_launch"),
+                               "source": "live CUDA-event time; pipe utilisation and DRAM bytes from the ncu --set full capture under profiles/ (ncu_traffic.json)",
+                               "note": "executed flops exceed the algorithmic ones: every (tile, residual) pair runs a full 32 x 32 x rows block"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_total, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, pd, world, nres, nt),

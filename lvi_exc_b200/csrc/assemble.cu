@@ -45,17 +45,24 @@ __global__ void pos_kernel(ProblemView P, int* __restrict__ pos) {
   pos[idx] = p;
 }
 
+__device__ __forceinline__ const int* set_pos(const RowSetView& S, int res) { return S.pos + (S.boff ? static_cast<size_t>(S.boff[res]) : static_cast<size_t>(res) * S.ncols); }
+__device__ __forceinline__ int set_ncols(const RowSetView& S, int res) { return S.bcols ? S.bcols[res] : S.ncols; }
+__device__ __forceinline__ const double* set_block(const RowSetView& S, int res) { return S.J + (S.boff ? static_cast<size_t>(S.boff[res]) : static_cast<size_t>(res) * S.rstride); }
+__device__ __forceinline__ int set_blen(const RowSetView& S, int res) { return S.bcols ? ((S.bcols[res] + 1) & ~1) : S.rstride; }
+
 struct TileDims { int nb, NT, T, RB, TPC; };
 __device__ __forceinline__ int virtual_tile_row(const TileDims& D, int p) { return p < D.nb ? p >> kTileLog : D.NT + ((p - D.nb) >> kTileLog); }
 
 // the distinct tile rows a residual touches (sorted) -> one (tile, residual) key per pair I >= J
 template <bool EMIT>
-__global__ void pairs_kernel(const int* __restrict__ pos, int ncols, int lo, int hi, int set, TileDims D, int res_base, const int* __restrict__ offsets,
+__global__ void pairs_kernel(RowSetView S, int set, TileDims D, int res_base, const int* __restrict__ offsets,
                              int* __restrict__ counts, unsigned long long* __restrict__ keys, int* __restrict__ fail) {
+  const int lo = S.lo, hi = S.hi;
   const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hi) return;
-  const int* pr = pos + static_cast<size_t>(i) * ncols;
-  constexpr int kMaxRows = 10;
+  const int* pr = set_pos(S, i);
+  const int ncols = set_ncols(S, i);
+  constexpr int kMaxRows = 48;   // a landmark's row spans its reference window and every observation window
   int vt[kMaxRows];
   int nv = 0;
   for (int c = 0; c < ncols; ++c) {
@@ -106,7 +113,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 
 // Per (tile, residual) entry: which Jacobian column feeds each of the 32 panel columns -- bytes [0,32) for the tile's row range, [32,64) for
 // its column range (255: none).  Static, so the per-iteration gather does no position arithmetic at all.
-constexpr int kDescBytes = 64;
+// DescT = unsigned char for the Jacobian sets (<= 60 columns), unsigned short for the Schur rows (a long track couples > 255 parameters)
+template <class DescT> struct DescNone;
+template <> struct DescNone<unsigned char> { static constexpr unsigned value = 0xffu; };
+template <> struct DescNone<unsigned short> { static constexpr unsigned value = 0xffffu; };
+constexpr int kDescEntries = 64;
 __device__ __forceinline__ void tile_ranges(const BandSys& H, long long tile, int& rowbase, int& rowend, int& colbase, int& colend) {
   const long long n_band_tiles = static_cast<long long>(H.NT) * H.TPC;
   if (tile < n_band_tiles) {
@@ -120,7 +131,8 @@ __device__ __forceinline__ void tile_ranges(const BandSys& H, long long tile, in
     colbase = H.nb + (bj << kTileLog); colend = colbase + kTile;
   }
 }
-__global__ void desc_kernel(AsmSets sets, BandSys H, const unsigned long long* __restrict__ keys, int n_entries, unsigned char* __restrict__ desc) {
+template <class DescT>
+__global__ void desc_kernel(AsmSets sets, BandSys H, const unsigned long long* __restrict__ keys, int n_entries, DescT* __restrict__ desc) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_entries) return;
   const unsigned long long key = keys[e];
@@ -128,12 +140,13 @@ __global__ void desc_kernel(AsmSets sets, BandSys H, const unsigned long long* _
   const int res = static_cast<int>(key & 0x1fffffffu);
   int rowbase, rowend, colbase, colend;
   tile_ranges(H, static_cast<long long>(key >> 32), rowbase, rowend, colbase, colend);
-  const int* pr = S.pos + static_cast<size_t>(res) * S.ncols;
-  unsigned char* d = desc + static_cast<size_t>(e) * kDescBytes;
-  for (int c = 0; c < S.ncols; ++c) {
+  const int* pr = set_pos(S, res);
+  const int ncols = set_ncols(S, res);
+  DescT* d = desc + static_cast<size_t>(e) * kDescEntries;
+  for (int c = 0; c < ncols; ++c) {
     const int p = pr[c];
-    if (p >= rowbase && p < rowend) d[p - rowbase] = static_cast<unsigned char>(c);
-    if (p >= colbase && p < colend) d[32 + p - colbase] = static_cast<unsigned char>(c);
+    if (p >= rowbase && p < rowend) d[p - rowbase] = static_cast<DescT>(c);
+    if (p >= colbase && p < colend && !(S.row_only_last && c == ncols - 1)) d[32 + p - colbase] = static_cast<DescT>(c);
   }
 }
 
@@ -161,22 +174,28 @@ __device__ __forceinline__ void g_mbar_wait(unsigned long long* b, unsigned pari
 // One warp's staging area: the Jacobian blocks ([rows x ncols | r | pad], 16-byte multiples) and the descriptors of one batch of entries land
 // here by bulk async copies -- every load of the batch is in flight at once; the tensor-core fragments are then read straight out of it.
 constexpr int kStageDoubles = 2048;   // 16 cam blocks of 112, 32 surfel blocks of 56, 32 camera-surfel blocks of 62
+template <class DescT>
 struct WarpStage {
   alignas(128) double J[kStageDoubles];
-  alignas(16) unsigned char desc[32 * kDescBytes];
+  alignas(16) DescT desc[32 * kDescEntries];
   unsigned short rowoff[kPanelRows];   // panel row -> offset of its Jacobian row in J
   unsigned short roff[kPanelRows];     //           -> offset of its residual value
   unsigned char rowent[kPanelRows];    //           -> entry slot of the batch (descriptor row)
   unsigned long long bar;
 };
 
+template <class DescT>
 __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets, BandSys H, const unsigned long long* __restrict__ keys,
-                                                                   const unsigned char* __restrict__ desc, const int* __restrict__ item_start, int n_items,
-                                                                   int n_entries, double* __restrict__ g) {
+                                                                   const DescT* __restrict__ desc, const int* __restrict__ item_start, int n_items,
+                                                                   int n_entries, double* __restrict__ g, int subtract) {
+  // subtract == 0: tile = sum (rows)(rows)^T, g += rows^T r  (normal equations; tiles pre-zeroed where items share them)
+  // subtract == 1: tile -= sum (rows)(rows)^T              (Schur complement on top of the damped system; no gradient)
   extern __shared__ __align__(128) unsigned char gather_smem[];
   constexpr unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpStage& W = reinterpret_cast<WarpStage*>(gather_smem)[warp];
+  constexpr unsigned kNone = DescNone<DescT>::value;
+  constexpr unsigned kDescBytes = kDescEntries * sizeof(DescT);
+  WarpStage<DescT>& W = reinterpret_cast<WarpStage<DescT>*>(gather_smem)[warp];
   const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: A[row fr][k fk], B[k fk][col fr], C[row fr][cols 2 fk, 2 fk + 1]
   const long long n_band_tiles = static_cast<long long>(H.NT) * H.TPC;
   if (lane == 0) {
@@ -207,7 +226,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets,
       if (lane < nk) key = keys[eb + lane];
       const int set = static_cast<int>((key >> 29) & 7u), res = static_cast<int>(key & 0x1fffffffu);
       const RowSetView& S = sets.s[set];
-      const int rows = lane < nk ? S.rows : 0, blk = lane < nk ? S.rstride : 0;
+      const int rows = lane < nk ? S.rows : 0, blk = lane < nk ? set_blen(S, res) : 0;
+      const int ncols = lane < nk ? set_ncols(S, res) : 0;
       int incl = rows, sincl = blk;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -229,14 +249,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets,
         __syncwarp();
         if (fits) {
           const int soff = sexcl - base_stage, row0 = excl - base_rows;
-          g_tma_load_1d(W.J + soff, S.J + static_cast<size_t>(res) * S.rstride, static_cast<unsigned>(S.rstride) * 8u, &W.bar);
+          g_tma_load_1d(W.J + soff, set_block(S, res), static_cast<unsigned>(blk) * 8u, &W.bar);
           for (int k = 0; k < rows; ++k) {
-            W.rowoff[row0 + k] = static_cast<unsigned short>(soff + k * S.ncols);
-            W.roff[row0 + k] = static_cast<unsigned short>(soff + rows * S.ncols + k);
+            W.rowoff[row0 + k] = static_cast<unsigned short>(soff + k * ncols);
+            W.roff[row0 + k] = static_cast<unsigned short>(soff + rows * ncols + k);
             W.rowent[row0 + k] = static_cast<unsigned char>(lane - consumed);
           }
         }
-        if (lane == 0) g_tma_load_1d(W.desc, desc + static_cast<size_t>(eb + consumed) * kDescBytes, static_cast<unsigned>(cnt) * kDescBytes, &W.bar);
+        if (lane == 0) g_tma_load_1d(W.desc, desc + static_cast<size_t>(eb + consumed) * kDescEntries, static_cast<unsigned>(cnt) * kDescBytes, &W.bar);
         __syncwarp();
         g_mbar_wait(&W.bar, phase);
         phase ^= 1u;
@@ -244,14 +264,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets,
           const int row = k0 + fk;
           const bool live = row < total_rows;
           const int off = live ? W.rowoff[row] : 0;
-          const unsigned char* dr = W.desc + (live ? W.rowent[row] : 0) * kDescBytes;
+          const DescT* dr = W.desc + (live ? W.rowent[row] : 0) * kDescEntries;
           double a[4], bf[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int cI = dr[8 * q + fr];
-            a[q] = (live && cI != 255) ? W.J[off + cI] : 0.0;
+            const unsigned cI = dr[8 * q + fr];
+            a[q] = (live && cI != kNone) ? W.J[off + cI] : 0.0;
             if (diag) bf[q] = a[q];
-            else { const int cJ = dr[32 + 8 * q + fr]; bf[q] = (live && cJ != 255) ? W.J[off + cJ] : 0.0; }
+            else { const unsigned cJ = dr[32 + 8 * q + fr]; bf[q] = (live && cJ != kNone) ? W.J[off + cJ] : 0.0; }
           }
 #pragma unroll
           for (int mb = 0; mb < 4; ++mb)
@@ -259,10 +279,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets,
             for (int nb = 0; nb < 4; ++nb)
               dmma_m8n8k4(acc[mb][nb], a[mb], bf[nb]);
         }
-        if (diag)
+        if (diag && !subtract)
           for (int r = 0; r < total_rows; ++r) {
-            const int c = W.desc[W.rowent[r] * kDescBytes + lane];
-            if (c != 255) gacc = fma(W.J[W.rowoff[r] + c], W.J[W.roff[r]], gacc);
+            const unsigned c = W.desc[W.rowent[r] * kDescEntries + lane];
+            if (c != kNone) gacc = fma(W.J[W.rowoff[r] + c], W.J[W.roff[r]], gacc);
           }
         __syncwarp();   // everybody is done with the staging area before the next batch's copies land in it
         base_rows += total_rows; base_stage += total_stage;
@@ -276,10 +296,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_kernel(AsmSets sets,
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           double* d = dst + (8 * mb + fr) + static_cast<size_t>(ld) * (8 * nb + 2 * fk + q);
-          if (sole) *d = acc[mb][nb][q];
-          else if (acc[mb][nb][q] != 0.0) atomicAdd(d, acc[mb][nb][q]);
+          const double v = acc[mb][nb][q];
+          if (subtract) {   // A holds its diagonal tiles as lower triangles: the mirrored half of the product is not applied
+            if (v != 0.0 && !(diag && 8 * mb + fr < 8 * nb + 2 * fk + q)) { if (sole) *d -= v; else atomicAdd(d, -v); }
+          }
+          else if (sole) *d = v;
+          else if (v != 0.0) atomicAdd(d, v);
         }
-    if (diag && gacc != 0.0) atomicAdd(g + rowbase + lane, gacc);
+    if (diag && !subtract && gacc != 0.0) atomicAdd(g + rowbase + lane, gacc);
   }
 }
 
@@ -293,17 +317,13 @@ static void launch_pos(lvi_problem* p, AsmPlan& A) {
   A.J[TYPE].alloc(static_cast<size_t>(T.n) * rstride);
   const long long n = static_cast<long long>(T.n) * cols;
   LVI_LAUNCH(p->ctx, pos_kernel<TYPE>, static_cast<int>((n + 255) / 256), 256, 0, p->view, A.pos[TYPE].p);
-  A.sets.s[TYPE] = RowSetView{A.J[TYPE].p, A.pos[TYPE].p, cols, rows, rstride, T.lo, T.hi};
+  A.sets.s[TYPE] = RowSetView{A.J[TYPE].p, A.pos[TYPE].p, cols, rows, rstride, T.lo, T.hi, nullptr, nullptr, 0};
 }
 
-void assemble_build_plan(lvi_problem* p) {
-  AsmPlan& A = p->asmp;
-  if (A.built) return;
+// keys, work items and descriptors of a plan whose row sets (positions) are in place
+static void build_plan_structure(lvi_problem* p, AsmPlan& A, const BandSys& H, int desc_width) {
   lvi_ctx* ctx = p->ctx;
   cudaStream_t st = ctx->stream;
-  for (int t = 0; t < RT_COUNT; ++t) A.sets.s[t] = RowSetView{nullptr, nullptr, rt_cols(t), rt_rows(t), asm_block_doubles(t), 0, 0};
-  launch_pos<RT_GYRO>(p, A); launch_pos<RT_ACCEL>(p, A); launch_pos<RT_SURFEL>(p, A); launch_pos<RT_CAM>(p, A); launch_pos<RT_CAMSURF>(p, A); launch_pos<RT_ORIENT>(p, A);
-  const BandSys& H = p->H;
   const TileDims D{H.nb, H.NT, H.T, H.RB, H.TPC};
   int n_res = 0, base[RT_COUNT];
   for (int t = 0; t < RT_COUNT; ++t) { base[t] = n_res; n_res += A.sets.s[t].hi - A.sets.s[t].lo; }
@@ -314,7 +334,7 @@ void assemble_build_plan(lvi_problem* p) {
   LVI_CUDA(cudaMemsetAsync(p->fail.p + 2, 0, sizeof(int), st));
   for (int t = 0; t < RT_COUNT; ++t) {
     const RowSetView& S = A.sets.s[t];
-    if (S.hi > S.lo) LVI_LAUNCH(ctx, pairs_kernel<false>, (S.hi - S.lo + 127) / 128, 128, 0, S.pos, S.ncols, S.lo, S.hi, t, D, base[t], nullptr, counts.p, nullptr, p->fail.p + 2);
+    if (S.hi > S.lo) LVI_LAUNCH(ctx, pairs_kernel<false>, (S.hi - S.lo + 127) / 128, 128, 0, S, t, D, base[t], nullptr, counts.p, nullptr, p->fail.p + 2);
   }
   size_t tb = 0, tb2 = 0, tb3 = 0, tb4 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, offsets.p, n_res + 1, st);
@@ -328,7 +348,7 @@ void assemble_build_plan(lvi_problem* p) {
   A.keys.alloc(n_entries);
   for (int t = 0; t < RT_COUNT; ++t) {
     const RowSetView& S = A.sets.s[t];
-    if (S.hi > S.lo) LVI_LAUNCH(ctx, pairs_kernel<true>, (S.hi - S.lo + 127) / 128, 128, 0, S.pos, S.ncols, S.lo, S.hi, t, D, base[t], offsets.p, nullptr, unsorted.p, p->fail.p + 2);
+    if (S.hi > S.lo) LVI_LAUNCH(ctx, pairs_kernel<true>, (S.hi - S.lo + 127) / 128, 128, 0, S, t, D, base[t], offsets.p, nullptr, unsorted.p, p->fail.p + 2);
   }
   cub::DeviceRadixSort::SortKeys(nullptr, tb2, unsorted.p, A.keys.p, n_entries, 0, 64, st);
   DBuf<unsigned char> tmp2(std::max<size_t>(tb2, 1));
@@ -351,13 +371,88 @@ void assemble_build_plan(lvi_problem* p) {
   LVI_CUDA(cudaMemcpyAsync(&n_items, n_sel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaMemcpyAsync(&fail, p->fail.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
   LVI_CUDA(cudaStreamSynchronize(st));
-  LVI_REQUIRE(fail == 0, LVI_ERR_INVALID, fail == 4 ? "assembly plan: a residual couples positions further apart than the half bandwidth" : "assembly plan: a residual touches more than 10 tile rows");
+  LVI_REQUIRE(fail == 0, LVI_ERR_INVALID, fail == 4 ? "assembly plan: a row couples positions further apart than the half bandwidth" : "assembly plan: a row touches more than 48 tile rows");
   LVI_CUDA(cudaMemcpyAsync(A.item_start.p + n_items, &n_entries, sizeof(int), cudaMemcpyHostToDevice, st));
   LVI_CUDA(cudaStreamSynchronize(st));
   A.n_items = n_items; A.n_entries = n_entries;
-  A.desc.alloc(static_cast<size_t>(n_entries) * kDescBytes);
+  A.desc_width = desc_width;
+  A.desc.alloc(static_cast<size_t>(n_entries) * kDescEntries * desc_width);
   LVI_CUDA(cudaMemsetAsync(A.desc.p, 0xFF, A.desc.n, st));
-  LVI_LAUNCH(ctx, desc_kernel, (n_entries + 127) / 128, 128, 0, A.sets, p->H, A.keys.p, n_entries, A.desc.p);
+  if (desc_width == 1) LVI_LAUNCH(ctx, desc_kernel<unsigned char>, (n_entries + 127) / 128, 128, 0, A.sets, H, A.keys.p, n_entries, A.desc.p);
+  else LVI_LAUNCH(ctx, desc_kernel<unsigned short>, (n_entries + 127) / 128, 128, 0, A.sets, H, A.keys.p, n_entries, reinterpret_cast<unsigned short*>(A.desc.p));
+}
+
+void assemble_build_plan(lvi_problem* p) {
+  AsmPlan& A = p->asmp;
+  if (A.built) return;
+  for (int t = 0; t < RT_COUNT; ++t) A.sets.s[t] = RowSetView{nullptr, nullptr, rt_cols(t), rt_rows(t), asm_block_doubles(t), 0, 0, nullptr, nullptr, 0};
+  launch_pos<RT_GYRO>(p, A); launch_pos<RT_ACCEL>(p, A); launch_pos<RT_SURFEL>(p, A); launch_pos<RT_CAM>(p, A); launch_pos<RT_CAMSURF>(p, A); launch_pos<RT_ORIENT>(p, A);
+  build_plan_structure(p, A, p->H, 1);
+}
+
+// ---- the Schur complement on the inverse depths through the same gather: one "residual" per free inverse depth, its row = the merged
+// coupling row of the landmark (distinct positions, SchurView::urow_pos) + one more column at the position of the right-hand-side row
+__global__ void schur_set_kernel(SchurView SV, int rhs_pos, int* __restrict__ boff, int* __restrict__ bcols, int* __restrict__ pos, int* __restrict__ max_cols) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= SV.n_rho) return;
+  const int lm = SV.lm_of_rho[k];
+  const int rs = SV.row_start[lm], lu = SV.ulen[lm];
+  const int off = rs + 2 * k;   // even; blocks of lu + 1 doubles (rounded up to even) never overlap: lu <= slots of the landmark
+  boff[k] = off; bcols[k] = lu + 1;
+  for (int i = 0; i < lu; ++i) pos[off + i] = SV.urow_pos[rs + i];
+  pos[off + lu] = rhs_pos;
+  atomicMax(max_cols, lu + 1);
+}
+
+void assemble_build_schur_plan(lvi_problem* p) {
+  AsmPlan& A = p->schur_plan;
+  p->schur_gather = false;
+  if (A.built) return;
+  A.built = true;
+  const int n_rho = p->L.n_rho;
+  // Measured at C2 (gpurun_out/r2w): 0.31 ms through the gather against 0.28 ms for schur_eliminate_kernel's atomics -- a landmark's row has
+  // ~300 columns spread over ~24 tile rows (its observation windows are 10 knots apart), so 888 k (tile, landmark) keys each stage a 2.6 KB
+  // row for <= 64 useful columns.  Kept as an option (LVI_SCHUR_GATHER=1: no atomics, bitwise reproducible A); the default is the atomic kernel.
+  if (n_rho == 0 || !std::getenv("LVI_SCHUR_GATHER")) return;
+  lvi_ctx* ctx = p->ctx;
+  cudaStream_t st = ctx->stream;
+  const size_t n_blocks = p->L.row_pos.size() + 2 * static_cast<size_t>(n_rho) + 2;
+  p->schur_boff.alloc(n_rho); p->schur_bcols.alloc(n_rho); p->schur_pos.alloc(n_blocks); p->schur_rows.alloc(n_blocks);
+  DBuf<int> mx(1);
+  mx.zero(st);
+  LVI_LAUNCH(ctx, schur_set_kernel, (n_rho + 127) / 128, 128, 0, p->schur, p->H.nb + p->H.nbo, p->schur_boff.p, p->schur_bcols.p, p->schur_pos.p, mx.p);
+  int max_cols = 0;
+  LVI_CUDA(cudaMemcpyAsync(&max_cols, mx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LVI_CUDA(cudaStreamSynchronize(st));
+  if (max_cols + 2 > kStageDoubles) return;   // a row has to fit the staging area: longer rows keep the atomic kernel
+  for (int t = 0; t < RT_COUNT; ++t) A.sets.s[t] = RowSetView{nullptr, nullptr, 0, 1, 0, 0, 0, nullptr, nullptr, 0};
+  A.sets.s[0] = RowSetView{p->schur_rows.p, p->schur_pos.p, 0, 1, 0, 0, n_rho, p->schur_boff.p, p->schur_bcols.p, 1};
+  build_plan_structure(p, A, p->A, 2);
+  p->schur_gather = A.n_items > 0;
+}
+
+static void launch_gather(lvi_problem* p, AsmPlan& A, const BandSys& target, double* g, int subtract) {
+  const int grid = std::min((A.n_items + kGatherWarps - 1) / kGatherWarps, p->ctx->sm_count * 3);
+  if (A.desc_width == 1) {
+    constexpr size_t smem = sizeof(WarpStage<unsigned char>) * kGatherWarps;
+    if (!p->ctx->ks.gather_attr[0]) {
+      LVI_CUDA(cudaFuncSetAttribute(gather_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      p->ctx->ks.gather_attr[0] = true;
+    }
+    LVI_LAUNCH_AS(p->ctx, subtract ? "gather_kernel(schur)" : "gather_kernel", gather_kernel<unsigned char>, grid, kGatherWarps * 32, smem, A.sets, target, A.keys.p, A.desc.p,
+                  A.item_start.p, A.n_items, A.n_entries, g, subtract);
+  } else {
+    constexpr size_t smem = sizeof(WarpStage<unsigned short>) * kGatherWarps;
+    if (!p->ctx->ks.gather_attr[1]) {
+      LVI_CUDA(cudaFuncSetAttribute(gather_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      p->ctx->ks.gather_attr[1] = true;
+    }
+    LVI_LAUNCH_AS(p->ctx, subtract ? "gather_kernel(schur)" : "gather_kernel", gather_kernel<unsigned short>, grid, kGatherWarps * 32, smem, A.sets, target, A.keys.p,
+                  reinterpret_cast<const unsigned short*>(A.desc.p), A.item_start.p, A.n_items, A.n_entries, g, subtract);
+  }
+}
+void assemble_schur_gather(lvi_problem* p) {
+  if (p->schur_plan.n_items) launch_gather(p, p->schur_plan, p->A, nullptr, 1);
 }
 
 __global__ void mark_tiles_kernel(const unsigned long long* __restrict__ keys, int n, long long n_band_tiles, unsigned char* __restrict__ flags) {
@@ -374,15 +469,7 @@ void assemble_mark_tiles(lvi_problem* p, unsigned char* flags_d) {
 
 // tile += gathered J^T J, g += J^T r  (H, g zeroed by the caller; the Jacobian rows are in the plan's buffers)
 void assemble_gather(lvi_problem* p) {
-  AsmPlan& A = p->asmp;
-  if (A.n_items == 0) return;
-  constexpr size_t smem = sizeof(WarpStage) * kGatherWarps;
-  if (!p->ctx->ks.gather_attr) {
-    LVI_CUDA(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    p->ctx->ks.gather_attr = true;
-  }
-  const int grid = std::min((A.n_items + kGatherWarps - 1) / kGatherWarps, p->ctx->sm_count * 3);
-  LVI_LAUNCH(p->ctx, gather_kernel, grid, kGatherWarps * 32, smem, A.sets, p->H_lin, A.keys.p, A.desc.p, A.item_start.p, A.n_items, A.n_entries, p->g_lin);
+  if (p->asmp.n_items) launch_gather(p, p->asmp, p->H_lin, p->g_lin, 0);
 }
 
 }  // namespace lvi

@@ -67,7 +67,7 @@ struct lvi_ctx {
     bool pair_table = false;          // problem.cu: g_pair_table uploaded to this device
     bool lin_attr[8] = {};            // problem.cu: linearize_kernel<TYPE> shared-memory attribute set
     bool jac_attr[8] = {};            //             jacobian_kernel<TYPE> likewise
-    bool gather_attr = false;         // assemble.cu: gather_kernel dynamic shared memory attribute set
+    bool gather_attr[2] = {};         // assemble.cu: gather_kernel<8 / 16-bit descriptors> dynamic shared memory attribute set
     int fac_resident = 0;             // solver.cu: co-resident CTAs of band_factor_ll_kernel (0 = not yet queried)
     int bs_resident = 0;              //            ... of band_backsolve_ll_kernel
     size_t corner_attr = 48 * 1024;   //            dynamic shared memory granted to corner_solve_kernel so far

@@ -600,6 +600,7 @@ void problem_ensure_solver_buffers(lvi_problem* p) {
   p->has_solver_buffers = true;
   p->H_lin = p->H; p->schur_lin = p->schur; p->g_lin = p->g.p; p->cost_lin = p->scal.p;
   assemble_build_plan(p);
+  assemble_build_schur_plan(p);
   if (p->ctx->world > 1 && p2p_prepare(p)) {   // the peers' contributions are read straight out of their HBM: the private store is only ever written
     p->H_tiles.zero(p->ctx->stream);
   }

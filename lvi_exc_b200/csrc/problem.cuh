@@ -77,7 +77,9 @@ struct SchurView {
 // one residual table's loss-corrected Jacobian in HBM: one block of `rstride` doubles per residual = [row][column] | r[row] | padding to a
 // 16-byte multiple (so a block moves with one bulk async copy); pos [residual][column] = position in the linear system (-1: constant block,
 // or a column merged into an earlier one)
-struct RowSetView { const double* J; const int* pos; int ncols, rows, rstride, lo, hi; };
+// Variable-length sets (the Schur rows of the landmarks): boff[res] = offset of the block / of its positions, bcols[res] = its columns;
+// row_only_last: the last column of every row feeds tile ROWS only (the right-hand-side element of a Schur row).
+struct RowSetView { const double* J; const int* pos; int ncols, rows, rstride, lo, hi; const int* boff; const int* bcols; int row_only_last; };
 LVI_HD int asm_block_doubles(int t) { return (rt_rows(t) * rt_cols(t) + rt_rows(t) + 1) & ~1; }
 struct AsmSets { RowSetView s[RT_COUNT]; };
 struct AsmPlan {
@@ -85,7 +87,8 @@ struct AsmPlan {
   DBuf<int> pos[RT_COUNT];
   DBuf<unsigned long long> keys;   // (tile << 32 | table << 29 | residual), sorted
   DBuf<int> item_start;            // [n_items + 1] offsets into keys: one work item = <= kChunk residuals of one tile
-  DBuf<unsigned char> desc;        // [n_entries][64] Jacobian column behind each panel column (row range | column range), 255 = none
+  DBuf<unsigned char> desc;        // [n_entries][64] x desc_width bytes: Jacobian column behind each tile row / tile column, all ones = none
+  int desc_width = 1;
   AsmSets sets{};
   int n_items = 0, n_entries = 0;
   bool built = false;
@@ -134,6 +137,10 @@ struct lvi_problem {
   lvi::DBuf<double> pack_buf;    // ... and their contiguous staging copy
   int n_pack = 0;
   lvi::AsmPlan asmp;
+  lvi::AsmPlan schur_plan;             // the same machinery for the Schur complement on the inverse depths: rows = landmarks
+  lvi::DBuf<double> schur_rows;        // [blocks] sqrt(1/d) * (merged coupling row | right-hand-side element)
+  lvi::DBuf<int> schur_boff, schur_bcols, schur_pos;
+  bool schur_gather = false;
   lvi::P2PPlan p2p;
   lvi::SchurView schur{};
   // where a linearisation writes: the private buffers (H, schur, g, scal), or this rank's peer-memory region (multi-GPU, p2p.cu)
@@ -160,6 +167,8 @@ void problem_download_params(lvi_problem* p);
 // assemble.cu
 void assemble_build_plan(lvi_problem* p);   // once per problem, after problem_ensure_solver_buffers
 void assemble_gather(lvi_problem* p);       // H tiles, corner and g from the Jacobian rows jacobian_kernel<TYPE> left in the plan's buffers
+void assemble_build_schur_plan(lvi_problem* p);                       // once per problem: landmarks as rows of a second plan (false: rows too long)
+void assemble_schur_gather(lvi_problem* p);                           // A -= sum over landmarks of (row)(row)^T from p->schur_rows
 void assemble_mark_tiles(lvi_problem* p, unsigned char* flags_d);   // flags[tile] = 1 for every band / border tile this rank's plan writes
 // p2p.cu
 bool p2p_prepare(lvi_problem* p);           // collective; true: the linearisation targets point into the peer-memory region

@@ -149,6 +149,36 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(BandSys A, SchurVi
   }
 }
 
+// The same elimination through the tile gather (assemble.cu): this kernel only writes, per free inverse depth, the block
+//   sqrt(1/d) * [ merged scaled coupling row h | b_r ]
+// and gather_kernel subtracts (block)(block)^T from the tiles of A -- the column at the position of the right-hand-side row turns the
+// rhs update into one more row of the same product.  No fp64 atomics on the band.
+__global__ void __launch_bounds__(128) schur_rows_kernel(BandSys A, SchurView SV, const double* __restrict__ scale, const double* __restrict__ diag,
+                                                         double inv_radius, const double* __restrict__ g, const int* __restrict__ boff, double* __restrict__ rows) {
+  extern __shared__ double sm[];
+  const int k = blockIdx.x;
+  const int lm = SV.lm_of_rho[k];
+  const int rs = SV.row_start[lm], len = SV.row_start[lm + 1] - rs;
+  const int lu = SV.ulen[lm];
+  double* out = rows + boff[k];
+  double* hv = sm;
+  const int t = SV.base + k;
+  const double sr = scale[t];
+  const double d = SV.Hrr[k] * sr * sr + diag[t] * inv_radius;
+  const double sq = sqrt(1.0 / d);
+  for (int i = threadIdx.x; i < lu; i += blockDim.x) hv[i] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int p = SV.row_pos[rs + i];
+    if (p < 0) continue;
+    const double v = SV.Hrx[rs + i] * scale[p] * sr;
+    if (v != 0.0) atomicAdd(&hv[SV.slot2u[rs + i]], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < lu; i += blockDim.x) out[i] = hv[i] * sq;
+  if (threadIdx.x == 0) { out[lu] = -g[t] * sr * sq; if (((lu + 1) & 1) != 0) out[lu + 1] = 0.0; }
+}
+
 // y_r = (b_r - h . x) / d  after the reduced system has been solved
 __global__ void __launch_bounds__(128) schur_back_kernel(BandSys A, SchurView SV, const double* __restrict__ scale, const double* __restrict__ diag,
                                                          double inv_radius, const double* __restrict__ g) {
@@ -1311,6 +1341,13 @@ static size_t max_row_len(const lvi_problem* p) {
 }
 static void schur_eliminate(lvi_problem* p, double inv_radius) {
   if (p->L.n_rho == 0) return;
+  if (p->schur_gather) {   // rows only; the products go through the tile gather (fp64 tensor pipe, single-owner tiles)
+    const size_t smem_rows = max_row_len(p) * 8 + 16;
+    LVI_REQUIRE(smem_rows <= 48 * 1024, LVI_ERR_INVALID, "Schur row too long");
+    LVI_LAUNCH(p->ctx, schur_rows_kernel, p->L.n_rho, 128, smem_rows, p->A, p->schur, p->scale.p, p->diag.p, inv_radius, p->g.p, p->schur_boff.p, p->schur_rows.p);
+    assemble_schur_gather(p);
+    return;
+  }
   size_t& attr = p->ctx->ks.schur_attr;
   const size_t smem = max_row_len(p) * 12 + 16;
   if (smem > attr) { LVI_CUDA(cudaFuncSetAttribute(schur_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = smem; }
