@@ -19,12 +19,20 @@
 // diagonal tiles' P_I panels.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "problem.cuh"
 
 namespace lvi {
 
-constexpr int kChunk = 96;         // residuals per work item
-constexpr int kGatherWarps = 4;
+#ifndef LVI_GATHER_CHUNK
+#define LVI_GATHER_CHUNK 96
+#endif
+constexpr int kChunk = LVI_GATHER_CHUNK;         // residuals per work item
+#ifndef LVI_GATHER_WARPS
+#define LVI_GATHER_WARPS 4
+#endif
+constexpr int kGatherWarps = LVI_GATHER_WARPS;
 constexpr int kPanelRows = 32;
 
 // ---- plan ---------------------------------------------------------------------------------------------------------------------------
@@ -173,7 +181,10 @@ __device__ __forceinline__ void g_mbar_wait(unsigned long long* b, unsigned pari
 
 // One warp's staging area: the Jacobian blocks ([rows x ncols | r | pad], 16-byte multiples) and the descriptors of one batch of entries land
 // here by bulk async copies -- every load of the batch is in flight at once; the tensor-core fragments are then read straight out of it.
-constexpr int kStageDoubles = 2048;   // 16 cam blocks of 112, 32 surfel blocks of 56, 32 camera-surfel blocks of 62
+#ifndef LVI_STAGE_DOUBLES
+#define LVI_STAGE_DOUBLES 2048
+#endif
+constexpr int kStageDoubles = LVI_STAGE_DOUBLES;   // 2048: 16 cam blocks of 112, 32 surfel blocks of 56, 32 camera-surfel blocks of 62
 template <class DescT>
 struct WarpStage {
   alignas(128) double J[kStageDoubles];
@@ -432,7 +443,8 @@ void assemble_build_schur_plan(lvi_problem* p) {
 }
 
 static void launch_gather(lvi_problem* p, AsmPlan& A, const BandSys& target, double* g, int subtract) {
-  const int grid = std::min((A.n_items + kGatherWarps - 1) / kGatherWarps, p->ctx->sm_count * 3);
+  static const int per_sm = std::getenv("LVI_GATHER_CTAS") ? std::atoi(std::getenv("LVI_GATHER_CTAS")) : 3;
+  const int grid = std::min((A.n_items + kGatherWarps - 1) / kGatherWarps, p->ctx->sm_count * per_sm);
   if (A.desc_width == 1) {
     constexpr size_t smem = sizeof(WarpStage<unsigned char>) * kGatherWarps;
     if (!p->ctx->ks.gather_attr[0]) {
