@@ -54,6 +54,7 @@ class PipelineConfig:
     lock_traj_lidar_2nd: bool = False
     lock_traj_lidar_3rd: bool = True
     with_camera: bool = True
+    initial_guess: str = "perturbed_gt"   # or "estimate": the reference's own initial-guess stage (initguess.py)
 
 
 class TrajectoryManager:
@@ -171,6 +172,21 @@ def perturbed_initial_extrinsics(gt: dict) -> dict:
     return dict(q_LtoI=quat_mul(gt["q_LtoI"], dq), p_LinI=gt["p_LinI"] + dp, q_CtoI=quat_mul(gt["q_CtoI"], dq), p_CinI=gt["p_CinI"] + dp)
 
 
+def estimated_initial_extrinsics(seq) -> dict:
+    """EstimateInitExtrinsicLI / CI (T:1044-1148) on the sequence's LOAM key poses and its visual-odometry poses.  Where an estimate fails
+    the reference's fall-backs apply: LCIoptimize refuses to run without both (T:540-543), CIoptimize uses identity / (-0.22, 0.02, 0.22)
+    (T:520-525); here a failed entry raises."""
+    from . import initguess
+    cam_t, cam_T = seq.visual_odometry() if hasattr(seq, "visual_odometry") else (None, None)
+    g = initguess.initial_extrinsics(seq.scan_times, seq.loam_poses, cam_t, cam_T, seq.imu_t, seq.gyro, seq.accel)
+    for k in ("q_LtoI", "p_LinI") + (("q_CtoI", "p_CinI") if cam_t is not None else ()):
+        if g[k] is None:
+            raise RuntimeError(f"initial guess: {k} could not be estimated (The Camera and LiDAR should be inited first!)")
+    if cam_t is None:
+        g["q_CtoI"], g["p_CinI"] = np.array([0, 0, 0, 1.0]), np.array([-0.22, 0.02, 0.22])
+    return g
+
+
 def extrinsic_errors(calib: CalibParams, gt: dict) -> dict:
     return dict(rot_L=quat_angle(calib.q_LtoI, gt["q_LtoI"]), pos_L=float(np.linalg.norm(calib.p_LinI - gt["p_LinI"])),
                 rot_C=quat_angle(calib.q_CtoI, gt["q_CtoI"]), pos_C=float(np.linalg.norm(calib.p_CinI - gt["p_CinI"])))
@@ -210,7 +226,8 @@ def run_calibration(seq, backend, cfg: PipelineConfig | None = None, verbose: bo
     cfg = cfg or PipelineConfig()
     out = {"stages": []}
     mgr = TrajectoryManager(CameraIntrinsics(), seq.map_time, seq.end_time, cfg.knot_distance, cfg.time_offset_padding)
-    init = perturbed_initial_extrinsics(seq.gt)
+    init = perturbed_initial_extrinsics(seq.gt) if cfg.initial_guess != "estimate" else estimated_initial_extrinsics(seq)
+    out["initial_guess"] = dict(kind=cfg.initial_guess, **{k: np.asarray(init[k]).tolist() for k in ("q_LtoI", "p_LinI", "q_CtoI", "p_CinI")})
     mgr.calib.q_LtoI, mgr.calib.p_LinI, mgr.calib.q_CtoI, mgr.calib.p_CinI = init["q_LtoI"], init["p_LinI"], init["q_CtoI"], init["p_CinI"]
     mgr.feed_imu(seq.imu_t, seq.gyro, seq.accel)
     map_time = seq.map_time

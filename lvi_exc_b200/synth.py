@@ -85,6 +85,30 @@ class Sequence:
     def end_time(self) -> float:
         return float(self.scan_times[-1] + 1.0 / self.cfg.scan_rate)
 
+    def visual_odometry(self, scale: float = 2.5):
+        """ORB-SLAM stand-in (`FramePose` of the reference's input): camera pose of every view in the first view's frame, translation
+        UP TO SCALE (metric / `scale`), from the ground-truth kinematics -> (stamps [V], poses [V, 4, 4])"""
+        if len(self.view_t0) == 0:
+            return None, None
+        def T_of(q, p):
+            x, y, z, w = q
+            T = np.eye(4)
+            T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+            T[:3, 3] = p
+            return T
+        T_IC = T_of(self.gt["q_CtoI"], self.gt["p_CinI"])
+        t0 = float(self.view_t0[0])
+        Ts = []
+        for t in self.view_t0:
+            st = gt_state(self.cfg, t0, float(t))
+            Ts.append(T_of(st["q"], st["p"]) @ T_IC)
+        inv0 = np.linalg.inv(Ts[0])
+        out = np.stack([inv0 @ T for T in Ts])
+        out[:, :3, 3] /= scale
+        return np.asarray(self.view_t0, dtype=np.float64), out
+
 
 def gt_extrinsics() -> dict:
     q_l, p_l, q_c, p_c, bg, ba = (np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3), np.zeros(3), np.zeros(3))

@@ -250,3 +250,20 @@ def test_pipeline_matches_oracle(cuda_backend):
     assert [s["iterations"] for s in og["stages"]] == [s["iterations"] for s in oo["stages"]]
     for a, b in zip(og["stages"], oo["stages"]):
         assert a["final_cost"] == pytest.approx(b["final_cost"], rel=1e-5)
+
+
+def test_self_starting_pipeline_matches_oracle(cuda_backend):
+    """the same replay started from the reference's own initial-guess stage (initguess.py: pre-integration, hand-eye rotation, linear
+    alignment; ~1 m translation error at the start) instead of the perturbed ground truth: CUDA and CPU paths walk the same stages"""
+    cfg = synth.default_config(duration=6.0, n_landmarks=800)
+    seq = synth.make_sequence(cfg)
+    pc = pipeline.PipelineConfig(initial_guess="estimate")
+    og = pipeline.run_calibration(seq, cuda_backend, pc)
+    oo = pipeline.run_calibration(seq, OracleBackend(), pc)
+    cg, co = og["calib"], oo["calib"]
+    assert og["initial_guess"] == oo["initial_guess"] and og["assoc_counts"] == oo["assoc_counts"]
+    assert pipeline.quat_angle(cg.q_LtoI, co.q_LtoI) < 1e-4 and np.linalg.norm(cg.p_LinI - co.p_LinI) < 1e-3
+    assert pipeline.quat_angle(cg.q_CtoI, co.q_CtoI) < 1e-4 and np.linalg.norm(cg.p_CinI - co.p_CinI) < 1e-3
+    assert [s["iterations"] for s in og["stages"]] == [s["iterations"] for s in oo["stages"]]
+    e = pipeline.extrinsic_errors(cg, seq.gt)
+    assert e["rot_L"] < 5e-3 and e["pos_L"] < 0.05 and e["rot_C"] < 5e-3 and e["pos_C"] < 0.05
