@@ -196,3 +196,42 @@ def test_sequence_initial_guess_rotation_close_translation_rough():
     assert pipeline.quat_angle(g["q_CtoI"], seq.gt["q_CtoI"]) < np.radians(0.5)
     assert np.linalg.norm(g["p_LinI"] - seq.gt["p_LinI"]) < 3.0 and np.linalg.norm(g["p_CinI"] - seq.gt["p_CinI"]) < 3.0
     assert g["scale"] > 0 and g["gravity_lidar"][3] == pytest.approx(seq.scan_times[0])
+
+
+def test_cpp_vi_init_headers_match(tmp_path):
+    """the C++ side of the stage (include/lvi_exc_b200/compat/vi_init/*.h: IntegrationBase, InitialEXRotation, VisualIMUAlignment under the
+    reference's include paths) driven through the reference's own call sequence (tests/cpp/initguess_check.cpp restates
+    ComputeIntegrationForFrames / EstimateInitExtrinsicLI / CI, T:952-1148) gives the Python stage's numbers on the synthetic sequence"""
+    import json
+    import struct
+    import subprocess
+    from pathlib import Path
+    from lvi_exc_b200 import synth
+    root = Path(__file__).resolve().parent.parent
+    compat = root / "include" / "lvi_exc_b200" / "compat"
+    exe = root / "build" / "initguess_check"
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(compat), str(root / "tests" / "cpp" / "initguess_check.cpp"), "-o", str(exe)], check=True)
+    seq = synth.make_sequence(synth.default_config(duration=6.0, n_landmarks=50))
+    keys = ig.select_key_poses(seq.scan_times, seq.loam_poses)
+    cam_t, cam_T = seq.visual_odometry()
+    blob = tmp_path / "init.bin"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<4i", 0x4C564932, len(keys), len(cam_t), len(seq.imu_t)))
+        f.write(np.array([k.timestamp for k in keys]).tobytes())
+        f.write(np.stack([k.T for k in keys]).tobytes())
+        f.write(np.ascontiguousarray(cam_t).tobytes())
+        f.write(np.ascontiguousarray(cam_T).tobytes())
+        for a in (seq.imu_t, seq.gyro, seq.accel):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    r = subprocess.run([str(exe), str(blob)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c = json.loads(r.stdout)
+    p = ig.initial_extrinsics(seq.scan_times, seq.loam_poses, cam_t, cam_T, seq.imu_t, seq.gyro, seq.accel)
+    for name, q, t, g in (("lidar", p["q_LtoI"], p["p_LinI"], p["gravity_lidar"]), ("camera", p["q_CtoI"], p["p_CinI"], p["gravity_cam"])):
+        assert c[name]["rot_ok"] == 1 and c[name]["ok"] == 1
+        qc = np.array(c[name]["q"])
+        assert min(np.abs(qc - q).max(), np.abs(qc + q).max()) < 1e-9
+        assert np.abs(np.array(c[name]["T"]) - t).max() < 1e-7
+        assert np.abs(np.array(c[name]["g"]) - g).max() < 1e-7
+    assert c["camera"]["scale"] == pytest.approx(p["scale"], rel=1e-8)
