@@ -196,6 +196,7 @@ def kernel_rooflines(times: dict, peaks: dict, peak_kind: str, n_points: int, n_
         ("voxel build (all kernels)", ("voxel_", "cub_radix_sort_runs", "cub_scan_runs"), 12 * n_points + 200 * n_leaves, "12 B read per point + 200 B written per leaf"),
         ("voxel_runs_kernel", ("voxel_runs_kernel",), 12 * n_points, "12 B read per point"),
         ("voxel_gather_kernel", ("voxel_gather_kernel",), 24 * n_points, "12 B read + 12 B written per point"),
+        ("surfel_fit kernels", ("surfel_fit",), 12 * n_points, "12 B read per point of a candidate leaf (every leaf at C3), RANSAC passes on chip"),
         ("assoc_hit_kernel", ("assoc_hit_kernel",), 16 * n_points, "12 B read + 4 B written per point"),
         ("association (all kernels)", ("assoc_",), 12 * n_points + 84 * n_selected, "12 B read per point + 20 B read / 64 B written per selected point"),
         ("jacobian_kernel<RT_SURFEL>", ("jacobian_kernel<RT_SURFEL>",), 8 * 56 * n_res.get("surfel", 0) + JAC_BYTES["surfel"] * n_res.get("surfel", 0) // 4, "record + plane read, fp64 J block (54 + r, padded) written per residual"),
@@ -267,6 +268,7 @@ def run_c3(args, rank: int, local_rank: int, world: int):
         batch = backend.undistort(mgr._base(), raw_d, seq.map_time, True)
         smap = backend.build_surfel_map(backend.map_cloud(batch), pc.ndt_resolution, pc.plane_lambda_refine)
         sp = backend.associate(smap, batch, raw_d, pc.associated_radius, pc.k_per_ring, pc.time_downsample)
+        smap.planes_Pi   # the closest points of the planes go to the host with the associated points (the residual tables carry them)
         return batch, smap, sp
 
     for _ in range(max(args.warmup, 3)):
@@ -372,6 +374,8 @@ def run_c4(args, rank: int, local_rank: int, world: int):
         batch = backend.undistort(mgr._base(), raw_d, seq.map_time, True)
         smap = backend.build_surfel_map_sharded(backend.map_cloud(batch), pc.ndt_resolution, pc.plane_lambda_refine)
         sp = backend.associate_sharded(smap, batch, raw_d, pc.associated_radius, pc.k_per_ring, pc.time_downsample, total_points=S * H * W, download=download)
+        if download:
+            smap.planes_Pi   # end to end: the planes' closest points reach the host with the associated points
         return batch, smap, sp
 
     for _ in range(max(args.warmup, 3)):

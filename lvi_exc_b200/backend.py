@@ -66,6 +66,8 @@ class CudaSurfelMap:
         self.vmap = C.c_void_p()
         self.surfels = C.c_void_p()
         self.shard_stats = None
+        self._planes = None
+        self._Pi = None
         if isinstance(cloud, CudaScanBatch):
             cloud = CudaMapCloud(cloud, None)
         if sharded:   # every rank passes the scans of its own time chunk: grid, leaves and planes are those of the whole cloud
@@ -76,8 +78,6 @@ class CudaSurfelMap:
             self.shard_stats = dict(points_sent=int(st[0]), points_received=int(st[1]), leaves_built=int(st[2]), planes_built=int(st[3]))
             self.num_leaves = lib.lvi_voxel_num_leaves(self.vmap)
             self.num_planes = lib.lvi_surfel_count(self.surfels)
-            self.planes = self.export_planes()
-            self.planes_Pi = self.planes["Pi"]
             return
         if isinstance(cloud, CudaMapCloud):
             check(lib.lvi_voxel_build_batch(backend.ctx, cloud.batch.h, ptr(cloud.keep), leaf, min_points, eig_mult, C.byref(self.vmap)))
@@ -89,8 +89,24 @@ class CudaSurfelMap:
         self._keep = None  # the map keeps its own sorted copy of the points
         self.num_leaves = lib.lvi_voxel_num_leaves(self.vmap)
         self.num_planes = lib.lvi_surfel_count(self.surfels)
-        self.planes = self.export_planes()
-        self.planes_Pi = self.planes["Pi"]
+
+    # The plane tables stay on the device (association reads them there); the host copies are made when somebody asks: `planes_Pi` (the
+    # closest points the residual tables carry) downloads 24 B per plane, `planes` everything (116 B per plane).
+    @property
+    def planes_Pi(self) -> np.ndarray:
+        if self._Pi is None:
+            if self._planes is not None:
+                self._Pi = self._planes["Pi"]
+            else:
+                self._Pi = np.zeros((self.num_planes, 3))
+                check(self.b.lib.lvi_surfel_export(self.b.ctx, self.surfels, None, ptr(self._Pi), None, None, None, None))
+        return self._Pi
+
+    @property
+    def planes(self) -> dict:
+        if self._planes is None:
+            self._planes = self.export_planes()
+        return self._planes
 
     def export_planes(self) -> dict:
         P = self.num_planes

@@ -66,7 +66,14 @@ __global__ void __launch_bounds__(256) assoc_plane_rec_kernel(const double* __re
   rec[i] = r;
 }
 
-constexpr int kHitIlp = 4;
+// cell -> plane in one step: the dense cell2leaf table of the map composed with the surfel set's leaf2plane (built once per surfel set,
+// association_tables()), so the per-point chain is point -> cell2plane -> plane record
+__global__ void __launch_bounds__(256) assoc_cell2plane_kernel(const int32_t* __restrict__ plane_key, int n_planes, int32_t* __restrict__ table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_planes) table[plane_key[i]] = i;
+}
+
+template <bool DIRECT, int kHitIlp, bool EAGER>
 __global__ void __launch_bounds__(256) assoc_hit_kernel(const char* __restrict__ scan_map, size_t stride, int64_t n, const GridParams* __restrict__ gp,
                                                         const int32_t* __restrict__ cell2leaf, const int32_t* __restrict__ leaf_key, int n_leaves,
                                                         const int32_t* __restrict__ leaf2plane, const PlaneRec* __restrict__ planes, double radius,
@@ -76,35 +83,62 @@ __global__ void __launch_bounds__(256) assoc_hit_kernel(const char* __restrict__
   __syncthreads();
   const bool vec = (stride % 16 == 0) && ((reinterpret_cast<size_t>(scan_map) & 15) == 0);
   const int64_t span = static_cast<int64_t>(blockDim.x) * kHitIlp;
-  for (int64_t c0 = blockIdx.x * span; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * span) {
-    float x[kHitIlp], y[kHitIlp], z[kHitIlp];
-    int leaf[kHitIlp], pl[kHitIlp];
+  const float nanv = __int_as_float(0x7fc00000);
+  auto load = [&](int64_t c0, float (&x)[kHitIlp], float (&y)[kHitIlp], float (&z)[kHitIlp]) {
 #pragma unroll
     for (int u = 0; u < kHitIlp; ++u) {
       const int64_t i = c0 + threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
-      x[u] = y[u] = z[u] = __int_as_float(0x7fc00000);
+      x[u] = y[u] = z[u] = nanv;
       if (i < n) {
         if (vec) { const float4 v = __ldcs(reinterpret_cast<const float4*>(scan_map + i * stride)); x[u] = v.x; y[u] = v.y; z[u] = v.z; }   // streamed: L2 stays with the tables
         else { const float* p = reinterpret_cast<const float*>(scan_map + i * stride); x[u] = p[0]; y[u] = p[1]; z[u] = p[2]; }
       }
     }
+  };
+  // the points of the NEXT chunk are requested before the dependent look-ups of the current one start, so the HBM stream never waits for
+  // the table chain (point -> cell -> plane record)
+  float xn[kHitIlp], yn[kHitIlp], zn[kHitIlp];
+  const int64_t step = static_cast<int64_t>(gridDim.x) * span;
+  if (blockIdx.x * span < n) load(blockIdx.x * span, xn, yn, zn);
+  for (int64_t c0 = blockIdx.x * span; c0 < n; c0 += step) {
+    float x[kHitIlp], y[kHitIlp], z[kHitIlp];
+    int pl[kHitIlp];
 #pragma unroll
-    for (int u = 0; u < kHitIlp; ++u) leaf[u] = lookup_leaf(g, cell2leaf, leaf_key, n_leaves, x[u], y[u], z[u]);
+    for (int u = 0; u < kHitIlp; ++u) { x[u] = xn[u]; y[u] = yn[u]; z[u] = zn[u]; }
+    if (c0 + step < n) load(c0 + step, xn, yn, zn);
+    if (DIRECT) {   // cell2leaf IS the cell -> plane table
 #pragma unroll
-    for (int u = 0; u < kHitIlp; ++u) pl[u] = leaf[u] >= 0 ? __ldg(leaf2plane + leaf[u]) : -1;
+      for (int u = 0; u < kHitIlp; ++u) pl[u] = lookup_leaf(g, cell2leaf, nullptr, 0, x[u], y[u], z[u]);
+    } else {
+      int leaf[kHitIlp];
+#pragma unroll
+      for (int u = 0; u < kHitIlp; ++u) leaf[u] = lookup_leaf(g, cell2leaf, leaf_key, n_leaves, x[u], y[u], z[u]);
+#pragma unroll
+      for (int u = 0; u < kHitIlp; ++u) pl[u] = leaf[u] >= 0 ? __ldg(leaf2plane + leaf[u]) : -1;
+    }
+    float4 r0[kHitIlp], r1[kHitIlp], r2[kHitIlp];
+    if (EAGER) {
+#pragma unroll
+      for (int u = 0; u < kHitIlp; ++u) {   // all plane records in flight before the first test
+        const float4* r = reinterpret_cast<const float4*>(planes + max(pl[u], 0));
+        r0[u] = __ldg(r); r1[u] = __ldg(r + 1); r2[u] = __ldg(r + 2);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < kHitIlp; ++u) {
       const int64_t i = c0 + threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
       if (i >= n) continue;
       int res = -1;
       if (pl[u] >= 0) {
-        const float4* r = reinterpret_cast<const float4*>(planes + pl[u]);
-        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-        if (x[u] > r0.x && x[u] < r1.x && y[u] > r0.y && y[u] < r1.y && z[u] > r0.z && z[u] < r1.z) {
-          double d = static_cast<double>(x[u]) * static_cast<double>(r0.w);   // point2PlaneDistance :296-303, in its order
-          d = d + static_cast<double>(y[u]) * static_cast<double>(r1.w);
-          d = d + static_cast<double>(z[u]) * static_cast<double>(r2.x);
-          d = d + static_cast<double>(r2.y);
+        if (!EAGER) {
+          const float4* r = reinterpret_cast<const float4*>(planes + pl[u]);
+          r0[u] = __ldg(r); r1[u] = __ldg(r + 1); r2[u] = __ldg(r + 2);
+        }
+        if (x[u] > r0[u].x && x[u] < r1[u].x && y[u] > r0[u].y && y[u] < r1[u].y && z[u] > r0[u].z && z[u] < r1[u].z) {
+          double d = static_cast<double>(x[u]) * static_cast<double>(r0[u].w);   // point2PlaneDistance :296-303, in its order
+          d = d + static_cast<double>(y[u]) * static_cast<double>(r1[u].w);
+          d = d + static_cast<double>(z[u]) * static_cast<double>(r2[u].x);
+          d = d + static_cast<double>(r2[u].y);
           if ((d > 0 ? d : -d) <= radius) res = pl[u];
         }
       }
@@ -473,8 +507,27 @@ static void associate_device(lvi_ctx* ctx, const lvi_voxel_map* m, const lvi_sur
   DBuf<int32_t> cand(n);
   DBuf<PlaneRec> prec(static_cast<size_t>(s->n_planes));
   LVI_LAUNCH(ctx, assoc_plane_rec_kernel, static_cast<int>((s->n_planes + 255) / 256), 256, 0, s->p4.p, s->bmin.p, s->bmax.p, static_cast<int>(s->n_planes), prec.p);
-  LVI_LAUNCH(ctx, assoc_hit_kernel, grid_for(n, 256 * kHitIlp, ctx->sm_count, 8), 256, 0, static_cast<const char*>(map_d), stride, n, m->grid_d.p,
-             m->cell2leaf.n ? m->cell2leaf.p : nullptr, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p, prec.p, radius, cand.p);
+  static const int variant = std::getenv("LVI_ASSOC_HIT_VARIANT") ? std::atoi(std::getenv("LVI_ASSOC_HIT_VARIANT")) : 0;
+  const char* map_c = static_cast<const char*>(map_d);
+  const int32_t* nul = nullptr;
+#define LVI_HIT(D, I, E, c2l, lk, nl, l2p) \
+  LVI_LAUNCH_AS(ctx, "assoc_hit_kernel", (assoc_hit_kernel<D, I, E>), grid_for(n, 256 * I, ctx->sm_count, 8), 256, 0, map_c, stride, n, m->grid_d.p, c2l, lk, nl, l2p, prec.p, radius, cand.p)
+  if (m->cell2leaf.n && variant != 9) {
+    if (s->cell2plane.n != m->cell2leaf.n) {   // first association with this surfel set
+      s->cell2plane.alloc(m->cell2leaf.n);
+      LVI_CUDA(cudaMemsetAsync(s->cell2plane.p, 0xff, sizeof(int32_t) * s->cell2plane.n, st));
+      LVI_LAUNCH(ctx, assoc_cell2plane_kernel, static_cast<int>((s->n_planes + 255) / 256), 256, 0, s->key.p, static_cast<int>(s->n_planes), s->cell2plane.p);
+    }
+    if (variant == 1) LVI_HIT(true, 8, true, s->cell2plane.p, nul, 0, nul);
+    else if (variant == 2) LVI_HIT(true, 8, false, s->cell2plane.p, nul, 0, nul);
+    else if (variant == 3) LVI_HIT(true, 2, true, s->cell2plane.p, nul, 0, nul);
+    else if (variant == 4) LVI_HIT(true, 2, false, s->cell2plane.p, nul, 0, nul);
+    else if (variant == 5) LVI_HIT(true, 4, true, s->cell2plane.p, nul, 0, nul);
+    else LVI_HIT(true, 4, false, s->cell2plane.p, nul, 0, nul);
+  } else {
+    LVI_HIT(false, 4, false, m->cell2leaf.n ? m->cell2leaf.p : nul, m->leaf_key.p, static_cast<int>(m->n_leaves), s->leaf2plane.p);
+  }
+#undef LVI_HIT
   if (static_cast<int64_t>(W) * H <= kScanSelMaxPts && !std::getenv("LVI_ASSOC_UNFUSED")) {   // selection + emission order of a scan inside one CTA
     const int HW = W * H;
     const size_t smem = static_cast<size_t>((HW + 31) / 32) * 4 + static_cast<size_t>(kScanSelWarps) * kSelHash * 12;

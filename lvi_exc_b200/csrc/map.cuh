@@ -41,13 +41,15 @@ struct ScanMinMax {
   __device__ __forceinline__ void flush(int* __restrict__ mm) const {
     if (scan < 0 || !(mn0 <= mx0)) return;
     int* m = mm + 6 * scan;
+    // the six slots are read together (one round trip to L2, not six dependent ones) before any of them is compared
+    const int2 c01 = __ldcg(reinterpret_cast<const int2*>(m)), c23 = __ldcg(reinterpret_cast<const int2*>(m) + 1), c45 = __ldcg(reinterpret_cast<const int2*>(m) + 2);
     int o;
-    o = f2ord(mn0); if (o < m[0]) atomicMin(m + 0, o);
-    o = f2ord(mn1); if (o < m[1]) atomicMin(m + 1, o);
-    o = f2ord(mn2); if (o < m[2]) atomicMin(m + 2, o);
-    o = f2ord(mx0); if (o > m[3]) atomicMax(m + 3, o);
-    o = f2ord(mx1); if (o > m[4]) atomicMax(m + 4, o);
-    o = f2ord(mx2); if (o > m[5]) atomicMax(m + 5, o);
+    o = f2ord(mn0); if (o < c01.x) atomicMin(m + 0, o);
+    o = f2ord(mn1); if (o < c01.y) atomicMin(m + 1, o);
+    o = f2ord(mn2); if (o < c23.x) atomicMin(m + 2, o);
+    o = f2ord(mx0); if (o > c23.y) atomicMax(m + 3, o);
+    o = f2ord(mx1); if (o > c45.x) atomicMax(m + 4, o);
+    o = f2ord(mx2); if (o > c45.y) atomicMax(m + 5, o);
   }
   __device__ __forceinline__ void add(int* __restrict__ mm, int64_t s, float x, float y, float z) {
     if (s != scan) { flush(mm); reset(s); }
@@ -121,4 +123,5 @@ struct lvi_surfel_set {
   lvi::DBuf<int32_t> key;      // [P] voxel linear index of the leaf
   lvi::DBuf<int32_t> ninl;     // [P]
   lvi::DBuf<int32_t> leaf2plane;  // [L] plane id or -1
+  mutable lvi::DBuf<int32_t> cell2plane;   // dense cell -> plane table (cell2leaf composed with leaf2plane), built by the first association
 };

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include "eig3.cuh"
+#include <cstdlib>
 #include <memory>
 
 #include "map.cuh"
@@ -123,7 +124,7 @@ __device__ __forceinline__ float block_min_float(float v, float* sh) {
 
 __global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start,
                                                                  const int32_t* __restrict__ leaf_key, const int32_t* __restrict__ cand, int n_cand,
-                                                                 float thr, int min_inliers, FitOut* __restrict__ out) {
+                                                                 float thr, int min_inliers, uint32_t small_max, FitOut* __restrict__ out) {
   __shared__ int shi[4];
   __shared__ unsigned shu[4];
   __shared__ double shd[4];
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* _
     const int leaf = cand[ci];
     const int beg = leaf_start[leaf];
     const uint32_t n = static_cast<uint32_t>(leaf_start[leaf + 1] - beg);
+    if (n <= small_max) continue;   // surfel_fit_warp_kernel's
     const float4* P = pts + beg;
     FitOut fo;
     fo.ok = 0; fo.ninl = 0;
@@ -237,6 +239,147 @@ __global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* _
   }
 }
 
+// Small leaves (<= kWarpFitMax points: every leaf of a map with 10^5 .. 10^6 surfels): ONE WARP per leaf with the leaf's points staged once
+// in the warp's slice of shared memory (coalesced, all loads in flight together), so a RANSAC pass is a short rolled loop over conflict-free
+// shared-memory reads and one warp reduction -- no block barrier, no second trip to L1/L2, and a code footprint that stays in the
+// instruction cache (the first version kept the points in registers with every pass unrolled 24x: 14 of 35 k stall samples were
+// instruction fetches).  Same specification as surfel_fit_kernel (counts are integers; the fp64 PCA sums are rounded to float before they
+// are used), which keeps the larger leaves.
+constexpr int kWarpFitMax = 768;
+__device__ __forceinline__ double warp_sum_double(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(kFitThreads) surfel_fit_warp_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start,
+                                                                      const int32_t* __restrict__ leaf_key, const int32_t* __restrict__ cand, int n_cand,
+                                                                      float thr, int min_inliers, FitOut* __restrict__ out) {
+  __shared__ float s_xyz[kFitThreads / 32][3][kWarpFitMax];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = (gridDim.x * kFitThreads) >> 5;
+  float* sx = s_xyz[warp][0]; float* sy = s_xyz[warp][1]; float* sz = s_xyz[warp][2];
+  for (int ci = (blockIdx.x * kFitThreads + threadIdx.x) >> 5; ci < n_cand; ci += n_warps) {
+    const int leaf = cand[ci];
+    const int beg = leaf_start[leaf];
+    const uint32_t n = static_cast<uint32_t>(leaf_start[leaf + 1] - beg);
+    if (n > static_cast<uint32_t>(kWarpFitMax)) continue;   // surfel_fit_kernel's
+    const float4* P = pts + beg;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) { const float4 p = __ldg(P + i); sx[i] = p.x; sy[i] = p.y; sz[i] = p.z; }
+    __syncwarp();
+    auto count_inliers = [&](float c0, float c1, float c2, float c3) {
+      int count = 0;
+      for (uint32_t i = lane; i < n; i += 32) {
+        float t = c0 * sx[i];
+        t = t + c1 * sy[i];
+        t = t + c2 * sz[i];
+        t = t + c3;
+        count += fabsf(t) < thr ? 1 : 0;
+      }
+      return __reduce_add_sync(0xffffffffu, count);
+    };
+    FitOut fo;
+    fo.ok = 0; fo.ninl = 0;
+    for (int k = 0; k < 4; ++k) fo.p4[k] = 0;
+    for (int k = 0; k < 3; ++k) { fo.bmin[k] = 0; fo.bmax[k] = 0; }
+    bool fail = n < 3;
+    float best[4] = {0, 0, 0, 0};
+    int best_count = 0;
+    if (!fail) {
+      const int max_iterations = 50;
+      const double log_probability = log(1.0 - 0.99);
+      const double one_over_n = 1.0 / static_cast<double>(n);
+      const uint64_t seed = mix64(static_cast<uint64_t>(static_cast<uint32_t>(leaf_key[leaf])) * 0x2545F4914F6CDD1Dull + 12345ull);
+      double k = 1.0;
+      int iterations = 0, skipped = 0;
+      uint32_t attempt = 0;
+      const int max_skip = max_iterations * 10;
+      while (iterations < k && skipped < max_skip) {
+        uint32_t a = draw(seed, attempt, 0, n);
+        uint32_t b = draw(seed, attempt, 1, n - 1);
+        uint32_t c = draw(seed, attempt, 2, n - 2);
+        ++attempt;
+        if (b >= a) ++b;
+        const uint32_t lo = min(a, b), hi = max(a, b);
+        if (c >= lo) ++c;
+        if (c >= hi) ++c;
+        float coef[4];
+        if (!model_from3(make_float4(sx[a], sy[a], sz[a], 0.f), make_float4(sx[b], sy[b], sz[b], 0.f), make_float4(sx[c], sy[c], sz[c], 0.f), coef)) { ++skipped; continue; }
+        const int count = count_inliers(coef[0], coef[1], coef[2], coef[3]);
+        if (count > best_count) {
+          best_count = count;
+          best[0] = coef[0]; best[1] = coef[1]; best[2] = coef[2]; best[3] = coef[3];
+          const double w = static_cast<double>(count) * one_over_n;
+          double p_no = 1.0 - w * w * w;
+          p_no = fmax(2.220446049250313e-16, p_no);
+          p_no = fmin(1.0 - 2.220446049250313e-16, p_no);
+          k = log_probability / log(p_no);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+      }
+      if (best_count == 0) fail = true;
+    }
+    float fin[4] = {best[0], best[1], best[2], best[3]};
+    if (!fail && best_count > 3) {
+      uint32_t first = 0xffffffffu;
+      for (uint32_t i = lane; i < n && first == 0xffffffffu; i += 32)
+        if (plane_dist(best, make_float4(sx[i], sy[i], sz[i], 0.f)) < thr) first = i;
+      first = __reduce_min_sync(0xffffffffu, first);
+      const double x0 = sx[first], y0 = sy[first], z0 = sz[first];
+      double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int cnt = 0;
+      for (uint32_t i = lane; i < n; i += 32) {
+        const float4 p = make_float4(sx[i], sy[i], sz[i], 0.f);
+        if (!(plane_dist(best, p) < thr)) continue;
+        const double dx = static_cast<double>(p.x) - x0, dy = static_cast<double>(p.y) - y0, dz = static_cast<double>(p.z) - z0;
+        sums[0] += dx; sums[1] += dy; sums[2] += dz;
+        sums[3] += dx * dx; sums[4] += dx * dy; sums[5] += dx * dz; sums[6] += dy * dy; sums[7] += dy * dz; sums[8] += dz * dz;
+        ++cnt;
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) sums[q] = warp_sum_double(sums[q]);
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      const double inv_n = 1.0 / cnt;
+      const double m0 = sums[0] * inv_n, m1 = sums[1] * inv_n, m2 = sums[2] * inv_n;
+      const float cf0 = static_cast<float>(x0 + m0), cf1 = static_cast<float>(y0 + m1), cf2 = static_cast<float>(z0 + m2);
+      const float cv0 = static_cast<float>(sums[3] * inv_n - m0 * m0), cv1 = static_cast<float>(sums[4] * inv_n - m0 * m1),
+                  cv2 = static_cast<float>(sums[5] * inv_n - m0 * m2), cv3 = static_cast<float>(sums[6] * inv_n - m1 * m1),
+                  cv4 = static_cast<float>(sums[7] * inv_n - m1 * m2), cv5 = static_cast<float>(sums[8] * inv_n - m2 * m2);
+      const double A[9] = {cv0, cv1, cv2, cv1, cv3, cv4, cv2, cv4, cv5};
+      double ev[3], V[9];
+      jacobi3_lower(A, ev, V);
+      const double nx = V[0], ny = V[3], nz = V[6];
+      double d = nx * static_cast<double>(cf0);
+      d = d + ny * static_cast<double>(cf1);
+      d = d + nz * static_cast<double>(cf2);
+      fin[0] = static_cast<float>(nx); fin[1] = static_cast<float>(ny); fin[2] = static_cast<float>(nz);
+      fin[3] = static_cast<float>(-d);
+    }
+    if (!fail) {
+      int cnt2 = 0;
+      float mn0 = 3.402823466e38f, mn1 = mn0, mn2 = mn0, mx0 = -mn0, mx1 = -mn0, mx2 = -mn0;
+      for (uint32_t i = lane; i < n; i += 32) {
+        const float4 p = make_float4(sx[i], sy[i], sz[i], 0.f);
+        cnt2 += plane_dist(fin, p) < thr ? 1 : 0;
+        mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
+        mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
+      }
+      cnt2 = __reduce_add_sync(0xffffffffu, cnt2);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o)); mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+      }
+      fo.ninl = cnt2;
+      fo.ok = cnt2 >= min_inliers;
+      for (int k = 0; k < 4; ++k) fo.p4[k] = fin[k];
+      fo.bmin[0] = mn0; fo.bmin[1] = mn1; fo.bmin[2] = mn2; fo.bmax[0] = mx0; fo.bmax[1] = mx1; fo.bmax[2] = mx2;
+    }
+    if (lane == 0) out[ci] = fo;
+  }
+}
+
 __global__ void __launch_bounds__(256) surfel_flag_ok_kernel(const FitOut* __restrict__ fit, int n, int32_t* __restrict__ flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = fit[i].ok;
@@ -298,8 +441,15 @@ int lvi_surfel_extract(lvi_ctx* ctx, const lvi_voxel_map* m, double lambda, int 
     DBuf<int32_t> cand(n_cand);
     LVI_LAUNCH(ctx, surfel_scatter_ids_kernel, (L + 255) / 256, 256, 0, flag.p, pos.p, L, cand.p);
     DBuf<FitOut> fit(n_cand);
+    // leaves of up to 768 points: one warp each, points in registers; larger ones: one CTA each (both kernels walk the candidate list and
+    // take their own leaves).  LVI_SURFEL_WARP_FIT=0 sends every leaf through the CTA kernel (diagnostics).
+    static const bool warp_fit = !(std::getenv("LVI_SURFEL_WARP_FIT") && std::atoi(std::getenv("LVI_SURFEL_WARP_FIT")) == 0);
+    const uint32_t small_max = warp_fit ? static_cast<uint32_t>(kWarpFitMax) : 0u;
+    if (warp_fit)
+      LVI_LAUNCH(ctx, surfel_fit_warp_kernel, std::min((n_cand + 3) / 4, ctx->sm_count * 24), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
+                 m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, fit.p);
     LVI_LAUNCH(ctx, surfel_fit_kernel, std::min(n_cand, ctx->sm_count * 16), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
-               m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, fit.p);
+               m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, small_max, fit.p);
     DBuf<int32_t> okf(n_cand), okpos(n_cand);
     LVI_LAUNCH(ctx, surfel_flag_ok_kernel, (n_cand + 255) / 256, 256, 0, fit.p, n_cand, okf.p);
     const int P = exclusive_scan_count(ctx, okf.p, okpos.p, n_cand);

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool lidar_pose(const TrajView& T, double t, Q4& q, V
   return true;
 }
 
-struct TargetPose { Q4 q; V3 p; int ok; int pad; };
+struct TargetPose { Q4 q; V3 p; int ok; int pad; double c[13]; };   // c = R(q)^T row-major (9), p (3), ok as a double: what the per-point kernel reads
 
 __global__ void undistort_target_kernel(TrajView T, const double* __restrict__ target_time, int n_scans, TargetPose* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,48 +61,174 @@ __global__ void undistort_target_kernel(TrajView T, const double* __restrict__ t
   TargetPose tp;
   tp.q = q4(0, 0, 0, 1); tp.p = v3(0, 0, 0); tp.pad = 0;
   tp.ok = lidar_pose(T, target_time[s], tp.q, tp.p) ? 1 : 0;
+  const M3 R = qmat(tp.q);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) tp.c[3 * r + c] = R.m[3 * c + r];
+  tp.c[9] = tp.p.x; tp.c[10] = tp.p.y; tp.c[11] = tp.p.z; tp.c[12] = tp.ok ? 1.0 : 0.0;
   out[s] = tp;
 }
+
+// ---- the per-point pose of the de-skew kernel -----------------------------------------------------------------------------------------------
+// undistort_kernel is bound by the fp64 pipe, not by HBM (one cumulative-SO3 pose per point), so its arithmetic is written out with explicit
+// fused multiply-adds (the file is compiled with -fmad=false for the float 4x4 path) and stripped of everything that does not depend on the
+// point's own stamp:
+//   * the knot-to-knot logs come as (unit axis, half angle) per knot (so3_axis_kernel): exp(B~_j(u) h_j) = (sin(B~_j a_j) n_j, cos(B~_j a_j))
+//     -- no square root and no division per point, and B~_j a_j < 0.25 rad for any trajectory a 0.02 s spline can follow, where sin / cos are
+//     short Taylor polynomials (|error| < 3e-18); larger angles take sincos();
+//   * the point is moved by matrices that are constant per call (R_L, p_L) or per scan (R_0^T, p_0 of the target pose):
+//       out = R_0^T [ R_I(t) (R_L x + p_L) + p_I(t) - p_0 ]            (rotation only: out = R_0^T R_I(t) R_L x),
+//     which is q_0^-1 (q_I q_L) x + q_0^-1 (q_I p_L + p_I - p_0) of the reference (scan_undistortion.h:150-170) with one quaternion rotation per
+//     point instead of three products and three rotations.
+__global__ void so3_axis_kernel(const double* __restrict__ hlog, int n, double* __restrict__ hax /* [n*4]: n_x n_y n_z a */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3 h = v3(hlog[3 * i], hlog[3 * i + 1], hlog[3 * i + 2]);
+  const double a = sqrt(dot(h, h));
+  const double inv = a > 0.0 ? 1.0 / a : 0.0;
+  hax[4 * i] = h.x * inv; hax[4 * i + 1] = h.y * inv; hax[4 * i + 2] = h.z * inv; hax[4 * i + 3] = a;
+}
+
+__device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
+  if (fabs(x) < 0.25) {
+    const double x2 = x * x;
+    double p = -2.5052108385441720e-08;                 // -1/11!
+    p = fma(p, x2, 2.7557319223985893e-06);             //  1/9!
+    p = fma(p, x2, -1.9841269841269841e-04);            // -1/7!
+    p = fma(p, x2, 8.3333333333333332e-03);             //  1/5!
+    p = fma(p, x2, -1.6666666666666666e-01);            // -1/3!
+    sn = fma(x * x2, p, x);
+    double c = 2.0876756987868100e-09;                  //  1/12!
+    c = fma(c, x2, -2.7557319223985888e-07);            // -1/10!
+    c = fma(c, x2, 2.4801587301587302e-05);             //  1/8!
+    c = fma(c, x2, -1.3888888888888889e-03);            // -1/6!
+    c = fma(c, x2, 4.1666666666666664e-02);             //  1/4!
+    c = fma(c, x2, -0.5);
+    cs = fma(c, x2, 1.0);
+  } else {
+    sincos(x, &sn, &cs);
+  }
+}
+
+__device__ __forceinline__ Q4 qmul_fma(const Q4& a, const Q4& b) {
+  Q4 r;
+  r.x = fma(a.w, b.x, fma(a.x, b.w, fma(a.y, b.z, -(a.z * b.y))));
+  r.y = fma(a.w, b.y, fma(a.y, b.w, fma(a.z, b.x, -(a.x * b.z))));
+  r.z = fma(a.w, b.z, fma(a.z, b.w, fma(a.x, b.y, -(a.y * b.x))));
+  r.w = fma(a.w, b.w, -fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)));
+  return r;
+}
+
+struct DeskewConst { double RL[9]; double pL[3]; };   // R(q_L) row-major, p_L
 
 // PACKED = false: out is pcl::PointXYZI-shaped (2 x float4 per point, the ABI layout).  PACKED = true: out is the library's own scan batch
 // (one float4 per point: x y z intensity) and the finite points are folded into their scan's min/max slots on the way out.
 template <bool PACKED>
-__global__ void __launch_bounds__(256) undistort_kernel(TrajView T, const lvi_point_xyzit* __restrict__ raw, int64_t n, int64_t pts_per_scan,
-                                                        const TargetPose* __restrict__ target, int correct_position, float4* __restrict__ out,
-                                                        int* __restrict__ mm) {
+__global__ void __launch_bounds__(256, 4) undistort_kernel(TrajView T, DeskewConst K, const double* __restrict__ hax, const lvi_point_xyzit* __restrict__ raw,
+                                                        int64_t n, int64_t pts_per_scan, const TargetPose* __restrict__ target, int correct_position,
+                                                        float4* __restrict__ out, int* __restrict__ mm) {
+  __shared__ double s_tp[2][13];   // R_0^T (9), p_0 (3), ok
+  __shared__ float4 s_raw[3][2][256];
   ScanMinMax acc;
   acc.reset(-1);
-  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kProducerChunk; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * kProducerChunk)
-  for (int j = 0; j < kProducerChunk / 256; ++j) {
-    const int64_t i = c0 + threadIdx.x + 256 * j;
+  const float nanv = __int_as_float(0x7fc00000);
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kProducerChunk; c0 < n; c0 += static_cast<int64_t>(gridDim.x) * kProducerChunk) {
+  int64_t scan = c0 / pts_per_scan;                       // one 64-bit division per chunk, not per point
+  int64_t in_scan = c0 - scan * pts_per_scan + threadIdx.x;
+  // the target poses of the (at most two, for any real scan size) scans a chunk of 2048 points touches are staged in shared memory; the raw
+  // record of the NEXT point is requested before the current one is worked on, so the HBM latency of the stream hides behind ~400
+  // instructions of pose arithmetic
+  __syncthreads();
+  if (threadIdx.x < 26) {
+    const int w = threadIdx.x / 13, k = threadIdx.x % 13;
+    const int64_t sc = min(scan + w, (n - 1) / pts_per_scan);
+    s_tp[w][k] = target[sc].c[k];
+  }
+  __syncthreads();
+  const int64_t scan_first = scan;
+  // raw records: asynchronous copies (cp.async) into this thread's own shared-memory slots, two points ahead of the arithmetic
+  auto issue = [&](int jj) {
+    const int64_t ii = c0 + threadIdx.x + 256 * jj;
+    if (jj < kProducerChunk / 256 && ii < n) {
+      const unsigned d0 = static_cast<unsigned>(__cvta_generic_to_shared(&s_raw[jj % 3][0][threadIdx.x]));
+      const unsigned d1 = static_cast<unsigned>(__cvta_generic_to_shared(&s_raw[jj % 3][1][threadIdx.x]));
+      const float4* src = reinterpret_cast<const float4*>(raw + ii);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(src + 1) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0); issue(1);
+  int64_t i = c0 + threadIdx.x;
+  for (int j = 0; j < kProducerChunk / 256; ++j, in_scan += 256, i += 256) {
+    issue(j + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     if (i >= n) break;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(raw + i));       // x y z pad
-    const float4 b = __ldg(reinterpret_cast<const float4*>(raw + i) + 1);   // intensity pad2 timestamp(lo,hi)
-    const double ts = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));
-    const int64_t scan = i / pts_per_scan;
-    const TargetPose tp = target[scan];
+    const float4 a = s_raw[j % 3][0][threadIdx.x], b = s_raw[j % 3][1][threadIdx.x];
+    while (in_scan >= pts_per_scan) { in_scan -= pts_per_scan; ++scan; }
+    const double* Rt = s_tp[0];
+    if (scan - scan_first == 1) Rt = s_tp[1];
+    else if (scan != scan_first) Rt = target[scan].c;   // scans shorter than a chunk: straight from global memory
+    const bool tp_ok = Rt[12] != 0.0;
+    const double p0x = Rt[9], p0y = Rt[10], p0z = Rt[11];
+    const double ts = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));   // x y z pad | intensity pad2 timestamp(lo, hi)
     float4 o0 = make_float4(0.f, 0.f, 0.f, 1.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!tp.ok || isnan(a.x)) {
-      const float nanv = __int_as_float(0x7fc00000);
+    if (!tp_ok || isnan(a.x)) {
       o0.x = nanv; o0.y = nanv; o0.z = nanv;
     } else {
-      Q4 qk; V3 pk;
-      if (lidar_pose(T, ts, qk, pk)) {
-        const Q4 q0c = qconj(tp.q);
-        const Q4 q = qmul(q0c, qk);
-        V3 po = qrot(q, v3(a.x, a.y, a.z));
-        if (correct_position) po = po + qrot(q0c, pk - tp.p);
-        o0.x = static_cast<float>(po.x); o0.y = static_cast<float>(po.y); o0.z = static_cast<float>(po.z);
+      const double tt = ts + T.toff;
+      if (!(T.t0 > tt || T.t_max <= tt || !(tt == tt))) {   // evaluateLidarPose range test (trajectory_manager_lvi.cpp:401-403)
+        // span and local time.  (tt - t0) * (1 / dt) can differ from the reference's division in the last place, which only matters when
+        // the stamp sits within an ulp of a knot: the spline is C2 there, so either span gives the same pose to 1e-15.
+        const double s = (tt - T.t0) * T.dt_inv;
+        const int i0 = min(max(static_cast<int>(floor(s)), 0), T.n_knots - 4);
+        const double u = s - i0;
+        const double u2 = u * u, u3 = u2 * u;
+        // cumulative basis (spline_math.cuh basis_cumul) and position basis
+        const double c3 = u3 * (1.0 / 6.0);
+        const double c2 = fma(-2.0, u3, fma(3.0, u2, fma(3.0, u, 1.0))) * (1.0 / 6.0);
+        const double c1 = fma(1.0, u3, fma(-3.0, u2, fma(3.0, u, 5.0))) * (1.0 / 6.0);
+        const double2 qa = __ldg(reinterpret_cast<const double2*>(T.so3) + 2 * i0), qb = __ldg(reinterpret_cast<const double2*>(T.so3) + 2 * i0 + 1);
+        Q4 q = q4(qa.x, qa.y, qb.x, qb.y);
+        const double cb[3] = {c1, c2, c3};
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          const double2 ha = __ldg(reinterpret_cast<const double2*>(hax) + 2 * (i0 + 1 + jj)), hb = __ldg(reinterpret_cast<const double2*>(hax) + 2 * (i0 + 1 + jj) + 1);
+          double sn, cs;
+          sincos_small(cb[jj] * hb.y, sn, cs);
+          q = qmul_fma(q, q4(sn * ha.x, sn * ha.y, sn * hb.x, cs));
+        }
+        // y = R_L x (+ p_L)
+        const double x = a.x, y = a.y, z = a.z;
+        double y0 = fma(K.RL[0], x, fma(K.RL[1], y, K.RL[2] * z)), y1 = fma(K.RL[3], x, fma(K.RL[4], y, K.RL[5] * z)),
+               y2 = fma(K.RL[6], x, fma(K.RL[7], y, K.RL[8] * z));
+        if (correct_position) { y0 += K.pL[0]; y1 += K.pL[1]; y2 += K.pL[2]; }
+        // z = R(q) y : v + w (2 u x v) + u x (2 u x v)
+        const double t0 = 2.0 * fma(q.y, y2, -(q.z * y1)), t1 = 2.0 * fma(q.z, y0, -(q.x * y2)), t2 = 2.0 * fma(q.x, y1, -(q.y * y0));
+        double z0 = fma(q.w, t0, y0) + fma(q.y, t2, -(q.z * t1));
+        double z1 = fma(q.w, t1, y1) + fma(q.z, t0, -(q.x * t2));
+        double z2 = fma(q.w, t2, y2) + fma(q.x, t1, -(q.y * t0));
+        if (correct_position) {
+          const double b0 = 1.0 - c1, b1 = c1 - c2, b2 = c2 - c3, b3 = c3;
+          const double* cp = T.r3 + 3 * i0;
+          z0 += fma(b0, __ldg(cp), fma(b1, __ldg(cp + 3), fma(b2, __ldg(cp + 6), b3 * __ldg(cp + 9)))) - p0x;
+          z1 += fma(b0, __ldg(cp + 1), fma(b1, __ldg(cp + 4), fma(b2, __ldg(cp + 7), b3 * __ldg(cp + 10)))) - p0y;
+          z2 += fma(b0, __ldg(cp + 2), fma(b1, __ldg(cp + 5), fma(b2, __ldg(cp + 8), b3 * __ldg(cp + 11)))) - p0z;
+        }
+        o0.x = static_cast<float>(fma(Rt[0], z0, fma(Rt[1], z1, Rt[2] * z2)));
+        o0.y = static_cast<float>(fma(Rt[3], z0, fma(Rt[4], z1, Rt[5] * z2)));
+        o0.z = static_cast<float>(fma(Rt[6], z0, fma(Rt[7], z1, Rt[8] * z2)));
         o1.x = b.x;
       }  // else: the reference leaves the default-constructed point (zeros)
     }
     if (PACKED) {
-      out[i] = make_float4(o0.x, o0.y, o0.z, o1.x);
+      __stcs(out + i, make_float4(o0.x, o0.y, o0.z, o1.x));
       acc.add(mm, scan, o0.x, o0.y, o0.z);
     } else {
-      out[2 * i] = o0;
-      out[2 * i + 1] = o1;
+      __stcs(out + 2 * i, o0);
+      __stcs(out + 2 * i + 1, o1);
     }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (PACKED) acc.flush(mm);
 }
@@ -259,17 +385,25 @@ static void undistort_device(lvi_ctx* ctx, const lvi_problem_desc* d, const lvi_
   DBuf<double> hlog(3 * static_cast<size_t>(n));
   LVI_LAUNCH(ctx, so3_log_kernel, (n + 127) / 128, 128, 0, so3.p, n, hlog.p);
   T.r3 = r3.p; T.so3 = so3.p; T.hlog = hlog.p;
+  DBuf<double> hax(4 * static_cast<size_t>(n));
+  LVI_LAUNCH(ctx, so3_axis_kernel, (n + 127) / 128, 128, 0, hlog.p, n, hax.p);
   static const double ident[4] = {0, 0, 0, 1}, zero[3] = {0, 0, 0};
   const double* lq = d->lidar_q ? d->lidar_q : ident; const double* lp = d->lidar_p ? d->lidar_p : zero;
   T.qL = q4(lq[0], lq[1], lq[2], lq[3]); T.pL = v3(lp[0], lp[1], lp[2]);
   DBuf<TargetPose> tp(n_scans);
   LVI_LAUNCH(ctx, undistort_target_kernel, (n_scans + 127) / 128, 128, 0, T, tt.p, n_scans, tp.p);
+  DeskewConst K;
+  {
+    const M3 RL = qmat(T.qL);
+    for (int k = 0; k < 9; ++k) K.RL[k] = RL.m[k];
+    K.pL[0] = T.pL.x; K.pL[1] = T.pL.y; K.pL[2] = T.pL.z;
+  }
   const int64_t np = static_cast<int64_t>(n_scans) * pts_per_scan;
   if (mm_packed)
-    LVI_LAUNCH(ctx, undistort_kernel<true>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
+    LVI_LAUNCH(ctx, undistort_kernel<true>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, K, hax.p, raw_d, np, pts_per_scan, tp.p, correct_position,
                static_cast<float4*>(out_d), mm_packed);
   else
-    LVI_LAUNCH(ctx, undistort_kernel<false>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, raw_d, np, pts_per_scan, tp.p, correct_position,
+    LVI_LAUNCH(ctx, undistort_kernel<false>, grid_for(np, kProducerChunk, ctx->sm_count, 8), 256, 0, T, K, hax.p, raw_d, np, pts_per_scan, tp.p, correct_position,
                static_cast<float4*>(out_d), static_cast<int*>(nullptr));
   std::vector<TargetPose> h(n_scans);
   tp.download(h.data(), n_scans, st);
