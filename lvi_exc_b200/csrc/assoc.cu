@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(256) assoc_emit_kernel(const int32_t* __restri
 constexpr int kScanSelThreads = 512;
 constexpr int kScanSelWarps = kScanSelThreads / 32;
 constexpr int kScanSelMaxPts = 1 << 17;   // bitmap of 16 KB in shared memory
+constexpr int kSelAhead = 8;               // 32-column steps of a ring whose loads are issued together
 
 struct FusedSel { int32_t e; int32_t plane; };   // e = w * H + h: position inside the scan in emission order
 
@@ -370,9 +371,16 @@ __global__ void __launch_bounds__(kScanSelThreads) assoc_scan_select_kernel(cons
       for (int i = lane; i < kSelHash; i += 32) { hk[i] = -1; ht[i] = 0; hr[i] = 0; }
       __syncwarp();
       bool full = false;
-      for (int w0 = 0; w0 < W; w0 += 32) {   // pass 1: hits per plane
-        const int w = w0 + lane;
-        const int c = w < W ? __ldg(row + w) : -1;
+      // both passes read the ring kSelAhead x 32 columns at a time: the loads of a batch are in flight together (the walk itself is serial
+      // in the column, so one load per step would pay one trip to L2 per 32 columns)
+      for (int wb = 0; wb < W; wb += 32 * kSelAhead) {   // pass 1: hits per plane
+        int cbuf[kSelAhead];
+#pragma unroll
+        for (int u = 0; u < kSelAhead; ++u) { const int w = wb + 32 * u + lane; cbuf[u] = w < W ? __ldg(row + w) : -1; }
+#pragma unroll
+        for (int u = 0; u < kSelAhead; ++u) {
+        if (wb + 32 * u >= W) break;
+        const int c = cbuf[u];
         const unsigned hits = __ballot_sync(FULL, c >= 0);
         if (c >= 0) {
           const unsigned grp = __match_any_sync(hits, c);
@@ -382,11 +390,18 @@ __global__ void __launch_bounds__(kScanSelThreads) assoc_scan_select_kernel(cons
           }
         }
         __syncwarp();
+        }
       }
       full = __any_sync(FULL, full);
-      for (int w0 = 0; w0 < W; w0 += 32) {   // pass 2: rank of every hit inside its plane's hit list -> the k picked ones
-        const int w = w0 + lane;
-        const int c = w < W ? __ldg(row + w) : -1;
+      for (int wb = 0; wb < W; wb += 32 * kSelAhead) {   // pass 2: rank of every hit inside its plane's hit list -> the k picked ones
+        int cbuf[kSelAhead];
+#pragma unroll
+        for (int u = 0; u < kSelAhead; ++u) { const int w = wb + 32 * u + lane; cbuf[u] = w < W ? __ldg(row + w) : -1; }
+#pragma unroll
+        for (int u = 0; u < kSelAhead; ++u) {
+        if (wb + 32 * u >= W) break;
+        const int w = wb + 32 * u + lane;
+        const int c = cbuf[u];
         const unsigned hits = __ballot_sync(FULL, c >= 0);
         if (c >= 0) {
           int rank, total;
@@ -416,6 +431,7 @@ __global__ void __launch_bounds__(kScanSelThreads) assoc_scan_select_kernel(cons
           }
         }
         __syncwarp();
+        }
       }
     }
     __syncthreads();
