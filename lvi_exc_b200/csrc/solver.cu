@@ -315,7 +315,7 @@ __device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, uns
 
 // the warps that idle during the diagonal block's Cholesky fetch flagged tiles into shared memory, all their loads in flight at once;
 // the non-blocking form gives up as soon as the Cholesky has finished (its barrier must not wait for a tile that is still being made)
-template <bool BLOCKING, int NTHREADS>
+template <bool BLOCKING, int NTHREADS, int LD = 32>
 __device__ __forceinline__ bool helper_fetch_tile(const unsigned long long* src, unsigned flag, double* dst, int ht, volatile int* progress) {
   constexpr int kPer = kTileElems / NTHREADS;
   static_assert(kPer * NTHREADS == kTileElems, "helper count must divide the tile");
@@ -332,16 +332,30 @@ __device__ __forceinline__ bool helper_fetch_tile(const unsigned long long* src,
     __nanosleep(100);   // the Cholesky warps share this SM's load/store pipe: do not hammer it while waiting
   }
 #pragma unroll
-  for (int q = 0; q < kPer; ++q) dst[ht + NTHREADS * q] = ll_value(w0[q], w1[q]);
+  for (int q = 0; q < kPer; ++q) {
+    const int e = ht + NTHREADS * q;
+    dst[LD == 32 ? e : (e & 31) + LD * (e >> 5)] = ll_value(w0[q], w1[q]);
+  }
   return true;
 }
 
-constexpr int kBufLd = 32 * kLP;   // one staging buffer: a 32x32 tile (8 KB, TMA destination) or a padded 32x33 tile
-constexpr int kStages = 3;
+// The chain CTA's products run on the fp64 tensor pipe (mma.sync.m8n8k4.f64): lane l of a warp holds element (l / 4, l % 4) of an 8x4
+// operand fragment.  With a leading dimension of kXL = 36 doubles the 16 lanes of a half-warp (4 rows x 4 k) fall into 16 distinct
+// 8-byte bank pairs ((row + 36 k) mod 16 = row + 4 k), so every fragment load is conflict-free; 32 or 33 would serialise them 4-way.
+constexpr int kXL = 36;
+#ifndef LVI_CHAIN_DMMA
+#define LVI_CHAIN_DMMA 1
+#endif
+constexpr bool kChainDmma = LVI_CHAIN_DMMA != 0;
+constexpr int kBufLd = 32 * kXL;   // one staging buffer: a 32x32 tile (8 KB, TMA destination) or a padded 32x33 / 32x36 tile
+#ifndef LVI_FAC_STAGES
+#define LVI_FAC_STAGES 3
+#endif
+constexpr int kStages = LVI_FAC_STAGES;   // staging depth of the workers' tile pipeline (each stage: two 8 KB tiles)
 struct FacShared {
   double buf[2 * kStages][kBufLd];   // workers: kStages x (A tile, B tile) filled by bulk async copies; chain CTA: sA, sB, sD, sM
-  double sW[32 * kLP], sR[32];
-  unsigned long long full[kStages];  // mbarriers: "stage filled"
+  double sW[32 * kXL], sR[32];
+  unsigned long long full[kStages];  // mbarriers: "stage filled" (one arrival + the copies' bytes)
   int q;
   volatile int progress;
   int leave;
@@ -360,6 +374,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
                "r"(smem_u32(b))
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// warp-uniform test: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity) {
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
   asm volatile(
@@ -410,6 +433,36 @@ __device__ __forceinline__ void panel_times_winv_t(const double* sP, const doubl
   }
 }
 
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {   // C(8x8) += A(8x4, row) B(4x8, col)
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// dst(lower triangle) = src - X X^T (- Y Y^T) for 32x32 tiles, on the tensor pipe, by FOUR warps (wq = 0..3): the ten 8x8 blocks of the lower
+// triangle as rows {3: 0 1 2}, {2: 0 1 2}, {(1,0) (1,1) (3,3)}, {(0,0)}.  src / dst have leading dimension 32, X and Y kXL.  `mirror` also
+// writes the transposed off-diagonal blocks (a full symmetric tile).
+__device__ __forceinline__ void lower_downdate_dmma(const double* src, double* dst, const double* X, const double* Y, int wq, int fg, int ft, bool mirror) {
+  const int nt = wq == 3 ? 1 : 3;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (q >= nt) break;   // warp-uniform
+    const int R = wq == 0 ? 3 : wq == 1 ? 2 : wq == 2 ? (q == 2 ? 3 : 1) : 0;
+    const int C = wq <= 1 ? q : wq == 2 ? (q == 2 ? 3 : q) : 0;
+    double d0 = src[(8 * R + fg) + 32 * (8 * C + 2 * ft)], d1 = src[(8 * R + fg) + 32 * (8 * C + 2 * ft + 1)];
+    const double* xr = X + (8 * R + fg) + kXL * ft;
+    const double* xc = X + (8 * C + fg) + kXL * ft;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) dmma_884(d0, d1, -xr[kXL * 4 * kk], xc[kXL * 4 * kk]);
+    if (Y) {
+      const double* yr = Y + (8 * R + fg) + kXL * ft;
+      const double* yc = Y + (8 * C + fg) + kXL * ft;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) dmma_884(d0, d1, -yr[kXL * 4 * kk], yc[kXL * 4 * kk]);
+    }
+    dst[(8 * R + fg) + 32 * (8 * C + 2 * ft)] = d0; dst[(8 * R + fg) + 32 * (8 * C + 2 * ft + 1)] = d1;
+    if (mirror && R != C) { dst[(8 * C + 2 * ft) + 32 * (8 * R + fg)] = d0; dst[(8 * C + 2 * ft + 1) + 32 * (8 * R + fg)] = d1; }
+  }
+}
+
 // ---- the pivot chain: one CTA per chain walks its block columns ---------------------------------------------------------------
 //   D_j = Dpre_j - X_{j-1} X_{j-1}^T ; L_jj L_jj^T = D_j, W_j = L_jj^-1 ; X_j = L(j+1,j) = Ppre_j W_j^T
 // Dpre_j and Ppre_j (the contributions of columns <= j-2 to the diagonal tile and to tile (j+1,j)) are pre-accumulated by worker CTAs
@@ -426,6 +479,9 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
   double* sA = sh.buf[0]; double* sB = sh.buf[1]; double* sD = sh.buf[2]; double* sM = sh.buf[3]; double* sX = sh.buf[4]; double* sT = sh.buf[5];
   double* sW = sh.sW;
   const int warp = tid >> 5;
+  // leading dimensions of the operand tiles (sB = Ppre, sT = L(j+1,j-1), sX = X_j: element (r, c) at r + ld c; sW: W(r, c) at r ld + c)
+  constexpr int XL = kChainDmma ? kXL : 32, WL = kChainDmma ? kXL : kLP;
+  const int fg = a >> 2, ft = a & 3;   // this lane's row and k index inside an m8n8k4 operand fragment
   bool have_next = false;   // Dpre_{j+1} already in sD (fetched under column j's Cholesky)
   {  // the first column of a chain has nothing before it: its tile is already final
     const double* tile = S.tiles + static_cast<size_t>(c_start) * S.TPC * kTileElems;
@@ -437,6 +493,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
     const int tq = j * S.TPC;
     LVI_TRACE(2);
     const bool has_panel = coupled && j + 1 < c_end;
+    const bool have_T = kChainDmma && has_panel && j != c_start && S.T >= 2;   // sT holds L(j+1,j-1) during this column
     int got_next = 1;
     if (warp == 0) {         // columns 0..15 and pivots 0..15
       const long long cyc0 = clock64();
@@ -451,18 +508,37 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
       if (!ok && a == 0) *S.fail = 1;
       if (S.trace && a == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 5] = gtime();
     } else if (warp == 2) {  // W = L^-1, one chunk of pivots behind
-      warp_inverse_cols(sM, sh.sR, &sh.progress, sW);
+      warp_inverse_cols<WL>(sM, sh.sR, &sh.progress, sW);
       if (S.trace && a == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 6] = gtime();
     } else if (warp == 4) {   // shares its scheduler with the head warp: stays idle
     } else if (has_panel) {   // warps 3, 5, 6, 7: Ppre_j, and its last update  Ppre_j -= L(j+1,j-1) X_{j-1}^T  (the freshest pair of tiles)
       const int h = (warp == 3 ? 0 : warp - 4) * 32 + a;   // 0..127
       if (j == c_start) {
         const double* tile = S.tiles + static_cast<size_t>(tq + 1) * kTileElems;
-        for (int e = h; e < kTileElems; e += 128) sB[e] = tile[e];
+        for (int e = h; e < kTileElems; e += 128) sB[(e & 31) + XL * (e >> 5)] = tile[e];
       } else {
         const int hrow = tq + S.T + 1;   // diagnostics: the helpers stamp into the (otherwise unstamped) first border row of the column
-        helper_fetch_tile<true, 128>(ll_P(S, j), ep, sB, h, &sh.progress);
-        if (S.T >= 2) {
+        helper_fetch_tile<true, 128, XL>(ll_P(S, j), ep, sB, h, &sh.progress);
+        if (S.T >= 2 && kChainDmma) {
+          // Ppre_j -= L(j+1,j-1) X_{j-1}^T on the tensor pipe: helper warp hw owns the 8 rows 8 hw .. 8 hw + 7 of the tile (four 8x8
+          // blocks); the negated row fragment of T is shared by the four.  32 DMMA + 40 conflict-free fragment loads per warp instead of
+          // 256 DFMA + 96 16-byte loads per thread: the Cholesky warps next door keep the shared-memory pipe.
+          helper_fetch_tile<true, 128, XL>(ll_tile(S, tq - S.TPC + 2), ep, sT, h, &sh.progress);
+          if (S.trace && h == 0) S.trace[static_cast<size_t>(hrow) * 8 + 2] = gtime();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int hw = h >> 5;
+          double acc[4][2];
+#pragma unroll
+          for (int C = 0; C < 4; ++C) { acc[C][0] = sB[(8 * hw + fg) + XL * (8 * C + 2 * ft)]; acc[C][1] = sB[(8 * hw + fg) + XL * (8 * C + 2 * ft + 1)]; }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const double ta = -sT[(8 * hw + fg) + XL * (4 * kk + ft)];
+#pragma unroll
+            for (int C = 0; C < 4; ++C) dmma_884(acc[C][0], acc[C][1], ta, sX[(8 * C + fg) + XL * (4 * kk + ft)]);
+          }
+#pragma unroll
+          for (int C = 0; C < 4; ++C) { sB[(8 * hw + fg) + XL * (8 * C + 2 * ft)] = acc[C][0]; sB[(8 * hw + fg) + XL * (8 * C + 2 * ft + 1)] = acc[C][1]; }
+        } else if (S.T >= 2) {
           helper_fetch_tile<true, 128>(ll_tile(S, tq - S.TPC + 2), ep, sT, h, &sh.progress);
           if (S.trace && h == 0) S.trace[static_cast<size_t>(hrow) * 8 + 2] = gtime();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -486,6 +562,15 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
       }
       if (S.trace && h == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 3] = gtime();
       got_next = helper_fetch_tile<false, 128>(ll_tile(S, tq + S.TPC), ep, sD, h, &sh.progress) ? 1 : 0;
+      if (kChainDmma) {
+        // The worker task of the next diagonal tile stops TWO columns back (its inputs are then a whole column period old when the chain
+        // gets here, so this fetch finds the tile waiting); the contribution of column j-1, L(j+1,j-1) L(j+1,j-1)^T, is taken here from
+        // the tile the helpers already hold for the Ppre update -- still under the Cholesky's shadow.
+        unsigned all_ok;
+        asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.red.and.pred p, 1, 128, q; selp.u32 %0, 1, 0, p; }" : "=r"(all_ok) : "r"(static_cast<unsigned>(got_next)) : "memory");
+        got_next = static_cast<int>(all_ok);
+        if (all_ok && have_T) lower_downdate_dmma(sD, sD, sT, nullptr, h >> 5, fg, ft, false);
+      }
       if (S.trace && h == 0) S.trace[static_cast<size_t>(tq + S.T + 1) * 8 + 4] = gtime();
     }
     have_next = __syncthreads_and(got_next) != 0 && has_panel;
@@ -495,11 +580,29 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int e = tid + kFacThreads * q4;
-        ll_store(wll + 2 * e, sW[(e & 31) * kLP + (e >> 5)], ep);
+        ll_store(wll + 2 * e, sW[(e & 31) * WL + (e >> 5)], ep);
       }
     }
     LVI_TRACE(4);
-    if (has_panel) {
+    if (has_panel && kChainDmma) {
+      // X_j = Ppre_j W_j^T on the tensor pipe.  W is lower triangular, so the 8 columns 8 C .. 8 C + 7 of X only need k < 8 (C + 1): warp w
+      // takes row block w / 2 and the column blocks {0, 3} or {1, 2} (10 k-steps of 4 either way), sharing the P fragment between its two.
+      const int R = warp >> 1, Ca = (warp & 1) ? 1 : 0, Cb = (warp & 1) ? 2 : 3;
+      double xa0 = 0.0, xa1 = 0.0, xb0 = 0.0, xb1 = 0.0;
+      const double* pP = sB + (8 * R + fg) + XL * ft;
+      const double* wA = sW + (8 * Ca + fg) * WL + ft;
+      const double* wB = sW + (8 * Cb + fg) * WL + ft;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        if (kk < 2 * (Cb + 1)) {   // warp-uniform
+          const double pa = pP[XL * 4 * kk];
+          if (kk < 2 * (Ca + 1)) dmma_884(xa0, xa1, pa, wA[4 * kk]);
+          dmma_884(xb0, xb1, pa, wB[4 * kk]);
+        }
+      }
+      sX[(8 * R + fg) + XL * (8 * Ca + 2 * ft)] = xa0; sX[(8 * R + fg) + XL * (8 * Ca + 2 * ft + 1)] = xa1;   // stays here for the next diagonal tile
+      sX[(8 * R + fg) + XL * (8 * Cb + 2 * ft)] = xb0; sX[(8 * R + fg) + XL * (8 * Cb + 2 * ft + 1)] = xb1;   // and the next Ppre update
+    } else if (has_panel) {
       double out[4];
       panel_times_winv_t(sB, sW, a, c0, out);
 #pragma unroll
@@ -518,7 +621,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) {
           const int e = h + 128 * q8;
-          const double x = sX[e];
+          const double x = sX[(e & 31) + XL * (e >> 5)];
           ll_store(sll + 2 * e, x, ep);
           tile[e] = x;
         }
@@ -527,7 +630,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8) {
         const int e = h + 128 * q8;
-        Wg[e] = sW[(e & 31) * kLP + (e >> 5)];
+        Wg[e] = sW[(e & 31) * WL + (e >> 5)];
       }
     } else if (j + 1 < c_end) {
       const int h = tid;                    // 0..127
@@ -543,6 +646,12 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
         LVI_TRACE(6);
+        if (kChainDmma) {
+          // D_{j+1} = Dpre_{j+1} - X_j X_j^T on the tensor pipe (lower triangle, mirrored on the way out: the head / tail Cholesky read whole
+          // columns).  When the helpers could not fetch Dpre_{j+1} under the Cholesky, the column j-1 term L(j+1,j-1) L(j+1,j-1)^T is taken here.
+          lower_downdate_dmma(sD, sA, sX, (!have_next && have_T) ? sT : nullptr, warp, fg, ft, true);
+          goto d_done;
+        }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) { p8[2 * cc] = sD[2 * rq + 32 * (4 * cq + cc)]; p8[2 * cc + 1] = sD[2 * rq + 1 + 32 * (4 * cq + cc)]; }
 #pragma unroll 8
@@ -558,6 +667,7 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
       }
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) { sA[2 * rq + 32 * (4 * cq + cc)] = p8[2 * cc]; sA[2 * rq + 1 + 32 * (4 * cq + cc)] = p8[2 * cc + 1]; }
+    d_done:;
     }
     if (tid == 96) sh.progress = 0;
     __syncthreads();  // D_{j+1} is in sA; the stores of column j are issued
@@ -629,7 +739,12 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     // chain arrives.  (Their inputs from the last two columns are then produced by tasks LATER in the queue; the host picks pre_shift so
     // that the resident workers always cover that span, which keeps the no-deadlock argument intact.)
     const int slot = q / S.TPC, s = q - slot * S.TPC;
-    const int jo = (s <= 1 && s <= S.T) ? slot : slot - S.pre_shift;
+    // The tiles right below them (s = 2 .. 4) run the longest serial update sequences of a column (T - s rank-32 updates, ~30 us) and feed
+    // the chain's helper warps directly: queued with everything else they finished their old updates only 2.6 us (median; +3.6 us at the
+    // 95th percentile) around the moment W_j appeared (tools/diag/trace_s2.py), and every late one stalls the chain.  They are queued one
+    // (s = 3, 4) or two (s = 2) slots earlier; their producers then sit at most two slots later in the queue, like those of the s <= 1 tasks.
+    const int early = (s <= 1) ? S.pre_shift : (s == 2) ? min(2, S.pre_shift) : (s <= 4) ? min(1, S.pre_shift) : 0;
+    const int jo = (s <= S.T) ? slot - (S.pre_shift - early) : slot - S.pre_shift;
     if (jo < 0 || jo >= S.NT) continue;
     const int j = ordered_column(jo, S.NT0, S.NT);
     const int c_start = j < S.NT0 ? 0 : S.NT0, c_end = j < S.NT0 ? S.NT0 : S.NT;   // the chain this column belongs to
@@ -653,7 +768,9 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
     const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
-    const int kend = (band && s <= 1) ? j - 1 : j;   // the two pre-accumulation tasks leave the update from column j-1 to the chain CTA
+    // the two pre-accumulation tasks leave the update from column j-1 to the chain CTA; the diagonal one also leaves column j-2 (the chain's
+    // helper warps hold L(j,j-2) anyway, factor_chain), so its last input is a whole column period old when the chain asks for the tile
+    const int kend = (band && s == 0 && kChainDmma && S.T >= 2) ? j - 2 : (band && s <= 1) ? j - 1 : j;
     // Updates from the older columns: their source tiles are staged into shared memory by bulk async copies (TMA) running two steps
     // ahead of the arithmetic, one elected thread issuing them as soon as the ready flags allow (one warp looks at the flags of up to 32
     // steps at once: one L2 round trip per batch, not per step).  The LAST update takes the flagged copies (below).
@@ -684,17 +801,18 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
         ++issued;
       }
     };
-    if (tid < 32) try_issue(2);
+    if (tid < 32) try_issue(kStages - 1);
     for (int t = 0; t < n_old; ++t) {
-      if (tid < 32) {   // stage (t + 2) % kStages was released by the barrier that ended step t - 1
-        try_issue(t + 3);
-        while (issued <= t) { __nanosleep(200); try_issue(t + 3); }
+      if (tid < 32) {   // stage (t + kStages - 1) % kStages was released by the barrier that ended step t - 1
+        try_issue(t + kStages);
+        while (issued <= t) { __nanosleep(200); try_issue(t + kStages); }
       }
       const unsigned st = (g + t) % kStages;
       mbar_wait(&sh.full[st], ((g + t) / kStages) & 1u);
       if (stamp && t == n_old - 1) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
       rank32_update_2x2(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rp, cp, acc);
-      __syncthreads();   // everybody is done with this stage
+      __syncthreads();   // everybody is done with this stage (per-stage `empty` mbarriers instead of this barrier let the warps drift apart
+                         // and measured slower: 2.08 against 1.92 ms)
     }
     g += n_old;
     if (kend - 1 >= kmin) {  // the freshest inputs -- the column that has only just been finished -- come as flagged copies

@@ -137,6 +137,7 @@ __device__ __noinline__ bool warp_potrf_cols(const double* tile, int ld, double*
   return !bad;
 }
 
+template <int WLD = kCholLd>
 __device__ __forceinline__ void warp_inverse_cols(const double* sLc, const double* sRinv, volatile int* progress, double* sW) {
   const int a = threadIdx.x & 31;
   double w[32];
@@ -153,7 +154,7 @@ __device__ __forceinline__ void warp_inverse_cols(const double* sLc, const doubl
     for (int r = t + 1; r < 32; ++r) w[r] = fma(-sLc[t * kCholLd + r], w[t], w[r]);
   }
 #pragma unroll
-  for (int r = 0; r < 32; ++r) sW[r * kCholLd + a] = w[r];
+  for (int r = 0; r < 32; ++r) sW[r * WLD + a] = w[r];
 }
 
 }  // namespace lvi

@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:band_factor_ll -s 6 -c 1 -f -o gpurun_out/prof_factor_r2z python bench.py --steps 2 --warmup 3 --no-calibration --no-cpu-baseline > gpurun_out/prof_factor_r2z.log 2>&1
-tail -3 gpurun_out/prof_factor_r2z.log
+timeout 300 python -m pytest tests/test_gpu_solver.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 bash tools/diag/tune_factor.sh "-DLVI_FAC_STAGES=3" "-DLVI_FAC_STAGES=4" "-DLVI_FAC_STAGES=5"
