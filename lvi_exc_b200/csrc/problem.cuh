@@ -42,6 +42,7 @@ struct BandSys {
   unsigned long long* ll;
   unsigned epoch;
   int pre_shift;     // column slots by which the pre-accumulation tasks are queued ahead of their column (set per launch)
+  unsigned char lead[64]; // column slots by which band tile s (distance to the diagonal) is queued ahead of the border tiles: pre_shift for s <= 1, less further out (set per launch)
   // ... followed by the flagged vectors of the back substitution (x_m and u_m, 32 values = 64 words each per column)
   size_t ll_count() const { return (static_cast<size_t>(NT) * TPC + 2 * static_cast<size_t>(NT)) * 2 * kTileElems + static_cast<size_t>(NT) * 4 * kTile; }
 };

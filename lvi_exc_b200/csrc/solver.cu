@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     // the chain's helper warps directly: queued with everything else they finished their old updates only 2.6 us (median; +3.6 us at the
     // 95th percentile) around the moment W_j appeared (tools/diag/trace_s2.py), and every late one stalls the chain.  They are queued one
     // (s = 3, 4) or two (s = 2) slots earlier; their producers then sit at most two slots later in the queue, like those of the s <= 1 tasks.
-    const int early = (s <= 1) ? S.pre_shift : (s == 2) ? min(2, S.pre_shift) : (s <= 4) ? min(1, S.pre_shift) : 0;
+    const int early = s < 64 ? static_cast<int>(S.lead[s]) : 0;
     const int jo = (s <= S.T) ? slot - (S.pre_shift - early) : slot - S.pre_shift;
     if (jo < 0 || jo >= S.NT) continue;
     const int j = ordered_column(jo, S.NT0, S.NT);
@@ -1323,10 +1323,27 @@ static void band_factor_only(lvi_ctx* ctx, BandSys& A, bool allow_trace = true) 
     resident = resident_ctas(ctx, reinterpret_cast<const void*>(band_factor_ll_kernel), kFacThreads, smem);
   }
   const int n_chains = (A.NT0 > 0 && A.NT0 < A.NT) ? 2 : 1;
-  // column slots by which the pre-accumulation tasks run ahead: at most 3, and the workers must cover that many slots twice over
+  // Column slots by which the pre-accumulation tasks (s <= 1) are queued ahead of the far tiles of their column.  A task may then wait for
+  // tiles whose tasks sit up to (pre_shift - 1) slots LATER in the queue; tasks are handed out in queue order, so nothing can block as long
+  // as the resident workers outnumber the live tasks of that span: (pre_shift - 1) * live_per_slot <= workers - live_per_slot / 2.
+  // More lead is better up to there (C2: 3 -> 1.92 ms, 4 -> 1.87, 5 -> 1.82, 6 -> 1.80): the s <= 4 tasks run ~20 serial updates (~30 us).
   const int live_per_slot = n_chains * (A.T + 1 + std::max(1, A.RB - (A.n_mid >> kTileLog)));
-  A.pre_shift = std::max(0, std::min(3, (resident - n_chains) / live_per_slot - 2));
+  const int workers = resident - 2 * n_chains;   // the chain CTAs, and the workers that leave the chains' SMs to them
+  A.pre_shift = std::max(0, std::min(6, (workers - live_per_slot / 2) / live_per_slot + 1));
   if (std::getenv("LVI_PRE_SHIFT")) A.pre_shift = std::atoi(std::getenv("LVI_PRE_SHIFT"));   // diagnostics
+  {
+    int e2 = std::max(A.pre_shift - 2, std::min(2, A.pre_shift)), e34 = std::max(A.pre_shift - 3, std::min(1, A.pre_shift)), prof = 0;
+    if (std::getenv("LVI_EARLY2")) e2 = std::min(A.pre_shift, std::atoi(std::getenv("LVI_EARLY2")));
+    if (std::getenv("LVI_EARLY34")) e34 = std::min(A.pre_shift, std::atoi(std::getenv("LVI_EARLY34")));
+    if (std::getenv("LVI_LEAD_PROFILE")) prof = std::atoi(std::getenv("LVI_LEAD_PROFILE"));
+    for (int s = 0; s < 64; ++s) {
+      int l = s <= 1 ? A.pre_shift : s == 2 ? e2 : s <= 4 ? e34 : 0;
+      if (prof == 1 && s >= 2) l = s <= A.T ? (A.pre_shift * (A.T - s + 2) + (A.T + 2) / 2) / (A.T + 2) : 0;                 // linear in the number of updates
+      if (prof == 2 && s >= 2) l = s <= A.T ? std::min(A.pre_shift - 2, (A.pre_shift * (A.T - s + 2) + (A.T + 2) / 2) / (A.T + 2)) : 0;
+      if (prof == 3 && s >= 2) l = s <= A.T ? std::max(0, std::min(A.pre_shift - 1, ((A.pre_shift + 1) * (A.T - s)) / A.T)) : 0;
+      A.lead[s] = static_cast<unsigned char>(std::max(0, std::min(l, A.pre_shift)));
+    }
+  }
   const int grid = std::max(n_chains + 1, std::min(resident, (A.NT + A.pre_shift) * A.TPC + n_chains));   // chain CTAs (always resident) + workers
   const char* trace_path = allow_trace ? std::getenv("LVI_TRACE_FACTOR") : nullptr;
   if (trace_path) {  // diagnostics: per-task timestamps of ONE factorisation, dumped as uint64[ntask][8]

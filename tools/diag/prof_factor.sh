@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_solver.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 bash tools/diag/tune_factor.sh "-DLVI_FAC_STAGES=3" "-DLVI_FAC_STAGES=4" "-DLVI_FAC_STAGES=5"
+run() { echo "== $1"; env $1 python bench.py --steps 20 --warmup 3 --no-calibration --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), d['phases_ms'], d['roofline']['kernels_ms'])"; }
+run "X=1"
+run "X=2"
+run "LVI_PRE_SHIFT=3"
