@@ -351,6 +351,10 @@ constexpr int kBufLd = 32 * kXL;   // one staging buffer: a 32x32 tile (8 KB, TM
 #ifndef LVI_FAC_STAGES
 #define LVI_FAC_STAGES 3
 #endif
+#ifndef LVI_FAC_PAIR
+#define LVI_FAC_PAIR 1
+#endif
+constexpr int kPair = LVI_FAC_PAIR;       // rank-32 updates per CTA barrier in the workers (kStages >= kPair + 2)
 constexpr int kStages = LVI_FAC_STAGES;   // staging depth of the workers' tile pipeline (each stage: two 8 KB tiles)
 struct FacShared {
   double buf[2 * kStages][kBufLd];   // workers: kStages x (A tile, B tile) filled by bulk async copies; chain CTA: sA, sB, sD, sM
@@ -802,16 +806,22 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       }
     };
     if (tid < 32) try_issue(kStages - 1);
-    for (int t = 0; t < n_old; ++t) {
-      if (tid < 32) {   // stage (t + kStages - 1) % kStages was released by the barrier that ended step t - 1
+    // kPair updates per CTA barrier: the barrier releases the stages of the pair, so steps t .. t + kStages - 1 may be in flight at its start
+    for (int t = 0; t < n_old; t += kPair) {
+      if (tid < 32) {
+        const int need = min(t + kPair, n_old);   // the steps of this pair must be on their way before anybody waits for them
         try_issue(t + kStages);
-        while (issued <= t) { __nanosleep(200); try_issue(t + kStages); }
+        while (issued < need) { __nanosleep(200); try_issue(t + kStages); }
       }
-      const unsigned st = (g + t) % kStages;
-      mbar_wait(&sh.full[st], ((g + t) / kStages) & 1u);
-      if (stamp && t == n_old - 1) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
-      rank32_update_2x2(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rp, cp, acc);
-      __syncthreads();   // everybody is done with this stage (per-stage `empty` mbarriers instead of this barrier let the warps drift apart
+#pragma unroll
+      for (int u = 0; u < kPair; ++u) {
+        if (t + u >= n_old) break;
+        const unsigned st = (g + t + u) % kStages;
+        mbar_wait(&sh.full[st], ((g + t + u) / kStages) & 1u);
+        if (stamp && t + u == n_old - 1) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
+        rank32_update_2x2(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rp, cp, acc);
+      }
+      __syncthreads();   // everybody is done with these stages (per-stage `empty` mbarriers instead of this barrier let the warps drift apart
                          // and measured slower: 2.08 against 1.92 ms)
     }
     g += n_old;
