@@ -1,2 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 bash tools/diag/tune_factor.sh "-DLVI_FAC_STAGES=3 -DLVI_FAC_PAIR=1" "-DLVI_FAC_STAGES=4 -DLVI_FAC_PAIR=2" "-DLVI_FAC_STAGES=5 -DLVI_FAC_PAIR=2" "-DLVI_FAC_STAGES=5 -DLVI_FAC_PAIR=3"
+python -m pytest tests/test_gpu_solver.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -2
+python bench.py --steps 20 --warmup 3 --no-calibration --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), d['phases_ms'], d['e2e']['value'], d['e2e']['final_cost'])"
+LVI_TRACE_FACTOR=gpurun_out/trace.bin timeout 120 python bench.py --steps 5 --warmup 3 --no-calibration --no-cpu-baseline >/dev/null 2>&1
+python tools/analyze_factor_trace.py gpurun_out/trace.bin 2>&1 | grep -v Warn | head -9
+rm -f gpurun_out/trace.bin
