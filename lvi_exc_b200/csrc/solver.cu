@@ -349,12 +349,12 @@ constexpr int kXL = 36;
 constexpr bool kChainDmma = LVI_CHAIN_DMMA != 0;
 constexpr int kBufLd = 32 * kXL;   // one staging buffer: a 32x32 tile (8 KB, TMA destination) or a padded 32x33 / 32x36 tile
 #ifndef LVI_FAC_STAGES
-#define LVI_FAC_STAGES 3
+#define LVI_FAC_STAGES 4
 #endif
 #ifndef LVI_FAC_PAIR
-#define LVI_FAC_PAIR 1
+#define LVI_FAC_PAIR 2
 #endif
-constexpr int kPair = LVI_FAC_PAIR;       // rank-32 updates per CTA barrier in the workers (kStages >= kPair + 2)
+constexpr int kPair = LVI_FAC_PAIR;       // rank-32 updates per CTA barrier in the workers (kStages >= kPair + 2): 1 -> 2 with 4 stages 1.798 -> 1.782 ms
 constexpr int kStages = LVI_FAC_STAGES;   // staging depth of the workers' tile pipeline (each stage: two 8 KB tiles)
 struct FacShared {
   double buf[2 * kStages][kBufLd];   // workers: kStages x (A tile, B tile) filled by bulk async copies; chain CTA: sA, sB, sD, sM
