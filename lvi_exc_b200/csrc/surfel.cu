@@ -124,17 +124,30 @@ __device__ __forceinline__ float block_min_float(float v, float* sh) {
 
 __global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start,
                                                                  const int32_t* __restrict__ leaf_key, const int32_t* __restrict__ cand, int n_cand,
-                                                                 float thr, int min_inliers, uint32_t small_max, FitOut* __restrict__ out) {
+                                                                 float thr, int min_inliers, uint32_t small_max, uint32_t large_min, FitOut* __restrict__ out) {
   __shared__ int shi[4];
   __shared__ unsigned shu[4];
   __shared__ double shd[4];
   __shared__ float shf[4];
   const int tid = threadIdx.x;
-  for (int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {
-    const int leaf = cand[ci];
+  __shared__ int s_leaf[32];
+  __shared__ uint32_t s_size[32];
+  const int step = static_cast<int>(gridDim.x);
+  for (int ci0 = blockIdx.x; ci0 < n_cand; ci0 += 32 * step) {   // candidate sizes 32 at a time (see surfel_fit_cluster_kernel)
+  __syncthreads();
+  if (tid < 32) {
+    const int c = ci0 + tid * step;
+    s_size[tid] = 0;
+    if (c < n_cand) { const int l = cand[c]; s_leaf[tid] = l; s_size[tid] = static_cast<uint32_t>(leaf_start[l + 1] - leaf_start[l]); }
+  }
+  __syncthreads();
+  for (int q = 0; q < 32; ++q) {
+    const int ci = ci0 + q * step;
+    if (ci >= n_cand) break;
+    const uint32_t n = s_size[q];
+    if (n <= small_max || n > large_min) continue;   // surfel_fit_warp_kernel's / surfel_fit_cluster_kernel's
+    const int leaf = s_leaf[q];
     const int beg = leaf_start[leaf];
-    const uint32_t n = static_cast<uint32_t>(leaf_start[leaf + 1] - beg);
-    if (n <= small_max) continue;   // surfel_fit_warp_kernel's
     const float4* P = pts + beg;
     FitOut fo;
     fo.ok = 0; fo.ninl = 0;
@@ -237,6 +250,201 @@ __global__ void __launch_bounds__(kFitThreads) surfel_fit_kernel(const float4* _
     if (tid == 0) out[ci] = fo;
     __syncthreads();
   }
+  }
+}
+
+// Large leaves (> kClusterFitMin points; the room scenes of C2 / C4 put 10^4 .. 10^5 points into a 0.5 m voxel): one THREAD-BLOCK CLUSTER of
+// kFitCluster CTAs per leaf.  Every CTA streams its 1/8 of the leaf's points per pass; counts, the first-inlier index, the nine fp64 PCA sums and
+// the box are reduced inside the CTA and then across the cluster through distributed shared memory (each CTA publishes its partials in its own
+// shared memory, one hardware cluster barrier, every CTA reads the eight sets in rank order -- identical results in all CTAs, so the RANSAC
+// control flow stays uniform without a broadcast).  Two alternating exchange slots make one cluster barrier per reduction enough.  With one CTA
+// per leaf, 252 leaves per rank (C4 at 8 GPUs) left 85 % of the warp slots empty: 3.5 ms per pass.
+constexpr int kFitCluster = 8;
+constexpr uint32_t kClusterFitMin = 4096;
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned n_clusters_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local, unsigned rank) {   // the same shared-memory variable in CTA `rank` of the cluster
+  unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(local)), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(r) : "memory");
+  return v;
+}
+// Exchange of up to 16 doubles per CTA.  op: 0 = sum, 1 = min.  vals[] holds this thread's values on entry (all threads of the CTA call it) and the
+// cluster-wide result in every thread of every CTA on return.
+struct ClusterExchange {
+  double part[2][16];        // [slot][value]: this CTA's block-level partials
+  double warp[kFitThreads / 32][16];
+  int use;
+};
+template <int NV>
+__device__ __forceinline__ void cluster_reduce(ClusterExchange& ex, double (&vals)[NV], int op) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(0xffffffffu, vals[k], o);
+      vals[k] = op == 0 ? vals[k] + t : fmin(vals[k], t);
+    }
+  }
+  __syncthreads();   // the previous reduction's reads of ex.warp are done
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) ex.warp[warp][k] = vals[k];
+  }
+  __syncthreads();
+  const int slot = ex.use & 1;
+  if (threadIdx.x < NV) {
+    double r = ex.warp[0][threadIdx.x];
+    for (int w = 1; w < kFitThreads / 32; ++w) r = op == 0 ? r + ex.warp[w][threadIdx.x] : fmin(r, ex.warp[w][threadIdx.x]);
+    ex.part[slot][threadIdx.x] = r;
+  }
+  cluster_barrier();   // every CTA's partials are published (release / acquire at cluster scope)
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double r = ld_dsmem_f64(&ex.part[slot][k], 0);
+    for (unsigned c = 1; c < static_cast<unsigned>(kFitCluster); ++c) { const double t = ld_dsmem_f64(&ex.part[slot][k], c); r = op == 0 ? r + t : fmin(r, t); }
+    vals[k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ex.use = ex.use + 1;   // the other slot next time: a CTA that reaches the NEXT cluster barrier has finished these reads
+}
+
+__global__ void __cluster_dims__(kFitCluster, 1, 1) __launch_bounds__(kFitThreads)
+surfel_fit_cluster_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ leaf_start, const int32_t* __restrict__ leaf_key,
+                          const int32_t* __restrict__ cand, int n_cand, float thr, int min_inliers, FitOut* __restrict__ out) {
+  __shared__ ClusterExchange ex;
+  const int tid = threadIdx.x;
+  const unsigned rank = cluster_rank();
+  if (tid == 0) ex.use = 0;
+  __syncthreads();
+  const uint32_t stride = kFitCluster * kFitThreads, first_i = rank * kFitThreads + tid;
+  __shared__ int s_leaf[kFitThreads];
+  __shared__ uint32_t s_size[kFitThreads];
+  const int step = static_cast<int>(n_clusters_x());
+  // the sizes of this cluster's next 128 candidates are looked up together (two dependent loads per candidate: one at a time, walking past the
+  // 150 k small leaves of a C3 map cost 0.5 ms)
+  for (int ci0 = cluster_id_x(); ci0 < n_cand; ci0 += kFitThreads * step) {
+  __syncthreads();
+  {
+    const int c = ci0 + tid * step;
+    s_size[tid] = 0;
+    if (c < n_cand) { const int l = cand[c]; s_leaf[tid] = l; s_size[tid] = static_cast<uint32_t>(leaf_start[l + 1] - leaf_start[l]); }
+  }
+  __syncthreads();
+  for (int q = 0; q < kFitThreads; ++q) {
+    const int ci = ci0 + q * step;
+    if (ci >= n_cand) break;
+    const uint32_t n = s_size[q];
+    if (n <= kClusterFitMin) continue;   // the one-CTA / one-warp kernels' (cluster-uniform)
+    const int leaf = s_leaf[q];
+    const int beg = leaf_start[leaf];
+    const float4* P = pts + beg;
+    FitOut fo;
+    fo.ok = 0; fo.ninl = 0;
+    for (int k = 0; k < 4; ++k) fo.p4[k] = 0;
+    for (int k = 0; k < 3; ++k) { fo.bmin[k] = 0; fo.bmax[k] = 0; }
+    bool fail = false;   // n > kClusterFitMin >= 3
+    float best[4] = {0, 0, 0, 0};
+    int best_count = 0;
+    {
+      const int max_iterations = 50;
+      const double log_probability = log(1.0 - 0.99);
+      const double one_over_n = 1.0 / static_cast<double>(n);
+      const uint64_t seed = mix64(static_cast<uint64_t>(static_cast<uint32_t>(leaf_key[leaf])) * 0x2545F4914F6CDD1Dull + 12345ull);
+      double k = 1.0;
+      int iterations = 0, skipped = 0;
+      uint32_t attempt = 0;
+      const int max_skip = max_iterations * 10;
+      while (iterations < k && skipped < max_skip) {
+        uint32_t a = draw(seed, attempt, 0, n);
+        uint32_t b = draw(seed, attempt, 1, n - 1);
+        uint32_t c = draw(seed, attempt, 2, n - 2);
+        ++attempt;
+        if (b >= a) ++b;
+        const uint32_t lo = min(a, b), hi = max(a, b);
+        if (c >= lo) ++c;
+        if (c >= hi) ++c;
+        float coef[4];
+        if (!model_from3(__ldg(P + a), __ldg(P + b), __ldg(P + c), coef)) { ++skipped; continue; }
+        double cv[1] = {0.0};
+        for (uint32_t i = first_i; i < n; i += stride) cv[0] += plane_dist(coef, __ldg(P + i)) < thr ? 1.0 : 0.0;   // counts < 2^31: exact in fp64
+        cluster_reduce(ex, cv, 0);
+        const int count = static_cast<int>(cv[0]);
+        if (count > best_count) {
+          best_count = count;
+          best[0] = coef[0]; best[1] = coef[1]; best[2] = coef[2]; best[3] = coef[3];
+          const double w = static_cast<double>(count) * one_over_n;
+          double p_no = 1.0 - w * w * w;
+          p_no = fmax(2.220446049250313e-16, p_no);
+          p_no = fmin(1.0 - 2.220446049250313e-16, p_no);
+          k = log_probability / log(p_no);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+      }
+      if (best_count == 0) fail = true;
+    }
+    float fin[4] = {best[0], best[1], best[2], best[3]};
+    if (!fail && best_count > 3) {
+      double fv[1] = {4294967295.0};
+      for (uint32_t i = first_i; i < n && fv[0] == 4294967295.0; i += stride) if (plane_dist(best, __ldg(P + i)) < thr) fv[0] = static_cast<double>(i);
+      cluster_reduce(ex, fv, 1);
+      const uint32_t first = static_cast<uint32_t>(fv[0]);
+      const float4 p0 = __ldg(P + first);
+      const double x0 = p0.x, y0 = p0.y, z0 = p0.z;
+      double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [9] = inlier count
+      for (uint32_t i = first_i; i < n; i += stride) {
+        const float4 p = __ldg(P + i);
+        if (!(plane_dist(best, p) < thr)) continue;
+        const double dx = static_cast<double>(p.x) - x0, dy = static_cast<double>(p.y) - y0, dz = static_cast<double>(p.z) - z0;
+        sums[0] += dx; sums[1] += dy; sums[2] += dz;
+        sums[3] += dx * dx; sums[4] += dx * dy; sums[5] += dx * dz; sums[6] += dy * dy; sums[7] += dy * dz; sums[8] += dz * dz;
+        sums[9] += 1.0;
+      }
+      cluster_reduce(ex, sums, 0);
+      const double inv_n = 1.0 / sums[9];
+      const double m0 = sums[0] * inv_n, m1 = sums[1] * inv_n, m2 = sums[2] * inv_n;
+      const float cf0 = static_cast<float>(x0 + m0), cf1 = static_cast<float>(y0 + m1), cf2 = static_cast<float>(z0 + m2);
+      const float cv0 = static_cast<float>(sums[3] * inv_n - m0 * m0), cv1 = static_cast<float>(sums[4] * inv_n - m0 * m1),
+                  cv2 = static_cast<float>(sums[5] * inv_n - m0 * m2), cv3 = static_cast<float>(sums[6] * inv_n - m1 * m1),
+                  cv4 = static_cast<float>(sums[7] * inv_n - m1 * m2), cv5 = static_cast<float>(sums[8] * inv_n - m2 * m2);
+      const double A[9] = {cv0, cv1, cv2, cv1, cv3, cv4, cv2, cv4, cv5};
+      double ev[3], V[9];
+      jacobi3_lower(A, ev, V);
+      const double nx = V[0], ny = V[3], nz = V[6];
+      double d = nx * static_cast<double>(cf0);
+      d = d + ny * static_cast<double>(cf1);
+      d = d + nz * static_cast<double>(cf2);
+      fin[0] = static_cast<float>(nx); fin[1] = static_cast<float>(ny); fin[2] = static_cast<float>(nz);
+      fin[3] = static_cast<float>(-d);
+    }
+    if (!fail) {
+      double mm[7] = {3.402823466e38, 3.402823466e38, 3.402823466e38, 3.402823466e38, 3.402823466e38, 3.402823466e38, 0.0};   // min xyz, min of -xyz
+      double cnt2[1] = {0.0};
+      for (uint32_t i = first_i; i < n; i += stride) {
+        const float4 p = __ldg(P + i);
+        cnt2[0] += plane_dist(fin, p) < thr ? 1.0 : 0.0;
+        mm[0] = fmin(mm[0], static_cast<double>(p.x)); mm[1] = fmin(mm[1], static_cast<double>(p.y)); mm[2] = fmin(mm[2], static_cast<double>(p.z));
+        mm[3] = fmin(mm[3], -static_cast<double>(p.x)); mm[4] = fmin(mm[4], -static_cast<double>(p.y)); mm[5] = fmin(mm[5], -static_cast<double>(p.z));
+      }
+      cluster_reduce(ex, cnt2, 0);
+      cluster_reduce(ex, mm, 1);
+      fo.ninl = static_cast<int>(cnt2[0]);
+      fo.ok = fo.ninl >= min_inliers;
+      for (int k = 0; k < 4; ++k) fo.p4[k] = fin[k];
+      fo.bmin[0] = mm[0]; fo.bmin[1] = mm[1]; fo.bmin[2] = mm[2]; fo.bmax[0] = -mm[3]; fo.bmax[1] = -mm[4]; fo.bmax[2] = -mm[5];
+    }
+    if (rank == 0 && tid == 0) out[ci] = fo;
+  }
+  }
+  cluster_barrier();   // no CTA leaves while a neighbour may still read its shared memory
 }
 
 // Small leaves (<= kWarpFitMax points: every leaf of a map with 10^5 .. 10^6 surfels): ONE WARP per leaf with the leaf's points staged once
@@ -448,8 +656,14 @@ int lvi_surfel_extract(lvi_ctx* ctx, const lvi_voxel_map* m, double lambda, int 
     if (warp_fit)
       LVI_LAUNCH(ctx, surfel_fit_warp_kernel, std::min((n_cand + 3) / 4, ctx->sm_count * 24), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
                  m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, fit.p);
+    // leaves above kClusterFitMin points: a cluster of 8 CTAs each (LVI_SURFEL_CLUSTER_FIT=0: the one-CTA kernel takes them, diagnostics)
+    static const bool cluster_fit = !(std::getenv("LVI_SURFEL_CLUSTER_FIT") && std::atoi(std::getenv("LVI_SURFEL_CLUSTER_FIT")) == 0);
+    const uint32_t large_min = cluster_fit ? kClusterFitMin : 0xffffffffu;
+    if (cluster_fit)
+      LVI_LAUNCH(ctx, surfel_fit_cluster_kernel, kFitCluster * std::min(n_cand, ctx->sm_count * 2), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
+                 m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, fit.p);
     LVI_LAUNCH(ctx, surfel_fit_kernel, std::min(n_cand, ctx->sm_count * 16), kFitThreads, 0, m->pts_sorted.p, m->leaf_start.p,
-               m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, small_max, fit.p);
+               m->leaf_key.p, cand.p, n_cand, ransac_threshold, min_inliers, small_max, large_min, fit.p);
     DBuf<int32_t> okf(n_cand), okpos(n_cand);
     LVI_LAUNCH(ctx, surfel_flag_ok_kernel, (n_cand + 255) / 256, 256, 0, fit.p, n_cand, okf.p);
     const int P = exclusive_scan_count(ctx, okf.p, okpos.p, n_cand);
