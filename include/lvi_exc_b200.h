@@ -153,8 +153,12 @@ typedef struct lvi_problem_desc {
   double* gravity;  /* [2] roll,pitch in/out (K/sensors/imu.h:41-70), never locked (Q5) */
   double* acc_bias; double* gyr_bias;  /* [3] in/out (K/sensors/constant_bias_imu.h:51-61) */
   double lidar_toff, cam_toff, imu_toff;
-  /* PinholeCamera(rows, cols, readout, 0,0,0,0,0, fx, fy, cx, cy) zero distortion (Q13) */
+  /* PinholeCamera(rows, cols, readout, k1, k2, p1, p2, k3, fx, fy, cx, cy) (K/sensors/pinhole_camera.h:253-281).  distortion = k1 k2 p1 p2 k3
+   * of the radial-tangential model (:199-215); it is applied when |k1|, |k2| or |p1| exceeds 1e-5 -- the reference's own test (:78, which
+   * never looks at p2 or k3): Project distorts the normalised point (:217-240), Unproject inverts by 8 fixed-point steps (:168-187).
+   * lvi.yaml ships all zeros (Q13). */
   double fx, fy, cx, cy, readout;
+  double distortion[5];
   int32_t cam_rows, cam_cols;
   /* landmarks: inverse depth blocks, lower bound 0 (K/measurements/static_rscamera_measurement.h:183-189) */
   int32_t n_landmarks;

@@ -245,8 +245,9 @@ class ConstantBiasImu : public SensorBase {
   bool lock_ba_ = true, lock_bg_ = true;   // constant_bias_imu.h:70-71
 };
 
-// PinholeCamera(rows, cols, readout, k1, k2, p1, p2, k3, fx, fy, cx, cy) (pinhole_camera.h:253-261).  The distortion coefficients are
-// kept and reported; a non-zero set is refused at Solve(): the reference's own distortion path NaNs and is disabled in lvi.yaml (Q13).
+// PinholeCamera(rows, cols, readout, k1, k2, p1, p2, k3, fx, fy, cx, cy) (pinhole_camera.h:253-281) with the radial-tangential distortion
+// model: Project / spaceToPlane distort the normalised point (:217-240), Unproject inverts with 8 fixed-point steps (liftProjective,
+// :131-190); the model is active when |k1|, |k2| or |p1| exceeds 1e-5 (:78).  The device residuals apply the same model (lvi_problem_desc.distortion).
 class PinholeCamera : public SensorBase {
  public:
   using CameraMatrix = Eigen::Matrix3d;
@@ -259,12 +260,34 @@ class PinholeCamera : public SensorBase {
   double readout() const { return readout_; }
   void set_readout(double r) { readout_ = r; }
   double fx() const { return fx_; } double fy() const { return fy_; } double cx() const { return cx_; } double cy() const { return cy_; }
-  bool has_distortion() const { return k1_ != 0 || k2_ != 0 || p1_ != 0 || p2_ != 0 || k3_ != 0; }
+  bool do_distortion() const { return std::fabs(k1_) > 1e-5 || std::fabs(k2_) > 1e-5 || std::fabs(p1_) > 1e-5; }   // :78 (p1 twice, never p2 / k3)
+  std::vector<double> distortion_params() const { return {k1_, k2_, p1_, p2_, k3_}; }
+  void distortion(const Eigen::Vector2d& p_u, Eigen::Vector2d& d_u) const {   // :199-215
+    const double x = p_u(0), y = p_u(1), x2 = x * x, y2 = y * y, xy = x * y, r2 = x2 + y2;
+    const double rad = k1_ * r2 + k2_ * r2 * r2 + k3_ * r2 * r2 * r2;
+    d_u = Eigen::Vector2d(x * rad + 2.0 * p1_ * xy + p2_ * (r2 + 2.0 * x2), y * rad + 2.0 * p2_ * xy + p1_ * (r2 + 2.0 * y2));
+  }
+  void liftProjective(const Eigen::Vector2d& p, Eigen::Vector3d& P) const {   // :131-190
+    const double mx_d = (p(0) - cx_) / fx_, my_d = (p(1) - cy_) / fy_;
+    double mx_u = mx_d, my_u = my_d;
+    if (do_distortion()) {
+      Eigen::Vector2d d_u;
+      distortion(Eigen::Vector2d(mx_d, my_d), d_u);
+      mx_u = mx_d - d_u(0); my_u = my_d - d_u(1);
+      for (int i = 1; i < 8; ++i) { distortion(Eigen::Vector2d(mx_u, my_u), d_u); mx_u = mx_d - d_u(0); my_u = my_d - d_u(1); }
+    }
+    P = Eigen::Vector3d(mx_u, my_u, 1.0);
+  }
   CameraMatrix camera_matrix() const { CameraMatrix K = CameraMatrix::Identity(); K(0, 0) = fx_; K(1, 1) = fy_; K(0, 2) = cx_; K(1, 2) = cy_; return K; }
-  // PinholeView::Project / Unproject / spaceToPlane (pinhole_camera.h:96-124): K X / z and K^-1 (u, v, 1); intrinsics only
-  Eigen::Vector2d Project(const Eigen::Vector3d& X) const { const double z = 1e-32 + X(2); return Eigen::Vector2d(fx_ * (X(0) / z) + cx_, fy_ * (X(1) / z) + cy_); }
+  // PinholeView::Project / Unproject / spaceToPlane (pinhole_camera.h:96-124, 217-240)
+  Eigen::Vector2d Project(const Eigen::Vector3d& X) const {
+    const double z = 1e-32 + X(2);
+    Eigen::Vector2d p_d(X(0) / z, X(1) / z);
+    if (do_distortion()) { Eigen::Vector2d d_u; distortion(p_d, d_u); p_d = p_d + d_u; }
+    return Eigen::Vector2d(fx_ * p_d(0) + cx_, fy_ * p_d(1) + cy_);
+  }
   Eigen::Vector2d spaceToPlane(const Eigen::Vector3d& X) const { return Project(X); }
-  Eigen::Vector3d Unproject(const Eigen::Vector2d& y) const { return Eigen::Vector3d((y(0) - cx_) / fx_, (y(1) - cy_) / fy_, 1.0); }
+  Eigen::Vector3d Unproject(const Eigen::Vector2d& y) const { Eigen::Vector3d P; liftProjective(y, P); return P; }
  private:
   size_t rows_, cols_;
   double readout_, k1_, k2_, p1_, p2_, k3_, fx_, fy_, cx_, cy_;
@@ -560,10 +583,10 @@ class TrajectoryEstimator {
     if (lidar_) { refuse_toff(*lidar_, "LiDAR"); d.lidar_q = lidar_->q_data(); d.lidar_p = lidar_->p_data(); d.lidar_toff = lidar_->time_offset();
                   d.lock_lidar_q = lidar_->RelativeOrientationIsLocked(); d.lock_lidar_p = lidar_->RelativePositionIsLocked(); }
     if (cam_) { refuse_toff(*cam_, "camera");
-                if (cam_->has_distortion()) throw std::invalid_argument("lvi_exc_b200: lens distortion is not built (Q13: the reference's own path NaNs and is disabled in lvi.yaml)");
                 d.cam_q = cam_->q_data(); d.cam_p = cam_->p_data(); d.cam_toff = cam_->time_offset();
                 d.lock_cam_q = cam_->RelativeOrientationIsLocked(); d.lock_cam_p = cam_->RelativePositionIsLocked();
                 d.fx = cam_->fx(); d.fy = cam_->fy(); d.cx = cam_->cx(); d.cy = cam_->cy(); d.readout = cam_->readout();
+                { const std::vector<double> k = cam_->distortion_params(); for (int q = 0; q < 5; ++q) d.distortion[q] = k[q]; }
                 d.cam_rows = static_cast<int32_t>(cam_->rows()); d.cam_cols = static_cast<int32_t>(cam_->cols()); }
     if (imu_) { d.gravity = imu_->g_data(); d.acc_bias = imu_->ba_data(); d.gyr_bias = imu_->bg_data(); d.imu_toff = imu_->time_offset();
                 d.lock_acc_bias = imu_->AccelerometerBiasIsLocked(); d.lock_gyr_bias = imu_->GyroscopeBiasIsLocked(); }

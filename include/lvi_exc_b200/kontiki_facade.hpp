@@ -162,10 +162,8 @@ class ConstantBiasImu : public Sensor {  // K/sensors/constant_bias_imu.h:33-119
 class PinholeCamera : public Sensor {  // PinholeCamera(rows, cols, readout, k1,k2,p1,p2,k3, fx,fy,cx,cy), pinhole_camera.h:253-261
  public:
   PinholeCamera(size_t rows, size_t cols, double readout, double k1, double k2, double p1, double p2, double k3, double fx, double fy, double cx, double cy)
-      : rows_(rows), cols_(cols), readout_(readout), fx_(fx), fy_(fy), cx_(cx), cy_(cy) {
-    if (k1 != 0 || k2 != 0 || p1 != 0 || p2 != 0 || k3 != 0)
-      throw std::invalid_argument("lvi_exc_b200: lens distortion is not built (SURVEY Q13: disabled in lvi.yaml because it NaNs upstream)");
-  }
+      : rows_(rows), cols_(cols), readout_(readout), fx_(fx), fy_(fy), cx_(cx), cy_(cy), k_{{k1, k2, p1, p2, k3}} {}
+  const std::array<double, 5>& distortion_params() const { return k_; }   // applied by the device residuals (lvi_problem_desc.distortion)
   size_t rows() const { return rows_; }
   size_t cols() const { return cols_; }
   double readout() const { return readout_; }
@@ -173,6 +171,7 @@ class PinholeCamera : public Sensor {  // PinholeCamera(rows, cols, readout, k1,
  private:
   size_t rows_, cols_;
   double readout_, fx_, fy_, cx_, cy_;
+  std::array<double, 5> k_;
 };
 }  // namespace sensors
 
@@ -295,6 +294,7 @@ class TrajectoryEstimator {
     if (cam_) { d.cam_q = cam_->q_.data(); d.cam_p = cam_->p_.data(); d.cam_toff = cam_->time_offset();
                 d.lock_cam_q = cam_->RelativeOrientationIsLocked(); d.lock_cam_p = cam_->RelativePositionIsLocked();
                 d.fx = cam_->fx(); d.fy = cam_->fy(); d.cx = cam_->cx(); d.cy = cam_->cy(); d.readout = cam_->readout();
+                for (int q = 0; q < 5; ++q) d.distortion[q] = cam_->distortion_params()[q];
                 d.cam_rows = static_cast<int32_t>(cam_->rows()); d.cam_cols = static_cast<int32_t>(cam_->cols()); }
     if (imu_) { d.gravity = imu_->g_.data(); d.acc_bias = imu_->ba_.data(); d.gyr_bias = imu_->bg_.data(); d.imu_toff = imu_->time_offset();
                 d.lock_acc_bias = imu_->AccelerometerBiasIsLocked(); d.lock_gyr_bias = imu_->GyroscopeBiasIsLocked(); }

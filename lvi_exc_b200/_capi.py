@@ -35,7 +35,7 @@ class ProblemDesc(C.Structure):
         ("lidar_q", c_double_p), ("lidar_p", c_double_p), ("cam_q", c_double_p), ("cam_p", c_double_p),
         ("gravity", c_double_p), ("acc_bias", c_double_p), ("gyr_bias", c_double_p),
         ("lidar_toff", C.c_double), ("cam_toff", C.c_double), ("imu_toff", C.c_double),
-        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("readout", C.c_double),
+        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("readout", C.c_double), ("distortion", C.c_double * 5),
         ("cam_rows", C.c_int32), ("cam_cols", C.c_int32),
         ("n_landmarks", C.c_int32), ("n_planes", C.c_int32),
         ("rho", c_double_p), ("rho_locked", c_uint8_p), ("planes", c_double_p),

@@ -371,6 +371,8 @@ inline ProblemView host_view(const lvi_problem_desc& d, const Lowered& L, const 
   ProblemView P{};
   P.dt_inv = 1.0 / d.dt; P.n_knots = d.n_knots; P.r3 = d.r3_knots; P.so3 = d.so3_knots; P.sens = sens; P.rho = d.rho; P.planes = d.planes;
   P.fx = d.fx; P.fy = d.fy; P.cx = d.cx; P.cy = d.cy; P.has_r3 = L.has_r3;
+  for (int k = 0; k < 5; ++k) P.dist[k] = d.distortion[k];
+  P.do_dist = (std::fabs(d.distortion[0]) > 1e-5 || std::fabs(d.distortion[1]) > 1e-5 || std::fabs(d.distortion[2]) > 1e-5) ? 1 : 0;   // pinhole_camera.h:78
   for (int t = 0; t < RT_COUNT; ++t) {
     const LoweredTable& T = L.tab[t];
     ResTable& R = P.tab[t];

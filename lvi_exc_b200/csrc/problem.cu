@@ -674,6 +674,8 @@ static lvi_problem* create_problem(lvi_ctx* ctx, const lvi_problem_desc* d) {
   ProblemView& V = p->view;
   V = ProblemView{};
   V.dt_inv = 1.0 / d->dt; V.n_knots = n; V.fx = d->fx; V.fy = d->fy; V.cx = d->cx; V.cy = d->cy; V.has_r3 = L.has_r3;
+  for (int k = 0; k < 5; ++k) V.dist[k] = d->distortion[k];
+  V.do_dist = (std::fabs(d->distortion[0]) > 1e-5 || std::fabs(d->distortion[1]) > 1e-5 || std::fabs(d->distortion[2]) > 1e-5) ? 1 : 0;   // pinhole_camera.h:78
   auto up_i = [&](DBuf<int>& b, const std::vector<int>& h) -> const int* { if (h.empty()) return nullptr; b.alloc(h.size()); b.upload(h.data(), h.size(), st); return b.p; };
   auto up_d = [&](DBuf<double>& b, const std::vector<double>& h) -> const double* { if (h.empty()) return nullptr; b.alloc(h.size()); b.upload(h.data(), h.size(), st); return b.p; };
   for (int t = 0; t < RT_COUNT; ++t) {

@@ -56,6 +56,8 @@ struct ProblemView {
   const double* rho;    // [n_landmarks]
   const double* planes; // [n_planes*3]
   double fx, fy, cx, cy;
+  double dist[5];       // k1 k2 p1 p2 k3
+  int do_dist;          // the reference's test: |k1|, |k2| or |p1| above 1e-5 (pinhole_camera.h:78)
   int has_r3;
   ResTable tab[RT_COUNT];
   // column positions in the linear system (-1: constant)
@@ -173,6 +175,38 @@ LVI_HD void eval_surfel(const ProblemView& P, int i, bool jac, ResOut& o) {
   put_row(o.J[0], 51, g0Rk - gL);
 }
 
+// ---- radial-tangential distortion of the pinhole camera (K/sensors/pinhole_camera.h:131-240) --------------------------------------------
+// d(p_u) with p_d = p_u + d (:199-215)
+LVI_HD void cam_distortion(const double k[5], double x, double y, double& dx, double& dy) {
+  const double x2 = x * x, y2 = y * y, xy = x * y, r2 = x2 + y2;
+  const double rad = k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2;
+  dx = x * rad + 2.0 * k[2] * xy + k[3] * (r2 + 2.0 * x2);
+  dy = y * rad + 2.0 * k[3] * xy + k[2] * (r2 + 2.0 * y2);
+}
+// M = I + d d / d p_u (the Jacobian of p_u -> p_d), row-major 2x2
+LVI_HD void cam_distortion_jac(const double k[5], double x, double y, double M[4]) {
+  const double x2 = x * x, y2 = y * y, r2 = x2 + y2;
+  const double rad = k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2;
+  const double drad = k[0] + 2.0 * k[1] * r2 + 3.0 * k[4] * r2 * r2;   // d rad / d r2
+  M[0] = 1.0 + rad + 2.0 * x2 * drad + 2.0 * k[2] * y + 6.0 * k[3] * x;
+  M[1] = 2.0 * x * y * drad + 2.0 * k[2] * x + 2.0 * k[3] * y;
+  M[2] = 2.0 * x * y * drad + 2.0 * k[3] * y + 2.0 * k[2] * x;
+  M[3] = 1.0 + rad + 2.0 * y2 * drad + 2.0 * k[3] * x + 6.0 * k[2] * y;
+}
+// Unproject (:112-124, liftProjective :131-190): K^-1 (u, v, 1), then -- with distortion -- the recursive inverse model, 8 steps, no early exit
+LVI_HD V3 cam_unproject(const ProblemView& P, double u, double v) {
+  const double mx_d = (u - P.cx) / P.fx, my_d = (v - P.cy) / P.fy;
+  if (!P.do_dist) return v3(mx_d, my_d, 1.0);
+  double dx, dy;
+  cam_distortion(P.dist, mx_d, my_d, dx, dy);
+  double mx_u = mx_d - dx, my_u = my_d - dy;
+  for (int it = 1; it < 8; ++it) {
+    cam_distortion(P.dist, mx_u, my_u, dx, dy);
+    mx_u = mx_d - dx; my_u = my_d - dy;
+  }
+  return v3(mx_u, my_u, 1.0);
+}
+
 LVI_HD void eval_camsurf(const ProblemView& P, int i, bool jac, ResOut& o) {
   const ResTable& T = P.tab[RT_CAMSURF];
   const int i0m = T.i0a[i], i0k = T.i0b[i];
@@ -187,7 +221,7 @@ LVI_HD void eval_camsurf(const ProblemView& P, int i, bool jac, ResOut& o) {
   const V3 pLI = v3(P.sens[SENS_LP], P.sens[SENS_LP + 1], P.sens[SENS_LP + 2]);
   const V3 pCI = v3(P.sens[SENS_CP], P.sens[SENS_CP + 1], P.sens[SENS_CP + 2]);
   const double s = 1.0 / (P.rho[T.ib[i]] + 1e-8);  // camera_surfel_landmark.h:57
-  const V3 yh = v3((T.v[2 * i] - P.cx) / P.fx * s, (T.v[2 * i + 1] - P.cy) / P.fy * s, s);
+  const V3 yh = s * cam_unproject(P, T.v[2 * i], T.v[2 * i + 1]);   // landmark position in the camera frame: Unproject(uv) / (rho + 1e-8)
   const V3 Ryh = qrot(qC, yh);
   const V3 p_I = Ryh + pCI;
   const V3 Rk_pI = qrot(ek.q, p_I);
@@ -226,7 +260,7 @@ LVI_HD void eval_cam(const ProblemView& P, int i, bool jac, ResOut& o) {
   const V3 pCI = v3(P.sens[SENS_CP], P.sens[SENS_CP + 1], P.sens[SENS_CP + 2]);
   const double rho = P.rho[T.ia[i]];
   const double* uv = T.v + 4 * i;  // uv_ref[2], uv_obs[2]
-  const V3 yh = v3((uv[0] - P.cx) / P.fx, (uv[1] - P.cy) / P.fy, 1.0);  // Unproject: K^-1 (u,v,1)
+  const V3 yh = cam_unproject(P, uv[0], uv[1]);  // Unproject: K^-1 (u,v,1) (+ inverse distortion)
   // the reference goes through p_ct = q_CI^-1 (-p_CI), q_ct = q_CI^-1 (static_rscamera_measurement.h:42-55)
   const V3 p_ct = qrot(qconj(qC), -1.0 * pCI);
   const V3 X_ref = qrot(qC, yh - rho * p_ct);
@@ -235,17 +269,30 @@ LVI_HD void eval_cam(const ProblemView& P, int i, bool jac, ResOut& o) {
   const V3 Xd = X - rho * po;
   const V3 X_obs = qrot(qconj(eo.q), Xd);
   const V3 Xc = qrot(qconj(qC), X_obs) + rho * p_ct;
-  const double z = 1e-32 + Xc.z;  // spaceToPlane
+  const double z = 1e-32 + Xc.z;  // spaceToPlane (pinhole_camera.h:217-240)
   const double w = T.weight[i];
-  o.r[0] = w * (uv[2] - (P.fx * (Xc.x / z) + P.cx));
-  o.r[1] = w * (uv[3] - (P.fy * (Xc.y / z) + P.cy));
+  double pdx = Xc.x / z, pdy = Xc.y / z;
+  double M[4] = {1.0, 0.0, 0.0, 1.0};
+  if (P.do_dist) {
+    double dx, dy;
+    cam_distortion(P.dist, pdx, pdy, dx, dy);
+    if (jac) cam_distortion_jac(P.dist, pdx, pdy, M);
+    pdx += dx; pdy += dy;
+  }
+  o.r[0] = w * (uv[2] - (P.fx * pdx + P.cx));
+  o.r[1] = w * (uv[3] - (P.fy * pdy + P.cy));
   if (!jac) return;
   const M3 RC = qmat(qC);
   const V3 Ryh = qrot(qC, yh);
   const V3 vC = X_obs - rho * pCI;  // X_c = R_CI^T vC
   // G rows: -w * dproj/dXc
-  const V3 G0 = v3(-w * P.fx / z, 0.0, w * P.fx * Xc.x / (z * z));
-  const V3 G1 = v3(0.0, -w * P.fy / z, w * P.fy * Xc.y / (z * z));
+  V3 G0 = v3(-w * P.fx / z, 0.0, w * P.fx * Xc.x / (z * z));
+  V3 G1 = v3(0.0, -w * P.fy / z, w * P.fy * Xc.y / (z * z));
+  if (P.do_dist) {   // chain rule through p_d = p_u + d(p_u)
+    const V3 a0 = v3(1.0 / z, 0.0, -Xc.x / (z * z)), a1 = v3(0.0, 1.0 / z, -Xc.y / (z * z));   // d p_u / d Xc
+    G0 = (-w * P.fx) * (M[0] * a0 + M[1] * a1);
+    G1 = (-w * P.fy) * (M[2] * a0 + M[3] * a1);
+  }
   const V3 dXobs_drho = qrot(qconj(eo.q), qrot(er.q, pCI) + pr - po);
   const V3 dXc_drho = mulT(RC, dXobs_drho - pCI);
   for (int k = 0; k < 2; ++k) {

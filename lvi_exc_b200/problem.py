@@ -27,7 +27,7 @@ def _i4(a):
 
 @dataclass
 class CameraIntrinsics:
-    """PinholeCamera(rows, cols, readout, 0,0,0,0,0, fx, fy, cx, cy) — L/cfg/lvi.yaml:54-78"""
+    """PinholeCamera(rows, cols, readout, k1, k2, p1, p2, k3, fx, fy, cx, cy) — L/cfg/lvi.yaml:54-78 (distortion all zero there)"""
     fx: float = 530.175
     fy: float = 530.095
     cx: float = 635.12
@@ -35,6 +35,7 @@ class CameraIntrinsics:
     readout: float = 0.0666
     rows: int = 720
     cols: int = 1280
+    distortion: tuple = (0.0, 0.0, 0.0, 0.0, 0.0)   # k1 k2 p1 p2 k3 (K/sensors/pinhole_camera.h:72-80)
 
 
 @dataclass
@@ -119,6 +120,8 @@ class ProblemData:
         d.lidar_toff, d.cam_toff, d.imu_toff = self.lidar_toff, self.cam_toff, self.imu_toff
         c = self.cam
         d.fx, d.fy, d.cx, d.cy, d.readout, d.cam_rows, d.cam_cols = c.fx, c.fy, c.cx, c.cy, c.readout, c.rows, c.cols
+        for k in range(5):
+            d.distortion[k] = float(c.distortion[k])
         d.n_landmarks = len(self.rho)
         d.n_planes = len(self.planes)
         d.rho = ptr(self.rho) if len(self.rho) else None

@@ -336,6 +336,34 @@ template <class T> static V3<T> refined_gravity(const T& roll, const T& pitch) {
   return V3<T>(-sp * cr * G, sr * G, -cr * cp * G);
 }
 
+// ---- pinhole distortion (K/sensors/pinhole_camera.h) -----------------------------------------------------------------------------------------
+static bool do_distortion(const lvi_problem_desc& d) {  // :78 (tests p1 twice, never p2 or k3)
+  return std::abs(d.distortion[0]) > 1e-5 || std::abs(d.distortion[1]) > 1e-5 || std::abs(d.distortion[2]) > 1e-5 || std::abs(d.distortion[2]) > 1e-5;
+}
+template <class T> static void distortion(const lvi_problem_desc& d, const T& x, const T& y, T& du, T& dv) {  // :199-215
+  const double k1 = d.distortion[0], k2 = d.distortion[1], p1 = d.distortion[2], p2 = d.distortion[3], k3 = d.distortion[4];
+  T mx2_u = x * x, my2_u = y * y, mxy_u = x * y;
+  T rho2_u = mx2_u + my2_u;
+  T rad_dist_u = k1 * rho2_u + k2 * rho2_u * rho2_u + k3 * rho2_u * rho2_u * rho2_u;
+  du = x * rad_dist_u + 2.0 * p1 * mxy_u + p2 * (rho2_u + 2.0 * mx2_u);
+  dv = y * rad_dist_u + 2.0 * p2 * mxy_u + p1 * (rho2_u + 2.0 * my2_u);
+}
+static void lift_projective(const lvi_problem_desc& d, double u, double v, double out[2]) {  // :131-190, on the (constant) observation
+  const double mx_d = (u - d.cx) / d.fx, my_d = (v - d.cy) / d.fy;   // m_inv_K11 * u + m_inv_K13 (:137-138)
+  double mx_u = mx_d, my_u = my_d;
+  if (do_distortion(d)) {
+    const int n = 8;   // recursive distortion model (:168-187), fixed number of steps
+    double du, dv;
+    distortion<double>(d, mx_d, my_d, du, dv);
+    mx_u = mx_d - du; my_u = my_d - dv;
+    for (int i = 1; i < n; ++i) {
+      distortion<double>(d, mx_u, my_u, du, dv);
+      mx_u = mx_d - du; my_u = my_d - dv;
+    }
+  }
+  out[0] = mx_u; out[1] = my_u;
+}
+
 template <class T> static bool functor(const Problem& P, const RBlock& rb, T const* const* params, T* res) {
   const lvi_problem_desc& d = P.d;
   const int nt = rb.meta.n_r3 + rb.meta.n_so3;
@@ -396,13 +424,20 @@ template <class T> static bool functor(const Problem& P, const RBlock& rb, T con
       V3<T> p_ct = rot(q_CinI.conj(), -p_CinI);
       Quat<T> q_ct = q_CinI.conj();
       // Unproject: K^-1 * (u, v, 1)
-      V3<T> yh(T((d.cam_uv_ref[2 * i] - d.cx) / d.fx), T((d.cam_uv_ref[2 * i + 1] - d.cy) / d.fy), T(1.0));
+      double lift[2];
+      lift_projective(d, d.cam_uv_ref[2 * i], d.cam_uv_ref[2 * i + 1], lift);
+      V3<T> yh(T(lift[0]), T(lift[1]), T(1.0));
       V3<T> X_ref = rot(q_ct.conj(), yh - rho * p_ct);
       V3<T> X = rot(er.q, X_ref) + er.p * rho;
       V3<T> X_obs = rot(eo.q.conj(), X - rho * eo.p);
       V3<T> Xc = rot(q_ct, X_obs) + p_ct * rho;
       const double eps = 1e-32;  // spaceToPlane
       T pu = Xc.x / (eps + Xc.z), pv = Xc.y / (eps + Xc.z);
+      if (do_distortion(d)) {  // p_d = p_u + d_u (pinhole_camera.h:228-233)
+        T du, dv;
+        distortion<T>(d, pu, pv, du, dv);
+        pu = pu + du; pv = pv + dv;
+      }
       T yx = d.fx * pu + d.cx, yy = d.fy * pv + d.cy;
       const double w = d.cam_weight[i];
       res[0] = w * (d.cam_uv_obs[2 * i] - yx);
@@ -420,7 +455,9 @@ template <class T> static bool functor(const Problem& P, const RBlock& rb, T con
       V3<T> p_CinI(cp[0], cp[1], cp[2]), p_LinI(lp[0], lp[1], lp[2]);
       Quat<T> q_CtoI(cq[0], cq[1], cq[2], cq[3]), q_LtoI(lq[0], lq[1], lq[2], lq[3]);
       const double s = 1.0 / (rho + 1e-8);
-      V3<T> yh(T((d.cs_uv[2 * i] - d.cx) / d.fx * s), T((d.cs_uv[2 * i + 1] - d.cy) / d.fy * s), T(s));
+      double lift[2];
+      lift_projective(d, d.cs_uv[2 * i], d.cs_uv[2 * i + 1], lift);
+      V3<T> yh(T(lift[0] * s), T(lift[1] * s), T(s));
       V3<T> p_I = rot(q_CtoI, yh) + p_CinI;
       V3<T> p_temp = rot(e0.q.conj(), rot(ek.q, p_I) + ek.p - e0.p);
       V3<T> p_M = rot(q_LtoI.conj(), p_temp - p_LinI);

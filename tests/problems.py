@@ -56,10 +56,17 @@ def gt_trajectory(seq, mgr, noise=0.0, seed=0):
     return r3, so3
 
 
+DISTORTION = (-0.28, 0.07, 1.0e-3, -5.0e-4, 0.01)   # k1 k2 p1 p2 k3 of the "_dist" stages (a wide-angle lens; the model is active: |k1| > 1e-5)
+
+
 def make_lvi_problem(stage: str, duration: float = 2.0, n_landmarks: int = 400):
-    """stage: so3 (S0) | surfel (S1) | lvi (S4) | lvi_locked (S5, trajectory + LiDAR locked, camera-surfel residuals)"""
+    """stage: so3 (S0) | surfel (S1) | lvi (S4) | lvi_locked (S5, trajectory + LiDAR locked, camera-surfel residuals); the suffix `_dist`
+    switches the pinhole camera's radial-tangential distortion on (SURVEY §8 f-4, K/sensors/pinhole_camera.h:131-240)"""
     seq = _sequence(duration, n_landmarks)
     mgr = _manager(seq)
+    if stage.endswith("_dist"):
+        stage = stage[:-5]
+        mgr.cam.distortion = DISTORTION
     if stage == "so3":
         return mgr.problem_so3()
     planes, sp = _oracle_association(duration, n_landmarks)

@@ -40,3 +40,33 @@ def test_facade_solves_on_the_gpu():
     assert d["usable"] == 1 and d["range_error"] == 1
     assert d["final_cost"] < 1e-9 * max(1.0, d["initial_cost"])
     assert abs(d["yaw"] - d["expected_yaw"]) < 1e-6
+
+
+def test_compat_pinhole_camera_distortion_round_trip():
+    """PinholeCamera::Project / Unproject of the compat headers with the radial-tangential model (K/sensors/pinhole_camera.h:96-240): the 8-step
+    inverse brings a projected point back to its ray; without coefficients it is K X / z and K^-1 (u, v, 1); and the numbers equal the oracle's
+    restatement of the same functions (through a one-residual evaluation they would be buried in, so here: a numpy restatement)"""
+    import json
+    import subprocess
+    import numpy as np
+    root = Path(__file__).resolve().parent.parent
+    compat = root / "include" / "lvi_exc_b200" / "compat"
+    lib = root / "lvi_exc_b200" / "lib"
+    exe = root / "build" / "camera_check"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(compat), "-I", str(root / "include"), str(root / "tests" / "cpp" / "camera_check.cpp"),
+                    "-o", str(exe), f"-L{lib}", "-llvi_exc_b200", f"-Wl,-rpath,{lib}"], check=True)
+    out = json.loads(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout)
+    assert out["do_distortion"] == [1, 0]
+    k1, k2, p1, p2, k3 = -0.28, 0.07, 1.0e-3, -5.0e-4, 0.01
+    fx, fy, cx, cy = 530.175, 530.095, 635.12, 356.522
+    pts = [(0.3, -0.2, 2.0), (-1.1, 0.4, 3.0), (0.05, 0.6, 1.5), (0.0, 0.0, 4.0)]
+    for X, o in zip(pts, out["points"]):
+        x, y = X[0] / X[2], X[1] / X[2]
+        r2 = x * x + y * y
+        rad = k1 * r2 + k2 * r2 ** 2 + k3 * r2 ** 3
+        xd = x + x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+        yd = y + y * rad + 2 * p2 * x * y + p1 * (r2 + 2 * y * y)
+        assert np.allclose(o["y"], [fx * xd + cx, fy * yd + cy], rtol=0, atol=1e-9)
+        assert np.allclose(o["y_plain"], [fx * x + cx, fy * y + cy], rtol=0, atol=1e-9)
+        assert np.allclose(o["ray"], [x, y, 1.0], atol=2e-8)            # 8 fixed-point steps: converged to ~1e-9 here, not to round-off
+        assert np.allclose(o["ray_plain"], [x, y, 1.0], atol=1e-14)

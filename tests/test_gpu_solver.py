@@ -64,7 +64,7 @@ def test_band_solver_reports_breakdown(cuda_backend):
         cuda_backend.band_solve_dense(A, np.ones(40), 40, 0, 0)
 
 
-@pytest.mark.parametrize("stage", ["so3", "surfel", "lvi", "lvi_locked"])
+@pytest.mark.parametrize("stage", ["so3", "surfel", "lvi", "lvi_locked", "lvi_dist", "lvi_locked_dist"])
 def test_evaluate_matches_oracle(cuda_backend, stage):
     pd_g, pd_o = make_lvi_problem(stage), make_lvi_problem(stage)
     gp, op = CudaProblem(cuda_backend, pd_g), ob.OracleProblem(pd_o)
@@ -81,7 +81,7 @@ def test_evaluate_matches_oracle(cuda_backend, stage):
     assert np.abs(eg["gradient"][real] - eo["gradient"][perm[real]]).max() <= 1e-7 * max(1.0, np.abs(eo["gradient"]).max())
 
 
-@pytest.mark.parametrize("stage,iters", [("so3", 30), ("surfel", 12), ("lvi", 10), ("lvi_locked", 10)])
+@pytest.mark.parametrize("stage,iters", [("so3", 30), ("surfel", 12), ("lvi", 10), ("lvi_locked", 10), ("lvi_dist", 10)])
 def test_solve_matches_oracle(cuda_backend, stage, iters):
     pd_g, pd_o = make_lvi_problem(stage), make_lvi_problem(stage)
     sg = CudaProblem(cuda_backend, pd_g).solve(iters)

@@ -10,7 +10,7 @@ from tests import hostcheck_binding as hc
 from tests import oracle_binding as ob
 from tests.problems import make_lvi_problem
 
-STAGES = ["so3", "surfel", "lvi", "lvi_locked"]
+STAGES = ["so3", "surfel", "lvi", "lvi_locked", "lvi_dist", "lvi_locked_dist"]
 
 
 def _rand_traj(n=12, seed=0):
