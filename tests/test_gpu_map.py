@@ -57,6 +57,23 @@ def test_voxel_surfel_synthetic(cuda_backend):
         gmap.close()
 
 
+def test_surfel_fit_all_leaf_sizes(cuda_backend):
+    """the three plane-fit kernels (one warp per leaf <= 768 points, one CTA per leaf <= 4096, one thread-block cluster of 8 CTAs above)
+    against the oracle: a 10 s map at 0.5 m has leaves of all three classes, at 2 m almost only cluster-sized ones"""
+    seq, scans_map = _cloud_synth(10.0)
+    cloud = scans_map.reshape(-1, 8)
+    for leaf, lam in ((0.5, 0.7), (2.0, 0.3)):
+        gmap = cuda_backend.build_surfel_map(cloud, leaf, lam)
+        ov = ob.OracleVoxelMap(cloud, leaf)
+        osf = ob.OracleSurfels(ov, lam)
+        n = ov.export()["nr_points"]
+        if leaf == 0.5:
+            assert (n > 4096).sum() > 20 and ((n > 768) & (n <= 4096)).sum() > 20 and ((n >= 10) & (n <= 768)).sum() > 20
+        assert gmap.num_planes > 10
+        _compare_maps(gmap, ov, osf)
+        gmap.close()
+
+
 def test_voxel_real_velodyne_fixture(cuda_backend):
     """20k-point subset of the reference's own ndt_omp/data/251370668.pcd (tests/golden/make_pcd_fixture.py)"""
     pts = np.load(GOLDEN / "velodyne_251370668_20k.npy")
