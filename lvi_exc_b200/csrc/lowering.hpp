@@ -13,7 +13,9 @@
 // laid out here.  Pure host C++ (no CUDA).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <set>
@@ -121,21 +123,18 @@ inline void locate2(const lvi_problem_desc& d, double ta, double tb, double ea, 
   locate(d, S, eb, i0b, ub);
 }
 
-// [0, n) cut into contiguous chunks, one host thread each (the calling thread takes the first); the first exception of any chunk is rethrown
-template <class F> inline void parallel_chunks(int n, int max_threads, F&& body /* (int lo, int hi, int chunk) */) {
-  const char* env = std::getenv("LVI_LOWER_THREADS");   // diagnostics / tests: 1 = serial
-  if (env) max_threads = std::max(1, std::min(max_threads, std::atoi(env)));
-  const int nt = std::max(1, std::min(max_threads, n / 2048));
-  if (nt == 1) { body(0, n, 0); return; }
-  std::vector<std::exception_ptr> err(nt);
-  std::vector<std::thread> th;
-  auto run = [&](int c) { try { body(static_cast<int>(static_cast<long long>(n) * c / nt), static_cast<int>(static_cast<long long>(n) * (c + 1) / nt), c); } catch (...) { err[c] = std::current_exception(); } };
-  for (int c = 1; c < nt; ++c) th.emplace_back(run, c);
-  run(0);
-  for (auto& t : th) t.join();
-  for (int c = 0; c < nt; ++c) if (err[c]) std::rethrow_exception(err[c]);
-}
-constexpr int kLowerThreads = 4;
+struct LowerLap {   // diagnostics: LVI_TIME_CREATE=1 prints the host phases of the lowering on stderr
+  bool on = std::getenv("LVI_TIME_CREATE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void operator()(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lvi]   lower: %-26s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+// Chunks of these loops on extra host threads were measured SLOWER on the GPU box (create 10.1 -> 11.9 ms: a thread start costs more than
+// the 0.3 - 1 ms a chunk saves); the one helper thread for the surfel table stays.
 
 inline void check_span(const lvi_problem_desc& d, double t1, double t2) {  // CheckTimeSpans
   const double mn = d.t0, mx = d.t0 + (d.n_knots - 3) * d.dt;
@@ -157,6 +156,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) knot_used[k] = 1; };
   auto use_span = [&](double ta, double tb) { int ia, ib; double u; time_to_index(d, ta, ia, u); time_to_index(d, tb, ib, u); for (int k = ia; k < ib + 4 && k < n; ++k) if (k >= 0) knot_used[k] = 1; };
   auto need = [&](const void* p, int cnt, const char* what) { if (cnt > 0 && !p) throw std::invalid_argument(std::string("null table pointer: ") + what); };
+  LowerLap lap;
   // ---- gyro / accel / orient: single evaluation
   {
     LoweredTable& T = L.tab[RT_GYRO];
@@ -220,6 +220,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     }
     if (T.n && T.active) surfel_sens = true;
   };
+  lap("imu tables");
   std::exception_ptr surfel_error;
   std::thread surfel_thread([&] { try { lower_surfel(); } catch (...) { surfel_error = std::current_exception(); } });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } surfel_joiner{surfel_thread};
@@ -245,14 +246,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     T.weight.assign(d.cam_weight, d.cam_weight + T.n); T.huber.assign(d.cam_huber, d.cam_huber + T.n);
     const double row_delta = d.readout / static_cast<double>(d.cam_rows);
     const double margin = 1e-3;
-    // 32 k residuals at C2, independent of each other: up to kLowerThreads chunks, each with its own "used" marks (merged below)
-    std::vector<std::vector<char>> knot_used_c(kLowerThreads), rho_used_c(kLowerThreads);
-    std::vector<std::vector<int>> rho_anchor_c(kLowerThreads);
-    parallel_chunks(T.n, kLowerThreads, [&](int lo_i, int hi_i, int chunk) {
-    std::vector<char>& knot_used = knot_used_c[chunk]; std::vector<char>& rho_used = rho_used_c[chunk]; std::vector<int>& rho_anchor = rho_anchor_c[chunk];
-    knot_used.assign(n, 0); rho_used.assign(std::max(d.n_landmarks, 1), 0); rho_anchor.assign(std::max(d.n_landmarks, 1), -1);
-    auto use_span = [&](double ta, double tb) { int ia, ib; double u; time_to_index(d, ta, ia, u); time_to_index(d, tb, ib, u); for (int k = ia; k < ib + 4 && k < n; ++k) if (k >= 0) knot_used[k] = 1; };
-    for (int i = lo_i; i < hi_i; ++i) {
+    for (int i = 0; i < T.n; ++i) {
       double t1 = d.cam_t0_ref[i], t2 = d.cam_t0_obs[i];
       if (!(t1 <= t2)) std::swap(t1, t2);
       check_span(d, t1 - margin, t1 + d.readout + margin); check_span(d, t2 - margin, t2 + d.readout + margin);
@@ -269,12 +263,6 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
         rho_used[T.ia[i]] = 1;
         rho_anchor[T.ia[i]] = std::max(rho_anchor[T.ia[i]], T.i0a[i] + 3);
       }
-    }
-    });
-    for (int c = 0; c < kLowerThreads; ++c) {
-      if (knot_used_c[c].empty()) continue;
-      for (int k = 0; k < n; ++k) knot_used[k] |= knot_used_c[c][k];
-      for (int l = 0; l < d.n_landmarks; ++l) { rho_used[l] |= rho_used_c[c][l]; rho_anchor[l] = std::max(rho_anchor[l], rho_anchor_c[c][l]); }
     }
     if (T.n && T.active) sens_used[TB_CQ] = sens_used[TB_CP] = true;
   }
@@ -309,7 +297,9 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     }
     if (T.n && T.active) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
+  lap("camera tables");
   surfel_thread.join();
+  lap("wait for the surfel thread");
   if (surfel_error) std::rethrow_exception(surfel_error);
   for (int i = 0; i < n; ++i) { knot_used[i] |= knot_used_surfel[i]; border_flag[i] |= border_flag_cs[i]; }
   if (surfel_sens) sens_used[TB_LQ] = sens_used[TB_LP] = true;
@@ -363,6 +353,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     const bool locked = d.rho_locked && d.rho_locked[l];
     if (rho_used[l] && !locked) { L.pos_rho[l] = pb++; ++L.n_rho; L.constrained = true; }
   }
+  lap("positions");
   // Schur rows: slot base of every camera residual inside its landmark's row (stored in tab[RT_CAM].ib)
   {
     LoweredTable& T = L.tab[RT_CAM];
@@ -387,6 +378,7 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     for (int i = 0; i < T.n; ++i) T.perm[i] = i;
     std::stable_sort(T.perm.begin(), T.perm.end(), [&](int x, int y) { return T.i0a[x] != T.i0a[y] ? T.i0a[x] < T.i0a[y] : T.i0b[x] < T.i0b[y]; });
   }
+  lap("schur rows + camera order");
   // ---- residual vector layout + bandwidth
   int ro = 0, nblk = 0;
   for (int t = 0; t < RT_COUNT; ++t) { L.res_offset[t] = ro; ro += L.tab[t].n * rt_rows(t); nblk += L.tab[t].n; }
@@ -457,8 +449,7 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
   bw_of_type<RT_GYRO>(P, acc); bw_of_type<RT_ACCEL>(P, acc); bw_of_type<RT_SURFEL>(P, acc);
   bw_of_type<RT_CAM>(P, acc, L.tab[RT_CAM].perm.empty() ? nullptr : L.tab[RT_CAM].perm.data()); bw_of_type<RT_CAMSURF>(P, acc); bw_of_type<RT_ORIENT>(P, acc);
   const LoweredTable& T = L.tab[RT_CAM];
-  parallel_chunks(T.n, kLowerThreads, [&](int lo_i, int hi_i, int) {   // every residual writes its own slots of its landmark's row
-  for (int i = lo_i; i < hi_i; ++i) {
+  for (int i = 0; i < T.n; ++i) {
     const int l = T.ia[i];
     const int rs = L.row_start[l];
     if (L.row_start[l + 1] == rs) continue;
@@ -476,19 +467,10 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
       L.row_pos[rs + 27 + d3] = P.pos_sens[TB_CP] < 0 ? -1 : P.pos_sens[TB_CP] + d3;
     }
   }
-  });
-  {
-    SpanAcc part[kLowerThreads];
-    for (auto& a : part) { a.c1 = acc.c1; a.nb = acc.nb; }
-    parallel_chunks(static_cast<int>(L.row_start.size()) - 1, kLowerThreads, [&](int lo_l, int hi_l, int chunk) {
-      SpanAcc& a = part[chunk];
-      for (int l = lo_l; l < hi_l; ++l) {
-        a.begin();
-        for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) a.add(L.row_pos[k]);
-        a.end();
-      }
-    });
-    for (const auto& a : part) acc.bw = std::max(acc.bw, a.bw);
+  for (size_t l = 0; l + 1 < L.row_start.size(); ++l) {
+    acc.begin();
+    for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) acc.add(L.row_pos[k]);
+    acc.end();
   }
   L.bw = acc.bw;
 }

@@ -220,16 +220,3 @@ def test_time_span_errors_match_reference_semantics():
         ob.OracleProblem(pd)
     with pytest.raises(IndexError):
         hc.layout(pd)
-
-
-def test_lowering_is_independent_of_the_host_thread_count(monkeypatch):
-    """the camera table and the Schur-row positions are lowered in up to 4 chunks on host threads (lowering.hpp parallel_chunks): layout,
-    residuals and Jacobian are identical to the serial lowering"""
-    pd = make_lvi_problem("lvi", 4.0, 3000)
-    assert len(pd.tables["cam"][0]) > 3 * 2048      # enough residuals for three chunks
-    monkeypatch.setenv("LVI_LOWER_THREADS", "1")
-    a = hc.evaluate(pd)
-    monkeypatch.delenv("LVI_LOWER_THREADS")
-    b = hc.evaluate(pd)
-    assert all(np.array_equal(a["layout"][k], b["layout"][k]) for k in a["layout"])
-    assert np.array_equal(a["J"], b["J"]) and np.array_equal(a["residuals"], b["residuals"])
