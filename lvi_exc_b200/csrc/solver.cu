@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
 // pick up each x_m as a flagged vector as well.  (The previous version passed x_m from CTA to CTA through a flagged mailbox: ~1 us of
 // hand-off plus a one-warp product per column, 4.4 us per column; this one is bound by the chain SM's copy bandwidth, ~0.5 us per column.)
 #ifndef LVI_BS_LOCAL
-#define LVI_BS_LOCAL 6
+#define LVI_BS_LOCAL 4
 #endif
 #ifndef LVI_BS_STAGES
 #define LVI_BS_STAGES 3
