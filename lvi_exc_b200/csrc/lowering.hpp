@@ -200,8 +200,10 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
   std::vector<char> border_flag(n + 4, 0);   // knots of the map-time windows (they go to the arrow border)
   std::vector<char> knot_used_surfel(n, 0), border_flag_cs(n + 4, 0);
   bool surfel_sens = false;
-  auto lower_surfel = [&]() {
-    auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) knot_used_surfel[k] = 1; };
+  // the table's set-up (sizes, copies of the plain columns) is done here, by the calling thread, before the helper starts; the rows are then
+  // split: the helper thread takes the first 60 %, the calling thread the rest once it is through with the camera tables (it used to wait
+  // 3 ms of the table's 4 ms for the helper)
+  {
     LoweredTable& T = L.tab[RT_SURFEL];
     need(d.surfel_t, d.n_surfel, "surfel_t"); need(d.surfel_point, d.n_surfel, "surfel_point"); need(d.surfel_plane, d.n_surfel, "surfel_plane");
     need(d.surfel_tmap, d.n_surfel, "surfel_tmap"); need(d.surfel_weight, d.n_surfel, "surfel_weight"); need(d.surfel_huber, d.n_surfel, "surfel_huber");
@@ -209,20 +211,28 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     if (d.n_surfel && !L.has_r3) throw std::invalid_argument("surfel residuals need the R3 spline");
     T.n = d.n_surfel; T.active = traj_free || !d.lock_lidar_q || !d.lock_lidar_p;
     T.i0a.resize(T.n); T.ua.resize(T.n); T.i0b.resize(T.n); T.ub.resize(T.n);
-    T.v.assign(d.surfel_point, d.surfel_point + 3 * static_cast<size_t>(T.n)); T.ia.assign(d.surfel_plane, d.surfel_plane + T.n);
-    T.weight.assign(d.surfel_weight, d.surfel_weight + T.n); T.huber.assign(d.surfel_huber, d.surfel_huber + T.n);
-    for (int i = 0; i < T.n; ++i) {
+    if (T.n && T.active) surfel_sens = true;
+  }
+  std::vector<char> knot_used_surfel2(n, 0), border_flag2(n + 4, 0);
+  auto lower_surfel = [&](int lo, int hi, std::vector<char>& used, std::vector<char>& flag, bool copies) {
+    auto use_window = [&](int i0) { for (int k = i0; k < i0 + 4 && k < n; ++k) used[k] = 1; };
+    LoweredTable& T = L.tab[RT_SURFEL];
+    if (copies) {
+      T.v.assign(d.surfel_point, d.surfel_point + 3 * static_cast<size_t>(T.n)); T.ia.assign(d.surfel_plane, d.surfel_plane + T.n);
+      T.weight.assign(d.surfel_weight, d.surfel_weight + T.n); T.huber.assign(d.surfel_huber, d.surfel_huber + T.n);
+    }
+    for (int i = lo; i < hi; ++i) {
       check_span(d, d.surfel_tmap[i], d.surfel_tmap[i]); check_span(d, d.surfel_t[i], d.surfel_t[i]);
       if (d.surfel_t[i] < d.surfel_tmap[i]) throw RangeError("Time spans are not ordered");
-      if (T.ia[i] < 0 || T.ia[i] >= d.n_planes) throw std::invalid_argument("surfel plane id out of range");
+      if (d.surfel_plane[i] < 0 || d.surfel_plane[i] >= d.n_planes) throw std::invalid_argument("surfel plane id out of range");
       locate2(d, d.surfel_tmap[i], d.surfel_t[i], d.surfel_tmap[i] + d.lidar_toff, d.surfel_t[i] + d.lidar_toff, T.i0a[i], T.ua[i], T.i0b[i], T.ub[i]);
-      if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) border_flag[T.i0a[i] + k] = 1; }
+      if (T.active) { use_window(T.i0a[i]); use_window(T.i0b[i]); for (int k = 0; k < 4; ++k) flag[T.i0a[i] + k] = 1; }
     }
-    if (T.n && T.active) surfel_sens = true;
   };
+  const int surfel_split = d.n_surfel >= 4096 ? static_cast<int>(0.6 * d.n_surfel) : d.n_surfel;
   lap("imu tables");
   std::exception_ptr surfel_error;
-  std::thread surfel_thread([&] { try { lower_surfel(); } catch (...) { surfel_error = std::current_exception(); } });
+  std::thread surfel_thread([&] { try { lower_surfel(0, surfel_split, knot_used_surfel, border_flag, true); } catch (...) { surfel_error = std::current_exception(); } });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } surfel_joiner{surfel_thread};
   // ---- camera
   std::vector<int> rho_anchor(std::max(d.n_landmarks, 1), -1);
@@ -298,10 +308,12 @@ inline void lower_problem(const lvi_problem_desc& d, Lowered& L) {
     if (T.n && T.active) sens_used[TB_CQ] = sens_used[TB_CP] = sens_used[TB_LQ] = sens_used[TB_LP] = true;
   }
   lap("camera tables");
+  lower_surfel(surfel_split, d.n_surfel, knot_used_surfel2, border_flag2, false);   // the calling thread's share of the surfel rows
+  lap("surfel rows (own share)");
   surfel_thread.join();
   lap("wait for the surfel thread");
   if (surfel_error) std::rethrow_exception(surfel_error);
-  for (int i = 0; i < n; ++i) { knot_used[i] |= knot_used_surfel[i]; border_flag[i] |= border_flag_cs[i]; }
+  for (int i = 0; i < n; ++i) { knot_used[i] |= knot_used_surfel[i] | knot_used_surfel2[i]; border_flag[i] |= border_flag_cs[i] | border_flag2[i]; }
   if (surfel_sens) sens_used[TB_LQ] = sens_used[TB_LP] = true;
   std::set<int> border_knots;
   for (int i = 0; i < n; ++i) if (border_flag[i]) border_knots.insert(i);
@@ -425,19 +437,29 @@ struct SpanAcc {
     for (int c = 0; c < 2; ++c) if (hi[c] >= 0) bw = std::max(bw, hi[c] - lo[c]);
   }
 };
+// band positions of one spline window (knots i0 .. i0 + 3; 3 dims per block): the only band columns a residual has -- its sensor blocks sit
+// in the border and its inverse depth is eliminated, both at positions >= nb, which SpanAcc ignores
+inline void add_window(SpanAcc& A, const ProblemView& P, int i0, bool r3, bool so3) {
+  for (int k = 0; k < 4; ++k) {
+    if (r3) { const int p = P.pos_r3[i0 + k]; if (p >= 0) { A.add(p); A.add(p + 2); } }
+    if (so3) { const int p = P.pos_so3[i0 + k]; if (p >= 0) { A.add(p); A.add(p + 2); } }
+  }
+}
 template <int TYPE> inline void bw_of_type(const ProblemView& P, SpanAcc& A, const int* order = nullptr) {
   const ResTable& T = P.tab[TYPE];
   if (!T.active) return;
-  // the band positions a residual touches depend only on its two spline windows (everything else it touches lives in the border or is
-  // an eliminated inverse depth), and consecutive residuals are time-ordered: evaluate each distinct window pair once
+  // consecutive residuals are time-ordered: evaluate each distinct window pair once
+  constexpr bool two = TYPE == RT_SURFEL || TYPE == RT_CAM || TYPE == RT_CAMSURF;
+  constexpr bool r3 = TYPE != RT_GYRO && TYPE != RT_ORIENT;
   int last_a = -1, last_b = -1;
   for (int q = 0; q < T.n; ++q) {
     const int i = order ? order[q] : q;
-    const int wa = T.i0a ? T.i0a[i] : 0, wb = T.i0b ? T.i0b[i] : 0;
+    const int wa = T.i0a ? T.i0a[i] : 0, wb = (two && T.i0b) ? T.i0b[i] : 0;
     if (q > 0 && wa == last_a && wb == last_b) continue;
     last_a = wa; last_b = wb;
     A.begin();
-    for (int c = 0; c < rt_cols(TYPE); ++c) A.add(col_pos<TYPE>(P, i, c));
+    add_window(A, P, wa, r3, true);
+    if (two) add_window(A, P, wb, r3, true);
     A.end();
   }
 }
@@ -467,10 +489,19 @@ inline void compute_bandwidth(const ProblemView& P, Lowered& L) {
       L.row_pos[rs + 27 + d3] = P.pos_sens[TB_CP] < 0 ? -1 : P.pos_sens[TB_CP] + d3;
     }
   }
-  for (size_t l = 0; l + 1 < L.row_start.size(); ++l) {
-    acc.begin();
-    for (int k = L.row_start[l]; k < L.row_start[l + 1]; ++k) acc.add(L.row_pos[k]);
-    acc.end();
+  // half bandwidth of the Schur rows: the band positions of a landmark's row are those of its residuals' windows, so the span of a row is
+  // accumulated per window (16 positions per residual) instead of re-reading the 54 slots per residual just written (1.7 M ints at C2)
+  {
+    const int nl = static_cast<int>(L.row_start.size()) - 1;
+    std::vector<SpanAcc> row(nl);
+    for (auto& a : row) { a.c1 = acc.c1; a.nb = acc.nb; a.begin(); }
+    for (int i = 0; i < T.n; ++i) {
+      const int l = T.ia[i];
+      if (L.row_start[l + 1] == L.row_start[l]) continue;
+      add_window(row[l], P, T.i0a[i], true, true);
+      add_window(row[l], P, T.i0b[i], true, true);
+    }
+    for (auto& a : row) { a.end(); acc.bw = std::max(acc.bw, a.bw); }
   }
   L.bw = acc.bw;
 }

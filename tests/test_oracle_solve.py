@@ -220,3 +220,38 @@ def test_time_span_errors_match_reference_semantics():
         ob.OracleProblem(pd)
     with pytest.raises(IndexError):
         hc.layout(pd)
+
+
+def test_product_jacobian_matches_oracle_on_a_larger_problem():
+    """5 s of data: more than 4096 surfel rows, so the surfel table is lowered in two shares (helper thread + calling thread, lowering.hpp),
+    and the half bandwidth comes from the per-window accumulation of the Schur rows"""
+    pd = make_lvi_problem("lvi", 5.0, 3000)
+    assert len(pd.tables["surfel"][0]) > 4096
+    op = ob.OracleProblem(pd)
+    eo, eh = op.evaluate(jacobian=True), hc.evaluate(pd)
+    assert eh["layout"]["n_res"] == op.num_residuals
+    perm = hc.perm_to_oracle(pd, eh["layout"], op)
+    real = perm >= 0
+    Jo = eo["J"][:, perm[real]]
+    assert np.abs(eh["residuals"] - eo["residuals"]).max() <= 1e-10 * max(1.0, np.abs(eo["residuals"]).max())
+    assert np.abs(eh["J"][:, real] - Jo).max() <= 1e-9 * max(1.0, np.abs(Jo).max())
+    # the half bandwidth equals the brute-force one: widest span of band columns (< nb) over the rows of one residual block, and -- after
+    # the inverse depths are eliminated -- over all rows of one landmark
+    lay = eh["layout"]
+    J, nb = eh["J"], lay["nb"]
+    n_g, n_a, n_s, n_c = (len(pd.tables[k][0]) for k in ("gyro", "accel", "surfel", "cam"))
+    spans = []
+    def span(rows):
+        cols = np.nonzero(np.abs(J[rows, :nb]).sum(axis=0))[0]
+        return (cols.max() - cols.min()) if len(cols) else 0
+    r0 = 0
+    for cnt, rows_per in ((n_g, 3), (n_a, 3), (n_s, 1)):
+        for b in range(0, cnt, max(1, cnt // 200)):        # a sample of the blocks (they are time-ordered and alike)
+            spans.append(span(slice(r0 + rows_per * b, r0 + rows_per * (b + 1))))
+        r0 += rows_per * cnt
+    lm = np.asarray(pd.tables["cam"][4])   # (t0_ref, t0_obs, uv_ref, uv_obs, landmark, weight, huber)
+    for l in np.unique(lm):
+        idx = np.nonzero(lm == l)[0]
+        rows = np.concatenate([[r0 + 2 * i, r0 + 2 * i + 1] for i in idx])
+        spans.append(span(rows))
+    assert lay["bw"] == max(spans)
