@@ -354,7 +354,8 @@ constexpr int kBufLd = 32 * kXL;   // one staging buffer: a 32x32 tile (8 KB, TM
 #ifndef LVI_FAC_PAIR
 #define LVI_FAC_PAIR 2
 #endif
-constexpr int kPair = LVI_FAC_PAIR;       // rank-32 updates per CTA barrier in the workers (kStages >= kPair + 2): 1 -> 2 with 4 stages 1.798 -> 1.782 ms
+constexpr int kPair = LVI_FAC_PAIR;
+static_assert(LVI_FAC_PAIR % 2 == 0, "the two halves of a worker CTA take alternate updates of a pair");       // rank-32 updates per CTA barrier in the workers (kStages >= kPair + 2): 1 -> 2 with 4 stages 1.798 -> 1.782 ms
 constexpr int kStages = LVI_FAC_STAGES;   // staging depth of the workers' tile pipeline (each stage: two 8 KB tiles)
 struct FacShared {
   double buf[2 * kStages][kBufLd];   // workers: kStages x (A tile, B tile) filled by bulk async copies; chain CTA: sA, sB, sD, sM
@@ -414,6 +415,22 @@ __device__ __forceinline__ void rank32_update_2x2(const double* sA, const double
     acc[1] = fma(-xa.y, xb.x, acc[1]);
     acc[2] = fma(-xa.x, xb.y, acc[2]);
     acc[3] = fma(-xa.y, xb.y, acc[3]);
+  }
+}
+// The workers' form: 2x4 register blocks on HALF the CTA (128 threads: rows 2rq.., columns 4cq..) over the k-range [m0, m1): 4 shared-memory
+// wavefronts per 8 DFMA instead of 3 per 4.  Two CTAs per SM made the 2x2 form shared-memory bound at the SM level (2 x 768 wavefronts =
+// 1536 cycles per update against 2 x 512 cycles of fp64 issue; measured 1.5 us per update); the two halves of the CTA take alternate
+// updates of a pair (or the two k-halves of one update) into PARTIAL accumulators that are added once, at the end of the task.
+__device__ __forceinline__ void rank32_update_2x4(const double* sA, const double* sB, int rq, int cq, double (&p8)[8], int m0, int m1) {
+#pragma unroll 8
+  for (int m = m0; m < m1; ++m) {
+    const double2 xa = *reinterpret_cast<const double2*>(sA + 2 * rq + 32 * m);
+    const double2 x01 = *reinterpret_cast<const double2*>(sB + 4 * cq + 32 * m);
+    const double2 x23 = *reinterpret_cast<const double2*>(sB + 4 * cq + 2 + 32 * m);
+    p8[0] = fma(-xa.x, x01.x, p8[0]); p8[1] = fma(-xa.y, x01.x, p8[1]);
+    p8[2] = fma(-xa.x, x01.y, p8[2]); p8[3] = fma(-xa.y, x01.y, p8[3]);
+    p8[4] = fma(-xa.x, x23.x, p8[4]); p8[5] = fma(-xa.y, x23.x, p8[5]);
+    p8[6] = fma(-xa.x, x23.y, p8[6]); p8[7] = fma(-xa.y, x23.y, p8[7]);
   }
 }
 // element index of accumulator q of thread (rp, cp) in a column-major 32x32 tile
@@ -769,8 +786,6 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     double* tile = S.tiles + static_cast<size_t>(tq) * kTileElems;
     if (stamp) LVI_TRACE_AT(trow, 0);
     double acc[4];
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
     const int kmin = max(sep_row ? sep_first : c_start, band ? i - S.T : j - S.T);
     // the two pre-accumulation tasks leave the update from column j-1 to the chain CTA; the diagonal one also leaves column j-2 (the chain's
     // helper warps hold L(j,j-2) anyway, factor_chain), so its last input is a whole column period old when the chain asks for the tile
@@ -780,6 +795,19 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
     // steps at once: one L2 round trip per batch, not per step).  The LAST update takes the flagged copies (below).
     auto tile_of = [&](int k, int& fi, int& fj) { fi = k * S.TPC + (band ? i - k : s); fj = k * S.TPC + (j - k); };
     const int n_old = max(kend - 1 - kmin, 0);
+    const bool any_update = kend - 1 >= kmin;
+    const int half = tid >> 7, rq = tid & 15, cq = (tid >> 4) & 7;   // partial accumulators: half 0 starts from the tile, half 1 from zero
+    double p8[8];
+    if (any_update) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        p8[2 * cc] = half == 0 ? tile[2 * rq + 32 * (4 * cq + cc)] : 0.0;
+        p8[2 * cc + 1] = half == 0 ? tile[2 * rq + 1 + 32 * (4 * cq + cc)] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = tile[acc_elem(rp, cp, q4)];
+    }
     int issued = 0, ready_n = 0;   // warp 0: steps issued / steps known to be published
     auto try_issue = [&](int upto) {   // warp 0 only
       upto = min(upto, n_old);
@@ -819,7 +847,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
         const unsigned st = (g + t + u) % kStages;
         mbar_wait(&sh.full[st], ((g + t + u) / kStages) & 1u);
         if (stamp && t + u == n_old - 1) LVI_TRACE_AT(trow, 6);   // inputs of the second-to-last update in shared memory
-        rank32_update_2x2(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rp, cp, acc);
+        if ((u & 1) == half) rank32_update_2x4(sh.buf[2 * st], (band && s == 0) ? sh.buf[2 * st] : sh.buf[2 * st + 1], rq, cq, p8, 0, 32);
       }
       __syncthreads();   // everybody is done with these stages (per-stage `empty` mbarriers instead of this barrier let the warps drift apart
                          // and measured slower: 2.08 against 1.92 ms)
@@ -834,7 +862,16 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       if (fj != fi) fetch_ll_tile(ll_tile(S, fj), ep, eager, sB, nullptr);
       __syncthreads();
       if (stamp) LVI_TRACE_AT(trow, 3);
-      rank32_update_2x2(sA, sB, rp, cp, acc);
+      rank32_update_2x4(sA, sB, rq, cq, p8, 16 * half, 16 * half + 16);   // the freshest update: its two k-halves on the two halves of the CTA
+    }
+    if (any_update) {   // add the two partial accumulators (through shared memory) and go back to the 2x2 layout of the rest of the task
+      __syncthreads();
+      double* sP = half == 0 ? sA : sB;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<double2*>(sP + 2 * rq + 32 * (4 * cq + cc)) = make_double2(p8[2 * cc], p8[2 * cc + 1]);
+      __syncthreads();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) acc[q4] = sA[acc_elem(rp, cp, q4)] + sB[acc_elem(rp, cp, q4)];
     }
     if (stamp) LVI_TRACE_AT(trow, 4);
     if (band && s <= 1) {  // pre-accumulated diagonal / first sub-diagonal tile: hand it to the chain CTA
