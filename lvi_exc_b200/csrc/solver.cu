@@ -290,7 +290,7 @@ __device__ __forceinline__ unsigned long long* ll_P(const BandSys& S, int j) { r
 // CTA-wide fetch of one flagged tile into shared memory (element e of the tile -> dst[e], optionally a second copy).  `eager` consumers
 // sit next to the pivot chain and poll the whole tile; the others first wait, with back-off, for one word, so that two dozen waiting CTAs
 // per chain do not spend L2 bandwidth on polling.
-__device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, unsigned flag, bool eager, double* dst, double* dst2) {
+__device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, unsigned flag, bool eager, double* dst, double* dst2, double* plain = nullptr) {
   const int tid = threadIdx.x;
   if (!eager) {
     if (tid == 0) {
@@ -310,6 +310,10 @@ __device__ __forceinline__ void fetch_ll_tile(const unsigned long long* src, uns
   if (dst2) {
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) dst2[tid + kFacThreads * q4] = v[q4];
+  }
+  if (plain) {   // the tile's plain copy in the tile store (only the back-substitution kernel reads it)
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) plain[tid + kFacThreads * q4] = v[q4];
   }
 }
 
@@ -347,6 +351,14 @@ constexpr int kXL = 36;
 #define LVI_CHAIN_DMMA 1
 #endif
 constexpr bool kChainDmma = LVI_CHAIN_DMMA != 0;
+
+// Who writes the PLAIN copies of the chain's own tiles X_j = L(j+1,j) and W_j (read by the back-substitution kernel only).  Once the workers
+// had slack again (2x4 updates), the 32 KB of stores per column at the end of the chain CTA's column were 0.7 us of a 5.6 us period.  The
+// first consumer among the workers has the values in registers anyway: the task of tile (j+2, j) fetches W_j, and the task of tile
+// (j+3, j+1) fetches X_j for its last update -- they write the copies.  Where those tasks do not exist (end of a chain, narrow bands) the
+// chain CTA still does.
+__device__ __forceinline__ bool worker_writes_W(const BandSys& S, int j, int c_end) { return kChainDmma && S.T >= 2 && j + 2 < c_end; }
+__device__ __forceinline__ bool worker_writes_X(const BandSys& S, int j, int c_end) { return kChainDmma && S.T >= 3 && j + 3 < c_end; }
 constexpr int kBufLd = 32 * kXL;   // one staging buffer: a 32x32 tile (8 KB, TMA destination) or a padded 32x33 / 32x36 tile
 #ifndef LVI_FAC_STAGES
 #define LVI_FAC_STAGES 4
@@ -471,14 +483,14 @@ __device__ __forceinline__ void lower_downdate_dmma(const double* src, double* d
     double d0 = src[(8 * R + fg) + 32 * (8 * C + 2 * ft)], d1 = src[(8 * R + fg) + 32 * (8 * C + 2 * ft + 1)];
     const double* xr = X + (8 * R + fg) + kXL * ft;
     const double* xc = X + (8 * C + fg) + kXL * ft;
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) dmma_884(d0, d1, -xr[kXL * 4 * kk], xc[kXL * 4 * kk]);
-    if (Y) {
+    if (Y) {   // Y first: the same order of accumulation as when the helper warps took the Y term earlier (bitwise the same D either way)
       const double* yr = Y + (8 * R + fg) + kXL * ft;
       const double* yc = Y + (8 * C + fg) + kXL * ft;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) dmma_884(d0, d1, -yr[kXL * 4 * kk], yc[kXL * 4 * kk]);
     }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) dmma_884(d0, d1, -xr[kXL * 4 * kk], xc[kXL * 4 * kk]);
     dst[(8 * R + fg) + 32 * (8 * C + 2 * ft)] = d0; dst[(8 * R + fg) + 32 * (8 * C + 2 * ft + 1)] = d1;
     if (mirror && R != C) { dst[(8 * C + 2 * ft) + 32 * (8 * R + fg)] = d0; dst[(8 * C + 2 * ft + 1) + 32 * (8 * R + fg)] = d1; }
   }
@@ -623,6 +635,12 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
       }
       sX[(8 * R + fg) + XL * (8 * Ca + 2 * ft)] = xa0; sX[(8 * R + fg) + XL * (8 * Ca + 2 * ft + 1)] = xa1;   // stays here for the next diagonal tile
       sX[(8 * R + fg) + XL * (8 * Cb + 2 * ft)] = xb0; sX[(8 * R + fg) + XL * (8 * Cb + 2 * ft + 1)] = xb1;   // and the next Ppre update
+      {  // the flagged copy of X_j = L(j+1,j) leaves straight from the accumulator fragments: a block column of worker tasks is waiting for it
+        unsigned long long* sll = ll_tile(S, tq + 1);
+        const int ea = (8 * R + fg) + 32 * (8 * Ca + 2 * ft), eb = (8 * R + fg) + 32 * (8 * Cb + 2 * ft);
+        ll_store(sll + 2 * ea, xa0, ep); ll_store(sll + 2 * (ea + 32), xa1, ep);
+        ll_store(sll + 2 * eb, xb0, ep); ll_store(sll + 2 * (eb + 32), xb1, ep);
+      }
     } else if (has_panel) {
       double out[4];
       panel_times_winv_t(sB, sW, a, c0, out);
@@ -643,15 +661,17 @@ __device__ void factor_chain(const BandSys& S, const int chain, FacShared& sh) {
         for (int q8 = 0; q8 < 8; ++q8) {
           const int e = h + 128 * q8;
           const double x = sX[(e & 31) + XL * (e >> 5)];
-          ll_store(sll + 2 * e, x, ep);
-          tile[e] = x;
+          if (!kChainDmma) ll_store(sll + 2 * e, x, ep);
+          if (!worker_writes_X(S, j, c_end)) tile[e] = x;
         }
       }
-      double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+      if (!worker_writes_W(S, j, c_end)) {
+        double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
 #pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8) {
-        const int e = h + 128 * q8;
-        Wg[e] = sW[(e & 31) * WL + (e >> 5)];
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const int e = h + 128 * q8;
+          Wg[e] = sW[(e & 31) * WL + (e >> 5)];
+        }
       }
     } else if (j + 1 < c_end) {
       const int h = tid;                    // 0..127
@@ -859,7 +879,9 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       __syncthreads();    // the previous k-step's reads of sA/sB are complete
       if (stamp) LVI_TRACE_AT(trow, 2);
       fetch_ll_tile(ll_tile(S, fi), ep, eager, sA, fj == fi ? sB : nullptr);
-      if (fj != fi) fetch_ll_tile(ll_tile(S, fj), ep, eager, sB, nullptr);
+      // fj is tile (j, kend-1); for the s = 2 task that is X_{j-1} = L(j, j-1), whose plain copy this task writes (worker_writes_X)
+      const bool plain_x = band && s == 2 && kend == j && fj != fi && worker_writes_X(S, j - 1, c_end);
+      if (fj != fi) fetch_ll_tile(ll_tile(S, fj), ep, eager, sB, nullptr, plain_x ? S.tiles + static_cast<size_t>(fj) * kTileElems : nullptr);
       __syncthreads();
       if (stamp) LVI_TRACE_AT(trow, 3);
       rank32_update_2x4(sA, sB, rq, cq, p8, 16 * half, 16 * half + 16);   // the freshest update: its two k-halves on the two halves of the CTA
@@ -901,6 +923,11 @@ __global__ void __launch_bounds__(kFacThreads, 2) band_factor_ll_kernel(BandSys 
       ll_load_n<4>(wll + 2 * tid, 2 * kFacThreads, v, ep);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) sW[a * kLP + c0 + 8 * q4] = v[q4];   // element e = tid + 256 q4: row e & 31 = a, column e >> 5
+      if (band && s == 2 && worker_writes_W(S, j, c_end)) {   // plain copy of W_j (see worker_writes_W)
+        double* Wg = S.Linv + static_cast<size_t>(j) * kTileElems;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) Wg[tid + kFacThreads * q4] = v[q4];
+      }
     }
     if (stamp) LVI_TRACE_AT(trow, 5);
     __syncthreads();
