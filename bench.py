@@ -574,7 +574,7 @@ def main():
         traffic = json.loads(tf.read_text()).get("band_factor_ll_kernel", {}).get("dram_bytes_per_launch")
     roofline = {"kernel": "band_factor_ll_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                "note": "latency-bound: two serial chains of ~273 block columns at ~6.5 us each (profiles/r1c_factor_trace_c2.txt); "
+                "note": "latency-bound: two serial chains of ~273 block columns at ~5.5 us each (profiles/r2z_factor_trace_c2.txt); "
                         "~9.5 GFLOP of fp64 per launch, neither HBM nor FLOP limited",
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fac_ms, "share_of_step": fac_ms / ms_total}
     # ---- the other kernels of an iteration, timed live with CUDA events around every launch (outside the timed region above): the
